@@ -1,0 +1,668 @@
+// caf.cu -- cross-ambiguity function (delay-Doppler map) on sm_100a.
+//
+// Replaces the arithmetic of the reference's Ambiguity class
+// (src/process/ambiguity/Ambiguity.cpp:11-200) behind the C ABI in include/b200dd.h.
+//
+//   K0  caf_convert / caf_prerotate   complex128 -> complex64 (+ the dopplerMiddle != 0
+//                                     pre-rotation, Ambiguity.cpp:95-102)
+//   K1  caf_range_kernel<LOG2M>       per-batch range correlation (Ambiguity.cpp:106-149):
+//                                     one CTA per batch, segmented power-of-two FFT
+//                                     cross-spectrum accumulated in registers, ONE inverse
+//                                     FFT per batch, nDelayBins lags written
+//   K2  caf_doppler_kernel<LOG2M>     DFT of odd length nDopplerBins down every delay
+//                                     column (Ambiguity.cpp:152-169) as a Bluestein chirp-z
+//                                     in shared memory, fftshift folded into the store
+//
+// Algebra of K1.  The reference zero-pads batch i of x and y to nfft >= 2 nCorr - 1, so
+// z = IFFT(FFT(y_i) conj(FFT(x_i))) is the LINEAR cross-correlation of the two batches
+// with everything outside the batch equal to zero:
+//     R[i][j] = sum_n y_i[n + l] conj(x_i[n]),  l = delayMin + j.
+// We split n into segments of L samples.  For segment s (n0 = s L) let
+//     xp[m] = x_i[n0 + m] (m < len), 0 otherwise                       (M points)
+//     yw[m] = y_i[n0 + delayMin + m] when that index is inside [0, nCorr), else 0
+// then for 0 <= j < nDel <= M - L + 1 the length-M CIRCULAR correlation
+//     c_s[j] = sum_m yw[m + j] conj(xp[m])
+// has no wrap-around and sum_s c_s[j] = R[i][j].  Because the inverse FFT is linear the
+// sum over segments is taken in the frequency domain (in registers) and only one
+// inverse transform per batch is executed.  The result is independent of nfft /
+// roundHamming (only Ambiguity::get_nfft() exposes those).
+#include "common.cuh"
+#include "fft_core.cuh"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace b2;
+
+namespace {
+
+// ------------------------------------------------------------------ host geometry
+
+// Ambiguity.cpp:16-66, with the reference's integer widths (uint16_t members).
+struct HostGeom {
+  int32_t delayMin, delayMax, dopplerMin, dopplerMax;
+  uint32_t fs, n;
+  bool roundHamming;
+  uint32_t nDel, nDop, nCorr, nfft;
+  double dopplerMiddle, cpi;
+  std::vector<int32_t> delay;
+  std::vector<double> doppler;
+};
+
+uint32_t next_hamming_host(uint32_t value) {
+  // first 5-smooth number strictly greater than value (HammingNumber.cpp:38-48)
+  uint64_t best = 0;
+  const uint64_t lim = 2ull * ((uint64_t)value + 1ull);
+  for (uint64_t p2 = 1; p2 <= lim; p2 *= 2)
+    for (uint64_t p3 = p2; p3 <= lim; p3 *= 3)
+      for (uint64_t p5 = p3; p5 <= lim; p5 *= 5)
+        if (p5 > value && (best == 0 || p5 < best)) best = p5;
+  return (uint32_t)best;
+}
+
+void compute_geometry(const b200dd_caf_params &p, HostGeom &g) {
+  g.delayMin = p.delay_min;
+  g.delayMax = p.delay_max;
+  g.dopplerMin = p.doppler_min;
+  g.dopplerMax = p.doppler_max;
+  g.fs = p.fs;
+  g.n = p.n_samples;
+  g.roundHamming = p.round_hamming != 0;
+  g.nDel = (uint16_t)(p.delay_max - p.delay_min + 1);           // Ambiguity.cpp:22
+  g.dopplerMiddle = (p.doppler_min + p.doppler_max) / 2.0;       // :23
+  double res = 1.0 / ((double)p.n_samples / (double)p.fs);       // :27
+  uint32_t count = 1;
+  int i = 1;
+  while (g.dopplerMiddle + (i * res) <= p.doppler_max) {          // :30-35
+    count += 2;
+    i++;
+  }
+  g.nDop = (uint16_t)count;                                      // :36 (uint16_t member)
+  g.nCorr = g.nDop ? (uint16_t)(p.n_samples / g.nDop) : 0;       // :39
+  g.cpi = ((double)g.nCorr * g.nDop) / p.fs;                     // :40
+  res = 1.0 / g.cpi;                                             // :43
+  g.delay.resize(g.nDel);
+  for (uint32_t j = 0; j < g.nDel; j++) g.delay[j] = p.delay_min + (int32_t)j;  // :49-50
+  g.doppler.assign(g.nDop, 0.0);
+  if (g.nDop) {
+    const int half = (int)(g.nDop - 1) / 2;                      // :52-59 push_front/push_back pairs
+    g.doppler[half] = g.dopplerMiddle;
+    for (int k = 1; k <= half; k++) {
+      g.doppler[half + k] = g.dopplerMiddle + (k * res);
+      g.doppler[half - k] = g.dopplerMiddle - (k * res);
+    }
+  }
+  g.nfft = 2 * g.nCorr - 1;                                      // :62
+  if (g.roundHamming) g.nfft = next_hamming_host(g.nfft);        // :63-65
+}
+
+// ------------------------------------------------------------------ device kernels
+
+struct RangeArgs {
+  const float2 *x;
+  const float2 *y;
+  float2 *R;         // [nDop][nDel]
+  const float2 *tw;  // exp(-2 pi i j / M)
+  int nCorr, nDel, lagMin, nSeg, L;
+};
+
+// resident CTAs per SM the register allocator must leave room for (<= 128 regs/thread)
+template <int LOG2M> constexpr int range_min_ctas() {
+  return Plan<LOG2M>::NT >= 512 ? 1 : (512 / Plan<LOG2M>::NT > 16 ? 16 : 512 / Plan<LOG2M>::NT);
+}
+
+template <int LOG2M>
+__global__ void __launch_bounds__(Plan<LOG2M>::NT, range_min_ctas<LOG2M>()) caf_range_kernel(RangeArgs a) {
+  using P = Plan<LOG2M>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *A = reinterpret_cast<float2 *>(smem_raw);
+  float2 *B = A + P::MP;
+  const int tid = threadIdx.x;
+  const int batch = blockIdx.x;
+  const float2 *__restrict__ xb = a.x + (size_t)batch * a.nCorr;
+  const float2 *__restrict__ yb = a.y + (size_t)batch * a.nCorr;
+  const float2 zero = make_float2(0.f, 0.f);
+
+  float2 Z[16];
+#pragma unroll
+  for (int r = 0; r < 16; r++) Z[r] = zero;
+
+  for (int seg = 0; seg < a.nSeg; seg++) {
+    const int n0 = seg * a.L;
+    const int len = min(a.L, a.nCorr - n0);
+    const int ylen = len + a.nDel - 1;   // window entries that can reach a wanted lag
+    const int yoff = n0 + a.lagMin;
+    auto ldx = [&](int m) { return m < len ? __ldg(xb + n0 + m) : zero; };
+    auto ldy = [&](int m) {
+      const int j = yoff + m;
+      return (m < ylen && j >= 0 && j < a.nCorr) ? __ldg(yb + j) : zero;
+    };
+    auto stA = [&](int i, float2 v) { A[pad(i)] = v; };
+    auto stB = [&](int i, float2 v) { B[pad(i)] = v; };
+    if (seg > 0) __syncthreads();  // previous segment's last pass has finished reading A/B
+    if constexpr (P::R0 == 16) {
+      fft_butterfly<float, 16, -1, LOG2M>(tid, P::log2S(0), a.tw, ldx, stA);
+      fft_butterfly<float, 16, -1, LOG2M>(tid, P::log2S(0), a.tw, ldy, stB);
+    } else {
+#pragma unroll 1
+      for (int b = tid; b < P::M / P::R0; b += P::NT) {
+        fft_butterfly<float, P::R0, -1, LOG2M>(b, P::log2S(0), a.tw, ldx, stA);
+        fft_butterfly<float, P::R0, -1, LOG2M>(b, P::log2S(0), a.tw, ldy, stB);
+      }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int p = 1; p < P::NP - 1; p++) {
+      smem_pass<float, LOG2M, -1>(A, a.tw, p, tid);
+      smem_pass<float, LOG2M, -1>(B, a.tw, p, tid);
+      __syncthreads();
+    }
+    float2 vx[16], vy[16];
+    fwd_last_to_regs<float, LOG2M>(A, tid, vx);
+    fwd_last_to_regs<float, LOG2M>(B, tid, vy);
+#pragma unroll
+    for (int r = 0; r < 16; r++) cfmac(Z[r], vy[r], vx[r]);  // Z += Y conj(X)
+  }
+
+  __syncthreads();
+  inv_first_from_regs<float, LOG2M>(A, tid, Z);
+  __syncthreads();
+#pragma unroll 1
+  for (int p = P::NP - 2; p >= 1; p--) {
+    smem_pass<float, LOG2M, +1>(A, a.tw, p, tid);
+    __syncthreads();
+  }
+  // final inverse pass: natural-order lag index m = delay bin; keep m < nDel only
+  const float scale = 1.0f / (float)P::M;
+  float2 *__restrict__ Rrow = a.R + (size_t)batch * a.nDel;
+  auto ldA = [&](int i) { return A[pad(i)]; };
+  auto stR = [&](int m, float2 v) {
+    if (m < a.nDel) Rrow[m] = make_float2(v.x * scale, v.y * scale);
+  };
+  constexpr int S0 = 1 << P::log2S(0);
+#pragma unroll 1
+  for (int b = tid; b < P::M / P::R0; b += P::NT) {
+    if ((b & (S0 - 1)) < a.nDel) fft_butterfly<float, P::R0, +1, LOG2M>(b, P::log2S(0), a.tw, ldA, stR);
+  }
+}
+
+struct DopplerArgs {
+  const float2 *R;      // [nDop][nDel] range matrix
+  float2 *out;          // [nDop][nDel] map
+  const float2 *chirp;  // exp(-i pi k^2 / nDop), k < nDop
+  const float2 *bhat;   // FFT_M2 of the wrapped conj chirp, digit-reversed position order
+  const float2 *tw;     // exp(-2 pi i j / M2)
+  int nDop, nDel;
+};
+
+// Column j: D[m] = sum_i R[i][j] exp(-2 pi i m i / nDop)  (Ambiguity.cpp:160) via
+// Bluestein: D[m] = c[m] * sum_i (R_i c[i]) conj(c)[m - i]; out[k] = D[(k + nDop/2 + 1) % nDop].
+template <int LOG2M>
+__global__ void __launch_bounds__(Plan<LOG2M>::NT) caf_doppler_kernel(DopplerArgs a) {
+  using P = Plan<LOG2M>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *A = reinterpret_cast<float2 *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int col = blockIdx.x;
+  const float2 zero = make_float2(0.f, 0.f);
+  auto ld0 = [&](int i) { return i < a.nDop ? cmul(__ldg(a.R + (size_t)i * a.nDel + col), __ldg(a.chirp + i)) : zero; };
+  auto stA = [&](int i, float2 v) { A[pad(i)] = v; };
+#pragma unroll 1
+  for (int b = tid; b < P::M / P::R0; b += P::NT) fft_butterfly<float, P::R0, -1, LOG2M>(b, P::log2S(0), a.tw, ld0, stA);
+  __syncthreads();
+#pragma unroll 1
+  for (int p = 1; p < P::NP - 1; p++) {
+    smem_pass<float, LOG2M, -1>(A, a.tw, p, tid);
+    __syncthreads();
+  }
+  float2 v[16];
+  fwd_last_to_regs<float, LOG2M>(A, tid, v);
+#pragma unroll
+  for (int r = 0; r < 16; r++) v[r] = cmul(v[r], __ldg(a.bhat + 16 * tid + brev<16>(r)));
+  __syncthreads();
+  inv_first_from_regs<float, LOG2M>(A, tid, v);
+  __syncthreads();
+#pragma unroll 1
+  for (int p = P::NP - 2; p >= 1; p--) {
+    smem_pass<float, LOG2M, +1>(A, a.tw, p, tid);
+    __syncthreads();
+  }
+  const float scale = 1.0f / (float)P::M;
+  const int shift = a.nDop / 2 + 1;
+  auto ldA = [&](int i) { return A[pad(i)]; };
+  auto stO = [&](int m, float2 val) {
+    if (m < a.nDop) {
+      float2 d = cmul(val, __ldg(a.chirp + m));
+      int k = m - shift;
+      if (k < 0) k += a.nDop;
+      a.out[(size_t)k * a.nDel + col] = make_float2(d.x * scale, d.y * scale);
+    }
+  };
+  constexpr int S0 = 1 << P::log2S(0);
+#pragma unroll 1
+  for (int b = tid; b < P::M / P::R0; b += P::NT) {
+    if ((b & (S0 - 1)) < a.nDop) fft_butterfly<float, P::R0, +1, LOG2M>(b, P::log2S(0), a.tw, ldA, stO);
+  }
+}
+
+// natural-order input -> digit-reversed POSITION order output (plan-creation helper)
+template <int LOG2M>
+__global__ void __launch_bounds__(Plan<LOG2M>::NT) fft_forward_kernel(const float2 *in, float2 *out, const float2 *tw) {
+  using P = Plan<LOG2M>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *A = reinterpret_cast<float2 *>(smem_raw);
+  const int tid = threadIdx.x;
+  auto ld0 = [&](int i) { return in[i]; };
+  auto stA = [&](int i, float2 v) { A[pad(i)] = v; };
+#pragma unroll 1
+  for (int b = tid; b < P::M / P::R0; b += P::NT) fft_butterfly<float, P::R0, -1, LOG2M>(b, P::log2S(0), tw, ld0, stA);
+  __syncthreads();
+#pragma unroll 1
+  for (int p = 1; p < P::NP - 1; p++) {
+    smem_pass<float, LOG2M, -1>(A, tw, p, tid);
+    __syncthreads();
+  }
+  float2 v[16];
+  fwd_last_to_regs<float, LOG2M>(A, tid, v);
+#pragma unroll
+  for (int r = 0; r < 16; r++) out[16 * tid + brev<16>(r)] = v[r];
+}
+
+// complex128 -> complex64, optional pre-rotation by exp(+j 2 pi mid i / fs) (Ambiguity.cpp:95-102)
+__global__ void caf_convert_kernel(const double2 *__restrict__ in, float2 *__restrict__ out, uint32_t n, double mid,
+                                   double fs) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double2 v = in[i];
+    if (mid != 0.0) {
+      // same association as the reference: ((2.0 * M_PI) * mid) * (i / fs)
+      double th = ((2.0 * 3.14159265358979323846) * mid) * ((double)i / fs);
+      double s, c;
+      sincos(th, &s, &c);
+      double2 r;
+      r.x = v.x * c - v.y * s;
+      r.y = v.x * s + v.y * c;
+      v = r;
+    }
+    out[i] = make_float2((float)v.x, (float)v.y);
+  }
+}
+
+__global__ void caf_prerotate_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, uint32_t n, double mid,
+                                     double fs) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float2 f = in[i];
+    double th = ((2.0 * 3.14159265358979323846) * mid) * ((double)i / fs);
+    double s, c;
+    sincos(th, &s, &c);
+    out[i] = make_float2((float)((double)f.x * c - (double)f.y * s), (float)((double)f.x * s + (double)f.y * c));
+  }
+}
+
+__global__ void caf_widen_kernel(const float2 *__restrict__ in, double2 *__restrict__ out, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float2 f = in[i];
+    out[i] = make_double2((double)f.x, (double)f.y);
+  }
+}
+
+// ------------------------------------------------------------------ launch dispatch
+
+template <int LOG2M> int launch_range(const RangeArgs &a, int nDop, cudaStream_t st) {
+  using P = Plan<LOG2M>;
+  const size_t smem = 2 * (size_t)P::MP * sizeof(float2);
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    B2_CUDA(cudaFuncSetAttribute(caf_range_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done[dev & 63] = true;
+  }
+  caf_range_kernel<LOG2M><<<nDop, P::NT, smem, st>>>(a);
+  B2_LAUNCH_CHECK();
+  return B200DD_OK;
+}
+
+template <int LOG2M> int launch_doppler(const DopplerArgs &a, cudaStream_t st) {
+  using P = Plan<LOG2M>;
+  const size_t smem = (size_t)P::MP * sizeof(float2);
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    B2_CUDA(cudaFuncSetAttribute(caf_doppler_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done[dev & 63] = true;
+  }
+  caf_doppler_kernel<LOG2M><<<a.nDel, P::NT, smem, st>>>(a);
+  B2_LAUNCH_CHECK();
+  return B200DD_OK;
+}
+
+template <int LOG2M> int launch_fft_forward(const float2 *in, float2 *out, const float2 *tw, cudaStream_t st) {
+  using P = Plan<LOG2M>;
+  const size_t smem = (size_t)P::MP * sizeof(float2);
+  B2_CUDA(cudaFuncSetAttribute(fft_forward_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fft_forward_kernel<LOG2M><<<1, P::NT, smem, st>>>(in, out, tw);
+  B2_LAUNCH_CHECK();
+  return B200DD_OK;
+}
+
+int dispatch_range(int log2m, const RangeArgs &a, int nDop, cudaStream_t st) {
+  switch (log2m) {
+    case 8: return launch_range<8>(a, nDop, st);
+    case 9: return launch_range<9>(a, nDop, st);
+    case 10: return launch_range<10>(a, nDop, st);
+    case 11: return launch_range<11>(a, nDop, st);
+    case 12: return launch_range<12>(a, nDop, st);
+    case 13: return launch_range<13>(a, nDop, st);
+  }
+  return geom_fail("range FFT length out of range");
+}
+
+int dispatch_doppler(int log2m, const DopplerArgs &a, cudaStream_t st) {
+  switch (log2m) {
+    case 8: return launch_doppler<8>(a, st);
+    case 9: return launch_doppler<9>(a, st);
+    case 10: return launch_doppler<10>(a, st);
+    case 11: return launch_doppler<11>(a, st);
+    case 12: return launch_doppler<12>(a, st);
+    case 13: return launch_doppler<13>(a, st);
+    case 14: return launch_doppler<14>(a, st);
+  }
+  return geom_fail("Doppler FFT length out of range");
+}
+
+int dispatch_fft_forward(int log2m, const float2 *in, float2 *out, const float2 *tw, cudaStream_t st) {
+  switch (log2m) {
+    case 8: return launch_fft_forward<8>(in, out, tw, st);
+    case 9: return launch_fft_forward<9>(in, out, tw, st);
+    case 10: return launch_fft_forward<10>(in, out, tw, st);
+    case 11: return launch_fft_forward<11>(in, out, tw, st);
+    case 12: return launch_fft_forward<12>(in, out, tw, st);
+    case 13: return launch_fft_forward<13>(in, out, tw, st);
+    case 14: return launch_fft_forward<14>(in, out, tw, st);
+  }
+  return geom_fail("FFT length out of range");
+}
+
+std::vector<float2> twiddle_table_f32(int M) {
+  std::vector<float2> t(M);
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  for (int j = 0; j < M; j++) {
+    long double ang = two_pi * (long double)j / (long double)M;
+    t[j] = make_float2((float)cosl(ang), (float)(-sinl(ang)));
+  }
+  return t;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ handle
+
+struct b200dd_caf {
+  b200dd_caf_params params;
+  HostGeom g;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  // range stage plan
+  int log2m = 12, nSeg = 1, L = 0;
+  // doppler stage plan
+  int log2m2 = 10;
+  float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_chirp = nullptr, *d_bhat = nullptr;
+  float2 *d_R = nullptr, *d_map = nullptr;
+  float2 *d_xrot = nullptr;                      // device path, dopplerMiddle != 0
+  double2 *d_xd = nullptr, *d_yd = nullptr;      // host path staging
+  float2 *d_xf = nullptr, *d_yf = nullptr;
+  double2 *d_mapd = nullptr;
+  uint32_t n_stage = 0;
+};
+
+namespace {
+
+// pick M = 2^log2m for the range stage: minimise (2 nSeg + 1) M log2 M
+void plan_range(b200dd_caf *h) {
+  const int nCorr = (int)h->g.nCorr, nDel = (int)h->g.nDel;
+  int forced = 0;
+  if (const char *e = getenv("B200DD_CAF_LOG2M")) forced = atoi(e);
+  double best = 1e300;
+  int best_l = 0;
+  for (int l = 8; l <= 13; l++) {
+    const int M = 1 << l;
+    const int Lmax = M - nDel + 1;
+    if (Lmax < 1) continue;
+    if (Lmax < M / 8 && l < 13) continue;  // hopeless overlap ratio; prefer a longer FFT
+    const int nSeg = (nCorr + Lmax - 1) / Lmax;
+    double cost = (2.0 * nSeg + 1.0) * (double)M * l;
+    if (l == 13) cost *= 1.15;  // 512 threads + 139 KB smem: one CTA per SM
+    if (l <= 9) cost *= 1.25;   // tiny CTAs
+    if (forced == l) cost = -1.0;
+    if (cost < best) { best = cost; best_l = l; }
+  }
+  h->log2m = best_l;
+  if (best_l) {
+    const int M = 1 << best_l;
+    const int Lmax = M - nDel + 1;
+    h->nSeg = (nCorr + Lmax - 1) / Lmax;
+    if (h->nSeg < 1) h->nSeg = 1;
+    h->L = (nCorr + h->nSeg - 1) / h->nSeg;
+    h->nSeg = (nCorr + h->L - 1) / h->L;
+  }
+}
+
+int caf_setup_device(b200dd_caf *h) {
+  const HostGeom &g = h->g;
+  B2_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  const int M1 = 1 << h->log2m, M2 = 1 << h->log2m2;
+  auto tw1 = twiddle_table_f32(M1), tw2 = twiddle_table_f32(M2);
+  B2_CUDA(cudaMalloc(&h->d_tw1, sizeof(float2) * M1));
+  B2_CUDA(cudaMalloc(&h->d_tw2, sizeof(float2) * M2));
+  B2_CUDA(cudaMemcpy(h->d_tw1, tw1.data(), sizeof(float2) * M1, cudaMemcpyHostToDevice));
+  B2_CUDA(cudaMemcpy(h->d_tw2, tw2.data(), sizeof(float2) * M2, cudaMemcpyHostToDevice));
+  // Bluestein chirp c[k] = exp(-i pi k^2 / n), k^2 reduced mod 2n exactly
+  const int64_t n = g.nDop;
+  std::vector<float2> chirp(n), bw(M2, make_float2(0.f, 0.f));
+  const long double pi = 3.141592653589793238462643383279502884L;
+  for (int64_t k = 0; k < n; k++) {
+    const int64_t k2 = (k * k) % (2 * n);
+    const long double ang = pi * (long double)k2 / (long double)n;
+    const float c = (float)cosl(ang), s = (float)sinl(ang);
+    chirp[k] = make_float2(c, -s);
+    bw[k] = make_float2(c, s);  // conj(chirp)
+    if (k) bw[M2 - k] = make_float2(c, s);
+  }
+  B2_CUDA(cudaMalloc(&h->d_chirp, sizeof(float2) * n));
+  B2_CUDA(cudaMemcpy(h->d_chirp, chirp.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+  float2 *d_bw = nullptr;
+  B2_CUDA(cudaMalloc(&d_bw, sizeof(float2) * M2));
+  B2_CUDA(cudaMalloc(&h->d_bhat, sizeof(float2) * M2));
+  B2_CUDA(cudaMemcpy(d_bw, bw.data(), sizeof(float2) * M2, cudaMemcpyHostToDevice));
+  int rc = dispatch_fft_forward(h->log2m2, d_bw, h->d_bhat, h->d_tw2, h->stream);
+  if (rc != B200DD_OK) { cudaFree(d_bw); return rc; }
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(d_bw);
+  B2_CUDA(cudaMalloc(&h->d_R, sizeof(float2) * (size_t)g.nDop * g.nDel));
+  B2_CUDA(cudaMalloc(&h->d_map, sizeof(float2) * (size_t)g.nDop * g.nDel));
+  return B200DD_OK;
+}
+
+int caf_run_device(b200dd_caf *h, const float2 *d_x, const float2 *d_y, float2 *d_map, cudaStream_t st) {
+  const HostGeom &g = h->g;
+  RangeArgs ra;
+  ra.x = d_x;
+  ra.y = d_y;
+  ra.R = h->d_R;
+  ra.tw = h->d_tw1;
+  ra.nCorr = (int)g.nCorr;
+  ra.nDel = (int)g.nDel;
+  ra.lagMin = g.delayMin;
+  ra.nSeg = h->nSeg;
+  ra.L = h->L;
+  int rc = dispatch_range(h->log2m, ra, (int)g.nDop, st);
+  if (rc != B200DD_OK) return rc;
+  DopplerArgs da;
+  da.R = h->d_R;
+  da.out = d_map;
+  da.chirp = h->d_chirp;
+  da.bhat = h->d_bhat;
+  da.tw = h->d_tw2;
+  da.nDop = (int)g.nDop;
+  da.nDel = (int)g.nDel;
+  return dispatch_doppler(h->log2m2, da, st);
+}
+
+inline int grid_for(uint32_t n) {
+  int b = (int)((n + 255u) / 256u);
+  return b > 148 * 8 ? 148 * 8 : (b < 1 ? 1 : b);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+uint32_t b200dd_next_hamming(uint32_t value) { return next_hamming_host(value); }
+
+int b200dd_caf_create(const b200dd_caf_params *params, b200dd_caf **out) {
+  if (!params || !out) return arg_fail("b200dd_caf_create: null argument");
+  *out = nullptr;
+  if (params->fs == 0 || params->n_samples == 0) return arg_fail("b200dd_caf_create: fs and n_samples must be > 0");
+  if (params->delay_max < params->delay_min) return geom_fail("b200dd_caf_create: delay_max < delay_min");
+  b200dd_caf *h = new (std::nothrow) b200dd_caf();
+  if (!h) return arg_fail("b200dd_caf_create: out of host memory");
+  h->params = *params;
+  compute_geometry(*params, h->g);
+  const HostGeom &g = h->g;
+  auto fail = [&](int rc) { b200dd_caf_destroy(h); return rc; };
+  if (g.nDop == 0 || g.nCorr == 0 || g.nDel == 0) return fail(geom_fail("b200dd_caf_create: empty geometry"));
+  if ((uint64_t)g.nDop * g.nCorr > params->n_samples)
+    return fail(geom_fail("b200dd_caf_create: nDopplerBins overflowed uint16_t in the reference formula"));
+  // the reference only reads defined memory for -nDel <= delayMin <= 1 (SURVEY.md s8 footnote c);
+  // we compute lag delayMin + j directly and accept any window that fits the FFT plan.
+  if (g.nDop > 8192) return fail(geom_fail("b200dd_caf_create: more than 8192 Doppler bins unsupported"));
+  plan_range(h);
+  if (h->log2m == 0) return fail(geom_fail("b200dd_caf_create: nDelayBins too large for the range FFT (max ~7168)"));
+  int l2 = 8;
+  while ((1 << l2) < 2 * (int)g.nDop - 1) l2++;
+  h->log2m2 = l2;
+  int dev = params->device;
+  if (dev < 0) {
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaGetDevice", __FILE__, __LINE__));
+  }
+  h->device = dev;
+  DeviceGuard guard(dev);
+  if (!guard.ok) return fail(cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__));
+  int rc = caf_setup_device(h);
+  if (rc != B200DD_OK) return fail(rc);
+  *out = h;
+  return B200DD_OK;
+}
+
+void b200dd_caf_destroy(b200dd_caf *h) {
+  if (!h) return;
+  {
+    DeviceGuard guard(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_dev(h->d_tw1);
+    free_dev(h->d_tw2);
+    free_dev(h->d_chirp);
+    free_dev(h->d_bhat);
+    free_dev(h->d_R);
+    free_dev(h->d_map);
+    free_dev(h->d_xrot);
+    free_dev(h->d_xd);
+    free_dev(h->d_yd);
+    free_dev(h->d_xf);
+    free_dev(h->d_yf);
+    free_dev(h->d_mapd);
+    if (h->stream) cudaStreamDestroy(h->stream);
+  }
+  delete h;
+}
+
+int b200dd_caf_get_geometry(const b200dd_caf *h, b200dd_caf_geometry *out) {
+  if (!h || !out) return arg_fail("b200dd_caf_get_geometry: null argument");
+  const HostGeom &g = h->g;
+  out->n_delay_bins = g.nDel;
+  out->n_doppler_bins = g.nDop;
+  out->n_corr = g.nCorr;
+  out->nfft = g.nfft;
+  out->n_used = g.nDop * g.nCorr;
+  out->cpi = g.cpi;
+  out->doppler_middle = g.dopplerMiddle;
+  out->range_fft_len = 1u << h->log2m;
+  out->range_segments = (uint32_t)h->nSeg;
+  out->range_hop = (uint32_t)h->L;
+  out->doppler_fft_len = 1u << h->log2m2;
+  return B200DD_OK;
+}
+
+int b200dd_caf_get_axes(const b200dd_caf *h, int32_t *delay, double *doppler) {
+  if (!h) return arg_fail("b200dd_caf_get_axes: null handle");
+  if (delay) memcpy(delay, h->g.delay.data(), sizeof(int32_t) * h->g.nDel);
+  if (doppler) memcpy(doppler, h->g.doppler.data(), sizeof(double) * h->g.nDop);
+  return B200DD_OK;
+}
+
+int b200dd_caf_process_device(b200dd_caf *h, const void *d_x, const void *d_y, uint32_t n, void *d_map, void *stream) {
+  if (!h || !d_x || !d_y) return arg_fail("b200dd_caf_process_device: null argument");
+  const uint32_t n_used = h->g.nDop * h->g.nCorr;
+  if (n < n_used) return arg_fail("b200dd_caf_process_device: fewer samples than nDopplerBins * nCorr");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const float2 *x = (const float2 *)d_x;
+  if (h->g.dopplerMiddle != 0.0) {
+    if (!h->d_xrot) B2_CUDA(cudaMalloc(&h->d_xrot, sizeof(float2) * n_used));
+    caf_prerotate_kernel<<<grid_for(n_used), 256, 0, st>>>(x, h->d_xrot, n_used, h->g.dopplerMiddle, (double)h->g.fs);
+    B2_LAUNCH_CHECK();
+    x = h->d_xrot;
+  }
+  return caf_run_device(h, x, (const float2 *)d_y, d_map ? (float2 *)d_map : h->d_map, st);
+}
+
+int b200dd_caf_process_host(b200dd_caf *h, const double *x, const double *y, uint32_t n, double *map_out) {
+  if (!h || !x || !y || !map_out) return arg_fail("b200dd_caf_process_host: null argument");
+  const HostGeom &g = h->g;
+  const uint32_t n_used = g.nDop * g.nCorr;
+  if (n < n_used) return arg_fail("b200dd_caf_process_host: fewer samples than nDopplerBins * nCorr");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = h->stream;
+  if (h->n_stage < n_used) {
+    free_dev(h->d_xd); free_dev(h->d_yd); free_dev(h->d_xf); free_dev(h->d_yf);
+    B2_CUDA(cudaMalloc(&h->d_xd, sizeof(double2) * n_used));
+    B2_CUDA(cudaMalloc(&h->d_yd, sizeof(double2) * n_used));
+    B2_CUDA(cudaMalloc(&h->d_xf, sizeof(float2) * n_used));
+    B2_CUDA(cudaMalloc(&h->d_yf, sizeof(float2) * n_used));
+    h->n_stage = n_used;
+  }
+  const size_t cells = (size_t)g.nDop * g.nDel;
+  if (!h->d_mapd) B2_CUDA(cudaMalloc(&h->d_mapd, sizeof(double2) * cells));
+  B2_CUDA(cudaMemcpyAsync(h->d_xd, x, sizeof(double2) * n_used, cudaMemcpyHostToDevice, st));
+  B2_CUDA(cudaMemcpyAsync(h->d_yd, y, sizeof(double2) * n_used, cudaMemcpyHostToDevice, st));
+  caf_convert_kernel<<<grid_for(n_used), 256, 0, st>>>(h->d_xd, h->d_xf, n_used, g.dopplerMiddle, (double)g.fs);
+  B2_LAUNCH_CHECK();
+  caf_convert_kernel<<<grid_for(n_used), 256, 0, st>>>(h->d_yd, h->d_yf, n_used, 0.0, (double)g.fs);
+  B2_LAUNCH_CHECK();
+  int rc = caf_run_device(h, h->d_xf, h->d_yf, h->d_map, st);
+  if (rc != B200DD_OK) return rc;
+  caf_widen_kernel<<<grid_for((uint32_t)cells), 256, 0, st>>>(h->d_map, h->d_mapd, (uint32_t)cells);
+  B2_LAUNCH_CHECK();
+  B2_CUDA(cudaMemcpyAsync(map_out, h->d_mapd, sizeof(double2) * cells, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  return B200DD_OK;
+}
+
+int b200dd_caf_debug_range_matrix(b200dd_caf *h, float *out) {
+  if (!h || !out) return arg_fail("b200dd_caf_debug_range_matrix: null argument");
+  DeviceGuard guard(h->device);
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  B2_CUDA(cudaMemcpy(out, h->d_R, sizeof(float2) * (size_t)h->g.nDop * h->g.nDel, cudaMemcpyDeviceToHost));
+  return B200DD_OK;
+}
+
+void *b200dd_caf_device_map(b200dd_caf *h) { return h ? (void *)h->d_map : nullptr; }
+void *b200dd_caf_stream(b200dd_caf *h) { return h ? (void *)h->stream : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,216 @@
+/* b200dd.h -- C ABI of the B200-native delay-Doppler processor (libb200dd.so).
+ *
+ * This is the drop-in boundary for blah2's hot path: every entry point replaces the
+ * arithmetic behind one public method of the reference's process classes, takes only
+ * plain C types (pointers + sizes, no CUDA / torch types in signatures; a stream is an
+ * opaque void* that may be NULL) and returns an integer status.  The C++ classes in
+ * blah2_b200/dropin/ (same names, constructors and method signatures as the reference)
+ * and the Python binding blah2_b200/capi.py are thin callers of this ABI.
+ *
+ * Reference interface each group replaces (paths relative to the blah2 repository):
+ *   b200dd_caf_*     Ambiguity::Ambiguity / Ambiguity::process / getters
+ *                    src/process/ambiguity/Ambiguity.h:34-58, Ambiguity.cpp:11-200
+ *   b200dd_wh_*      WienerHopf::WienerHopf / WienerHopf::process
+ *                    src/process/clutter/WienerHopf.h:68-78, WienerHopf.cpp:7-163
+ *   b200dd_det_*     CfarDetector1D::process, Centroid::process, Interpolate::process,
+ *                    Map::set_metrics
+ *                    src/process/detection/CfarDetector1D.h:46-55, Centroid.h:35-44,
+ *                    Interpolate.h:36-45, src/data/Map.cpp:188-206
+ *   b200dd_next_hamming   next_hamming, src/process/meta/HammingNumber.h:36
+ *
+ * Data conventions
+ *   host IQ      interleaved complex128 (re, im doubles) -- what IqData holds
+ *                (src/data/IqData.h:26).
+ *   device IQ    interleaved complex64 (float2).  Every capture format of the reference
+ *                (int16 RSPduo, fc32 USRP, int8 HackRF / Kraken) is exactly representable.
+ *   map          row-major [nDopplerBins][nDelayBins] complex, row k <-> doppler[k],
+ *                column j <-> delay[j]: the layout of Map<complex<double>>::data
+ *                (src/data/Map.h:30); complex128 on the host, complex64 on the device.
+ *   detections   three parallel double arrays delay (bins) / doppler (Hz) / snr (dB)
+ *                (src/data/Detection.h:17-24), in the reference's emission order.
+ *
+ * Threading: a handle owns one CUDA stream and scratch buffers and is NOT re-entrant
+ * (the reference's objects are not either; they are called from one thread,
+ * src/blah2.cpp:245).  Different handles may be used from different threads.
+ *
+ * There is no CPU fallback: every *_process* entry point runs CUDA kernels for sm_100a
+ * and fails with B200DD_ERR_CUDA when no usable device is present.
+ */
+#ifndef B200DD_H
+#define B200DD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200DD_API __attribute__((visibility("default")))
+#else
+#define B200DD_API
+#endif
+
+#define B200DD_OK 0
+#define B200DD_ERR_ARG 1         /* null pointer / size mismatch */
+#define B200DD_ERR_GEOMETRY 2    /* geometry outside the supported range (see DESIGN.md "limits") */
+#define B200DD_ERR_CUDA 3        /* CUDA runtime error; b200dd_last_error() has the text */
+#define B200DD_ERR_CAPACITY 4    /* output capacity too small (detections) */
+#define B200DD_FILTER_FAILED 10  /* WienerHopf: matrix not positive definite -> y left untouched
+                                    (reference returns false, WienerHopf.cpp:111-122) */
+
+/* Text of the last error raised on the calling thread ("" if none). */
+B200DD_API const char *b200dd_last_error(void);
+
+/* Library / device probe: returns number of CUDA devices (0 when none), fills optional name. */
+B200DD_API int b200dd_device_count(void);
+B200DD_API int b200dd_device_name(int device, char *buf, int buflen);
+
+/* next_hamming(value): first 5-smooth number strictly greater than value
+ * (src/process/meta/HammingNumber.cpp:38-48). Host arithmetic. */
+B200DD_API uint32_t b200dd_next_hamming(uint32_t value);
+
+/* ------------------------------------------------------------------ CAF / Ambiguity */
+
+typedef struct b200dd_caf b200dd_caf;
+
+typedef struct {
+  int32_t delay_min;     /* bins  (Ambiguity.h:34 delayMin) */
+  int32_t delay_max;     /* bins */
+  int32_t doppler_min;   /* Hz */
+  int32_t doppler_max;   /* Hz */
+  uint32_t fs;           /* Hz */
+  uint32_t n_samples;    /* samples per CPI per channel */
+  int32_t round_hamming; /* only affects get_nfft(); the GPU FFT length is independent */
+  int32_t device;        /* CUDA device ordinal, -1 = current device */
+} b200dd_caf_params;
+
+typedef struct {
+  uint32_t n_delay_bins;   /* Ambiguity::get_n_delay_bins   */
+  uint32_t n_doppler_bins; /* Ambiguity::get_n_doppler_bins */
+  uint32_t n_corr;         /* Ambiguity::get_n_corr         */
+  uint32_t nfft;           /* Ambiguity::get_nfft           */
+  uint32_t n_used;         /* nDopplerBins * nCorr: samples consumed per channel (Ambiguity.cpp:105) */
+  double cpi;              /* Ambiguity::get_cpi            */
+  double doppler_middle;   /* Ambiguity::get_doppler_middle */
+  /* implementation facts (for DESIGN / bench reporting) */
+  uint32_t range_fft_len;   /* M of the segmented range FFT */
+  uint32_t range_segments;  /* segments per batch */
+  uint32_t range_hop;       /* new samples per segment */
+  uint32_t doppler_fft_len; /* Bluestein length M2 */
+} b200dd_caf_geometry;
+
+B200DD_API int b200dd_caf_create(const b200dd_caf_params *params, b200dd_caf **out);
+B200DD_API void b200dd_caf_destroy(b200dd_caf *h);
+B200DD_API int b200dd_caf_get_geometry(const b200dd_caf *h, b200dd_caf_geometry *out);
+/* Map axes as the Ambiguity constructor builds them (Ambiguity.cpp:46-59):
+ * delay[n_delay_bins] (bins), doppler[n_doppler_bins] (Hz). */
+B200DD_API int b200dd_caf_get_axes(const b200dd_caf *h, int32_t *delay, double *doppler);
+
+/* Ambiguity::process on HOST buffers: x, y = n interleaved complex128 samples each
+ * (n >= n_used; only the first n_used are consumed, like the FIFO pops at
+ * Ambiguity.cpp:108-112).  map_out = [n_doppler_bins][n_delay_bins] complex128.
+ * H2D, conversion to float2, kernels and D2H all run on the handle's stream; the call
+ * returns after the map is in map_out. */
+B200DD_API int b200dd_caf_process_host(b200dd_caf *h, const double *x, const double *y, uint32_t n, double *map_out);
+
+/* Device-resident variant: d_x, d_y = n float2 samples in device memory, d_map =
+ * [n_doppler_bins][n_delay_bins] float2 in device memory.  Asynchronous on `stream`
+ * (NULL = the handle's stream); no host synchronisation. */
+B200DD_API int b200dd_caf_process_device(b200dd_caf *h, const void *d_x, const void *d_y, uint32_t n, void *d_map,
+                              void *stream);
+
+/* Intermediate range matrix of the last process call (row i = batch i, nDelayBins lags;
+ * Ambiguity.cpp:106-149) copied to host as complex64 -- parity tests only. */
+B200DD_API int b200dd_caf_debug_range_matrix(b200dd_caf *h, float *out);
+
+/* Device pointer to the handle's last map (float2 [nDop][nDel]) for chaining detection
+ * without a host round trip; valid until the next process call on this handle. */
+B200DD_API void *b200dd_caf_device_map(b200dd_caf *h);
+/* Handle's stream (cudaStream_t as void*). */
+B200DD_API void *b200dd_caf_stream(b200dd_caf *h);
+
+/* ------------------------------------------------------------------ WienerHopf */
+
+typedef struct b200dd_wh b200dd_wh;
+
+/* WienerHopf(delayMin, delayMax, nSamples): nBins = delayMax - delayMin (no +1,
+ * WienerHopf.cpp:12). device = -1 -> current device. */
+B200DD_API int b200dd_wh_create(int32_t delay_min, int32_t delay_max, uint32_t n_samples, int32_t device, b200dd_wh **out);
+B200DD_API void b200dd_wh_destroy(b200dd_wh *h);
+
+/* WienerHopf::process on HOST buffers.  x: n_samples complex128 (read only);
+ * y: n_samples complex128, overwritten with the filtered surveillance channel.
+ * Returns B200DD_OK, or B200DD_FILTER_FAILED with y untouched. */
+B200DD_API int b200dd_wh_process_host(b200dd_wh *h, const double *x, double *y);
+
+/* Device-resident variant: d_x, d_y float2[n_samples]; d_y_out float2[n_samples] (may
+ * alias d_y).  Asynchronous; the success flag is written to the handle's device status
+ * word and, when the solve fails, d_y_out receives d_y unchanged.  Use
+ * b200dd_wh_last_status() (synchronises the stream) to read it. */
+B200DD_API int b200dd_wh_process_device(b200dd_wh *h, const void *d_x, const void *d_y, void *d_y_out, void *stream);
+B200DD_API int b200dd_wh_last_status(b200dd_wh *h);
+/* Filter weights w[nBins] / correlations a, b of the last call as complex128 -- parity tests. */
+B200DD_API int b200dd_wh_debug_weights(b200dd_wh *h, double *w, double *a, double *b);
+B200DD_API uint32_t b200dd_wh_n_bins(const b200dd_wh *h);
+B200DD_API void *b200dd_wh_stream(b200dd_wh *h);
+
+/* ------------------------------------------------------------------ detection tail */
+
+typedef struct b200dd_det b200dd_det;
+
+typedef struct {
+  double pfa;           /* CfarDetector1D(pfa, ...)          CfarDetector1D.h:46 */
+  int32_t n_guard;      /* int8_t in the reference */
+  int32_t n_train;      /* int8_t */
+  int32_t min_delay;    /* int8_t */
+  double min_doppler;
+  uint32_t n_centroid_delay;   /* Centroid(nDelay, nDoppler, resolutionDoppler)  Centroid.h:35 */
+  uint32_t n_centroid_doppler;
+  double resolution_doppler;
+  int32_t interp_delay;   /* Interpolate(doDelay, doDoppler)  Interpolate.h:36 */
+  int32_t interp_doppler;
+  int32_t device;
+} b200dd_det_params;
+
+B200DD_API int b200dd_det_create(const b200dd_det_params *params, uint32_t max_doppler_bins, uint32_t max_delay_bins,
+                      b200dd_det **out);
+B200DD_API void b200dd_det_destroy(b200dd_det *h);
+
+/* Map::set_metrics on a device map (float2 [n_dop][n_del]): metrics[0] = noisePower,
+ * metrics[1] = maxPower (Map.cpp:188-206).  Synchronises the stream. */
+B200DD_API int b200dd_det_set_metrics_device(b200dd_det *h, const void *d_map, uint32_t n_dop, uint32_t n_del, double *metrics,
+                                  void *stream);
+
+/* Stage selectors for b200dd_det_process_*: run CFAR only, CFAR+Centroid, or all three. */
+#define B200DD_DET_CFAR 1
+#define B200DD_DET_CENTROID 2
+#define B200DD_DET_INTERPOLATE 3
+
+/* CfarDetector1D -> Centroid -> Interpolate on a device map (blah2.cpp:285-287).
+ * delay[n_del] / doppler[n_dop] are the map axes (host), noise_power = Map::noisePower.
+ * Outputs (host): up to `cap` detections; *n_out = number found (may exceed cap ->
+ * B200DD_ERR_CAPACITY with the first cap filled). */
+B200DD_API int b200dd_det_process_device(b200dd_det *h, int last_stage, const void *d_map, uint32_t n_dop, uint32_t n_del,
+                              const int32_t *delay, const double *doppler, double noise_power, double *o_delay,
+                              double *o_doppler, double *o_snr, uint32_t cap, uint32_t *n_out, void *stream);
+
+/* Same on a HOST complex128 map (what the drop-in classes hold in Map::data). */
+B200DD_API int b200dd_det_process_host(b200dd_det *h, int last_stage, const double *map, uint32_t n_dop, uint32_t n_del,
+                            const int32_t *delay, const double *doppler, double noise_power, double *o_delay,
+                            double *o_doppler, double *o_snr, uint32_t cap, uint32_t *n_out);
+
+/* Centroid / Interpolate alone on a host detection list (class-level drop-ins). */
+B200DD_API int b200dd_det_centroid_host(b200dd_det *h, const double *delay, const double *doppler, const double *snr,
+                             uint32_t n, double *o_delay, double *o_doppler, double *o_snr, uint32_t cap,
+                             uint32_t *n_out);
+B200DD_API int b200dd_det_interpolate_host(b200dd_det *h, const double *delay, const double *doppler, const double *snr,
+                                uint32_t n, const double *map, uint32_t n_dop, uint32_t n_del, const int32_t *mdelay,
+                                const double *mdoppler, double noise_power, double *o_delay, double *o_doppler,
+                                double *o_snr, uint32_t cap, uint32_t *n_out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* B200DD_H */

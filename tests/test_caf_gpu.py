@@ -1,0 +1,134 @@
+"""GPU parity: CUDA cross-ambiguity function (through the C ABI) vs the oracle.
+
+Mirrors the reference's test/unit/process/ambiguity/TestAmbiguity.cpp (constructor
+known answers, Process_Simple on random IQ) and extends it with numeric pins against
+oracle/blah2_oracle.py (itself pinned to the compiled reference).  Tolerance is the
+north star's: map within 1e-5 relative (max-abs and Frobenius), written below.
+"""
+import numpy as np
+import pytest
+
+from blah2_b200.process import Ambiguity
+from blah2_b200.scene import make_scene, random_iq, Target
+from oracle import blah2_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+# (delayMin, delayMax, dopplerMin, dopplerMax, fs, n, roundHamming)
+GEOMS = [
+    (-3, 20, -50, 50, 10000, 4000, False),        # tiny, odd everything
+    (0, 31, -20, 60, 10000, 5000, True),          # asymmetric Doppler window -> pre-rotation (A2)
+    (2, 40, -30, 30, 10000, 3000, True),          # positive delayMin
+    (-10, 120, -5000, 5000, 2000000, 200000, True),   # many Doppler bins (1001), short batches
+    (-10, 300, -300, 300, 2000000, 1000000, False),   # the reference unit test geometry
+    (-10, 300, -300, 300, 2000000, 1000000, True),
+    (0, 299, -128, 128, 2000000, 2000000, True),      # BASELINE config 1/2 geometry
+    (-40, 1200, -100, 100, 2000000, 400000, True),    # wide delay window (nDel = 1241)
+]
+
+
+def _run(geom, x, y):
+    amb = Ambiguity(*geom)
+    m = amb.process(x, y)
+    return amb, m
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_geometry_matches_reference_constructor(geom):
+    amb = Ambiguity(*geom)
+    g = O.ambiguity_geometry(*geom)
+    assert amb.get_n_delay_bins() == g.nDelayBins
+    assert amb.get_n_doppler_bins() == g.nDopplerBins
+    assert amb.get_n_corr() == g.nCorr
+    assert amb.get_nfft() == g.nfft
+    assert amb.get_cpi() == g.cpi
+    assert amb.get_doppler_middle() == g.dopplerMiddle
+    assert np.array_equal(amb.delay, g.delay)
+    assert np.array_equal(amb.doppler, g.doppler)
+
+
+def test_constructor_known_answers():
+    # TestAmbiguity.cpp:73-116
+    a = Ambiguity(-10, 300, -300, 300, 2000000, 1000000)
+    assert (a.get_n_corr(), a.get_n_delay_bins(), a.get_n_doppler_bins(), a.get_nfft()) == (3322, 311, 301, 6643)
+    assert abs(a.get_cpi() - 0.5) < 0.02 and a.get_doppler_middle() == 0
+    b = Ambiguity(-10, 300, -300, 300, 2000000, 1000000, True)
+    assert b.get_nfft() == 6750
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_map_matches_oracle_random_iq(geom, relerr):
+    n = geom[5]
+    x, y = random_iq(n, seed=11)
+    amb, m = _run(geom, x, y)
+    g = O.ambiguity_geometry(*geom)
+    ref, lx, ly = O.ambiguity_process(x, y, g)
+    # range matrix first (localises a failure to K1 or K2)
+    Rref = O.range_matrix(O.ambiguity_prerotate(np.asarray(x, np.complex128), g), np.asarray(y, np.complex128), g)
+    e_r = relerr(amb.debug_range_matrix(), Rref)
+    assert e_r[0] < TOL and e_r[1] < TOL, f"range matrix {e_r}"
+    e = relerr(m.data, ref)
+    assert e[0] < TOL and e[1] < TOL, f"map {e}"
+    # Process_Simple assertions (TestAmbiguity.cpp:142-143) + metric parity within 1e-3 dB
+    noise, mx = O.set_metrics(m.data)
+    noise_ref, mx_ref = O.set_metrics(ref)
+    assert mx > 0 and noise > 0
+    assert abs(noise - noise_ref) < 1e-3 and abs(mx - mx_ref) < 1e-3
+    assert amb.get_n_samples() == g.n_used
+
+
+def test_map_matches_oracle_radar_scene(relerr):
+    geom = (0, 299, -128, 128, 2000000, 2000000, True)
+    sc = make_scene(geom[5], geom[4], seed=20260924)
+    amb, m = _run(geom, sc.x, sc.y)
+    g = O.ambiguity_geometry(*geom)
+    ref, _, _ = O.ambiguity_process(sc.x, sc.y, g)
+    e = relerr(m.data, ref)
+    assert e[0] < TOL and e[1] < TOL, f"map {e}"
+    # the targets must show up where they were put
+    k = np.unravel_index(np.argmax(np.abs(m.data[:, 20:]) * (np.abs(m.doppler) > 20)[:, None]), m.data[:, 20:].shape)
+    assert (k[1] + 20) in (37, 92, 151, 230)
+
+
+@pytest.mark.parametrize("log2m", [8, 9, 10, 11, 12, 13])
+def test_every_range_fft_length_gives_the_same_map(log2m, relerr, monkeypatch):
+    monkeypatch.setenv("B200DD_CAF_LOG2M", str(log2m))
+    geom = (-5, 60, -200, 200, 100000, 100000, True)
+    x, y = random_iq(geom[5], seed=5)
+    amb, m = _run(geom, x, y)
+    assert amb.geometry.range_fft_len == (1 << log2m)
+    g = O.ambiguity_geometry(*geom)
+    ref, _, _ = O.ambiguity_process(x, y, g)
+    e = relerr(m.data, ref)
+    assert e[0] < TOL and e[1] < TOL, f"log2m={log2m} map {e}"
+
+
+def test_linearity_and_determinism_full_size():
+    """Size-independent properties at BASELINE config-3 size (oracle too slow to run in
+    seconds): CAF(x, a*y1 + b*y2) = a CAF(x,y1) + b CAF(x,y2), and bitwise repeatability."""
+    geom = (0, 511, -256, 256, 10000000, 20000000, True)
+    amb = Ambiguity(*geom)
+    n = geom[5]
+    rng = np.random.default_rng(3)
+    x = (rng.integers(-2000, 2000, n) + 1j * rng.integers(-2000, 2000, n)).astype(np.complex128)
+    y1 = (rng.integers(-2000, 2000, n) + 1j * rng.integers(-2000, 2000, n)).astype(np.complex128)
+    y2 = np.roll(x, 100) * 0.25
+    m1 = amb.process(x, y1).data
+    m2 = amb.process(x, y2).data
+    m12 = amb.process(x, 2.0 * y1 - 3.0 * y2).data
+    lin = 2.0 * m1 - 3.0 * m2
+    assert np.max(np.abs(m12 - lin)) / np.max(np.abs(lin)) < TOL
+    again = amb.process(x, y1).data
+    assert np.array_equal(again, m1)
+    # y2 is x delayed by 100 bins: the zero-Doppler row must peak at delay bin 100
+    zero = (amb.get_n_doppler_bins() - 1) // 2
+    assert int(np.argmax(np.abs(m2[zero]))) == 100
+
+
+def test_too_few_samples_is_an_error():
+    from blah2_b200 import capi
+    amb = Ambiguity(-3, 20, -50, 50, 10000, 4000)
+    with pytest.raises(capi.B200ddError):
+        amb.process(np.zeros(100, complex), np.zeros(100, complex))

@@ -1,0 +1,45 @@
+"""Scratch timing of the device-resident CAF (CUDA events on torch's current stream)."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from blah2_b200.process import Ambiguity
+
+CFGS = {
+    "cfg1": (0, 299, -128, 128, 2000000, 2000000, True),
+    "cfg3": (0, 511, -256, 256, 10000000, 20000000, True),
+    "cfg4": (0, 511, -512, 512, 10000000, 10000000, True),
+}
+PEAK = 6584.8e9
+
+def run(name, log2m=None, iters=20, nbuf=8):
+    if log2m: os.environ["B200DD_CAF_LOG2M"] = str(log2m)
+    else: os.environ.pop("B200DD_CAF_LOG2M", None)
+    geom = CFGS[name]
+    amb = Ambiguity(*geom)
+    g = amb.geometry
+    n = geom[5]
+    nbuf = max(2, min(nbuf, int(400e6 // (16 * n)) ))
+    xs = [torch.randn(n, dtype=torch.complex64, device="cuda") for _ in range(nbuf)]
+    ys = [torch.randn(n, dtype=torch.complex64, device="cuda") for _ in range(nbuf)]
+    out = torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for i in range(3):
+        amb.process_device(xs[i % nbuf], ys[i % nbuf], out, st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        amb.process_device(xs[i % nbuf], ys[i % nbuf], out, st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    byts = 16 * g.n_used + 8 * g.n_doppler_bins * g.n_delay_bins
+    print(json.dumps(dict(cfg=name, log2m=g.range_fft_len, nseg=g.range_segments, hop=g.range_hop, m2=g.doppler_fft_len,
+                          ms=round(ms, 4), maps_per_s=round(1e3 / ms, 1), msamples_per_s=round(n / ms / 1e3, 1),
+                          gbs=round(byts / ms / 1e6, 1), frac=round(byts / (ms * 1e-3) / PEAK, 4))), flush=True)
+    amb.close()
+
+if __name__ == "__main__":
+    for name in sys.argv[1:] or ["cfg1", "cfg3"]:
+        for l in (None, 10, 11, 12, 13):
+            run(name, l)
