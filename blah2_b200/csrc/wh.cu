@@ -1,0 +1,593 @@
+// wh.cu -- Wiener-Hopf clutter canceller on sm_100a, FP64 throughout.
+//
+// Replaces the arithmetic of the reference's WienerHopf class
+// (src/process/clutter/WienerHopf.cpp:7-163) behind the C ABI in include/b200dd.h.
+//
+//   K3  wh_corr_kernel<LOG2M>    W2+W3: the first nBins lags of the CIRCULAR auto-correlation of
+//                                the shifted reference and of its cross-correlation with the
+//                                surveillance channel (WienerHopf.cpp:65-108):
+//                                    a[k] = sum_n conj(xs[(n+k) mod N]) xs[n]
+//                                    b[k] = sum_n ys[(n+k) mod N] conj(xs[n])
+//                                segmented double-precision FFT cross-spectra, accumulated per CTA
+//                                in shared memory, one inverse FFT per CTA and per correlation,
+//                                per-CTA partial sums reduced in a fixed order by K4.
+//   K4  wh_solve_kernel          W4: Hermitian Toeplitz system A w = b (the reference builds A
+//                                with arma::toeplitz and solves by Cholesky, :85-122).  Single CTA
+//                                Levinson recursion in FP64; "not positive definite" (a reflection
+//                                coefficient with |.| >= 1, equivalently a non-positive Cholesky
+//                                pivot) raises the failure flag = the reference's `return false`.
+//   K5  wh_apply_kernel<LOG2M>   W5: y'[i] = ys[i] - sum_{k<nBins, k<=i} w[k] xs[i-k]  (:125-160, a
+//                                LINEAR convolution with zero history) by overlap-save with the
+//                                spectrum of w computed once per CPI.
+//
+// Why FP64: the solve amplifies correlation error by cond(A) and the filter output is a small
+// difference of large numbers (30-60 dB of cancellation); SURVEY.md s7 "hard part 3".  Products of
+// float32 inputs are exact in FP64, so a and b match the reference's FFT-based values to ~1e-15.
+//
+// xs[i] = x[(i - delayMin) mod N] reproduces the reference's uint32 expression
+// (WienerHopf.cpp:67) exactly, including its behaviour for delayMin > 0.
+#include "common.cuh"
+#include "fft_core.cuh"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <type_traits>
+#include <vector>
+
+using namespace b2;
+
+namespace {
+
+constexpr int kSolveThreads = 512;
+constexpr int kMaxBins = 2048;
+
+__device__ __forceinline__ uint32_t xs_index(uint32_t i, int32_t delayMin, uint32_t N) {
+  if (delayMin <= 0) {
+    uint32_t t = i + (uint32_t)(-delayMin);
+    return t >= N ? t % N : t;
+  }
+  uint32_t t = i - (uint32_t)delayMin;  // wraps modulo 2^32 like the reference
+  return ((t % N) + N) % N;
+}
+
+template <class TIN> __device__ __forceinline__ double2 ld_iq(const TIN *p, uint32_t i) {
+  TIN v = p[i];
+  return make_double2((double)v.x, (double)v.y);
+}
+
+struct CorrArgs {
+  const void *x;
+  const void *y;
+  double2 *partial;   // [grid][2][nBins]
+  const double2 *tw;  // exp(-2 pi i j / M)
+  uint32_t N;
+  int32_t delayMin;
+  int nBins, L, nSegTotal, segPerCta;
+};
+
+// forward FFT of M points from a loader, result in registers (position order of fft_core.cuh)
+template <int LOG2M, class LD>
+__device__ __forceinline__ void fwd_fft_regs(double2 *A, const double2 *tw, int tid, LD ld, double2 (&v)[16]) {
+  using P = Plan<LOG2M>;
+  auto stA = [&](int i, double2 val) { A[pad(i)] = val; };
+#pragma unroll 1
+  for (int b = tid; b < P::M / P::R0; b += P::NT) fft_butterfly<double, P::R0, -1, LOG2M>(b, P::log2S(0), tw, ld, stA);
+  __syncthreads();
+#pragma unroll 1
+  for (int p = 1; p < P::NP - 1; p++) {
+    smem_pass<double, LOG2M, -1>(A, tw, p, tid);
+    __syncthreads();
+  }
+  fwd_last_to_regs<double, LOG2M>(A, tid, v);
+}
+
+// inverse FFT from registers; the final pass hands natural-order outputs to st(m, value)
+template <int LOG2M, class ST>
+__device__ __forceinline__ void inv_fft_from_regs(double2 *A, const double2 *tw, int tid, const double2 (&z)[16], int keep,
+                                                  ST st) {
+  using P = Plan<LOG2M>;
+  inv_first_from_regs<double, LOG2M>(A, tid, z);
+  __syncthreads();
+#pragma unroll 1
+  for (int p = P::NP - 2; p >= 1; p--) {
+    smem_pass<double, LOG2M, +1>(A, tw, p, tid);
+    __syncthreads();
+  }
+  auto ldA = [&](int i) { return A[pad(i)]; };
+  constexpr int S0 = 1 << P::log2S(0);
+#pragma unroll 1
+  for (int b = tid; b < P::M / P::R0; b += P::NT) {
+    if ((b & (S0 - 1)) < keep) fft_butterfly<double, P::R0, +1, LOG2M>(b, P::log2S(0), tw, ldA, st);
+  }
+}
+
+template <int LOG2M, class TIN>
+__global__ void __launch_bounds__(Plan<LOG2M>::NT, 1) wh_corr_kernel(CorrArgs a) {
+  using P = Plan<LOG2M>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *A = reinterpret_cast<double2 *>(smem_raw);
+  double2 *Za = A + P::MP;
+  double2 *Zb = Za + P::M;
+  const int tid = threadIdx.x;
+  const TIN *__restrict__ x = reinterpret_cast<const TIN *>(a.x);
+  const TIN *__restrict__ y = reinterpret_cast<const TIN *>(a.y);
+  const double2 zero = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int r = 0; r < 16; r++) {
+    Za[r * P::NT + tid] = zero;
+    Zb[r * P::NT + tid] = zero;
+  }
+  const int s0 = blockIdx.x * a.segPerCta;
+  const int s1 = min(s0 + a.segPerCta, a.nSegTotal);
+  for (int s = s0; s < s1; s++) {
+    const uint32_t n0 = (uint32_t)s * (uint32_t)a.L;
+    const int len = (int)min((uint32_t)a.L, a.N - n0);
+    const int wlen = len + a.nBins - 1;
+    auto ldxp = [&](int m) { return m < len ? ld_iq(x, xs_index(n0 + (uint32_t)m, a.delayMin, a.N)) : zero; };
+    auto ldxw = [&](int m) {
+      if (m >= wlen) return zero;
+      uint32_t i = n0 + (uint32_t)m;
+      if (i >= a.N) i -= a.N;  // circular correlation over N (WienerHopf.cpp:76-108)
+      return ld_iq(x, xs_index(i, a.delayMin, a.N));
+    };
+    auto ldyw = [&](int m) {
+      if (m >= wlen) return zero;
+      uint32_t i = n0 + (uint32_t)m;
+      if (i >= a.N) i -= a.N;
+      return ld_iq(y, i);
+    };
+    double2 vxp[16], v[16];
+    fwd_fft_regs<LOG2M>(A, a.tw, tid, ldxp, vxp);
+    __syncthreads();
+    fwd_fft_regs<LOG2M>(A, a.tw, tid, ldxw, v);
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+      double2 acc = Za[r * P::NT + tid];
+      cfmac(acc, v[r], vxp[r]);
+      Za[r * P::NT + tid] = acc;
+    }
+    __syncthreads();
+    fwd_fft_regs<LOG2M>(A, a.tw, tid, ldyw, v);
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+      double2 acc = Zb[r * P::NT + tid];
+      cfmac(acc, v[r], vxp[r]);
+      Zb[r * P::NT + tid] = acc;
+    }
+    __syncthreads();
+  }
+  const double scale = 1.0 / (double)P::M;
+  double2 *pa = a.partial + (size_t)blockIdx.x * 2 * a.nBins;
+  double2 *pb = pa + a.nBins;
+  double2 z[16];
+#pragma unroll
+  for (int r = 0; r < 16; r++) z[r] = Za[r * P::NT + tid];
+  // IFFT gives ra[k] = sum xs[n+k] conj(xs[n]);  a[k] = conj(ra[k])  (WienerHopf.cpp:82-84)
+  inv_fft_from_regs<LOG2M>(A, a.tw, tid, z, a.nBins, [&](int m, double2 val) {
+    if (m < a.nBins) pa[m] = make_double2(val.x * scale, -val.y * scale);
+  });
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 16; r++) z[r] = Zb[r * P::NT + tid];
+  inv_fft_from_regs<LOG2M>(A, a.tw, tid, z, a.nBins, [&](int m, double2 val) {
+    if (m < a.nBins) pb[m] = make_double2(val.x * scale, val.y * scale);
+  });
+}
+
+// ---------------------------------------------------------------------------------
+// K4: Levinson recursion for the Hermitian Toeplitz system A w = b,
+//     A(i,j) = a[j-i] (j >= i), conj(a[i-j]) (i > j)   (WienerHopf.cpp:85-97).
+// With t_k = conj(a[k]):  f = forward vector (T_m f = e_1), g = J conj(f) backward vector.
+//     eps_f = sum_{i<m} t_{m-i} f[i],  eps_x = sum_{i<m} t_{m-i} x[i]
+//     f' = ([f;0] - eps_f [0;g]) / (1 - |eps_f|^2),  x' = [x;0] + (b[m] - eps_x) J conj(f')
+// 1 - |eps_f|^2 <= 0  <=>  A not positive definite  <=>  the reference's chol() fails.
+// ---------------------------------------------------------------------------------
+struct SolveArgs {
+  const double2 *partial;  // [nPartial][2][nBins]
+  int nPartial, nBins;
+  double2 *a_out, *b_out, *w_out;
+  int *status;  // 0 ok, 1 failed
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(kSolveThreads, 1) wh_solve_kernel(SolveArgs s) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = s.nBins;
+  double2 *tk = reinterpret_cast<double2 *>(smem_raw);  // t_k = conj(a[k])
+  double2 *fb0 = tk + n;
+  double2 *fb1 = fb0 + n;
+  double2 *xv = fb1 + n;
+  double2 *bv = xv + n;
+  __shared__ double red[2][kSolveThreads / 32][4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kSolveThreads / 32;
+
+  // fixed-order reduction of the per-CTA partial correlations
+  for (int k = tid; k < n; k += kSolveThreads) {
+    double2 sa = make_double2(0.0, 0.0), sb = make_double2(0.0, 0.0);
+    for (int p = 0; p < s.nPartial; p++) {
+      const double2 va = s.partial[((size_t)p * 2) * n + k];
+      const double2 vb = s.partial[((size_t)p * 2 + 1) * n + k];
+      sa.x += va.x; sa.y += va.y;
+      sb.x += vb.x; sb.y += vb.y;
+    }
+    s.a_out[k] = sa;
+    s.b_out[k] = sb;
+    tk[k] = make_double2(sa.x, -sa.y);
+    bv[k] = sb;
+    fb0[k] = make_double2(0.0, 0.0);
+    fb1[k] = make_double2(0.0, 0.0);
+    xv[k] = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  const double a0 = tk[0].x;
+  bool ok = (a0 > 0.0) && isfinite(a0);
+  if (ok && tid == 0) {
+    fb0[0] = make_double2(1.0 / a0, 0.0);
+    xv[0] = make_double2(bv[0].x / a0, bv[0].y / a0);
+  }
+  __syncthreads();
+  double2 *fc = fb0, *fn = fb1;
+  for (int m = 1; m < n && ok; m++) {
+    // [A] partial dot products over own elements
+    double pfx = 0.0, pfy = 0.0, pxx = 0.0, pxy = 0.0;
+    for (int i = tid; i < m; i += kSolveThreads) {
+      const double2 t = tk[m - i];
+      const double2 f = fc[i];
+      const double2 xx = xv[i];
+      pfx += t.x * f.x - t.y * f.y;
+      pfy += t.x * f.y + t.y * f.x;
+      pxx += t.x * xx.x - t.y * xx.y;
+      pxy += t.x * xx.y + t.y * xx.x;
+    }
+    pfx = warp_sum(pfx); pfy = warp_sum(pfy); pxx = warp_sum(pxx); pxy = warp_sum(pxy);
+    if (lane == 0) {
+      red[m & 1][warp][0] = pfx; red[m & 1][warp][1] = pfy;
+      red[m & 1][warp][2] = pxx; red[m & 1][warp][3] = pxy;
+    }
+    __syncthreads();  // [B]
+    double efx = 0.0, efy = 0.0, exx = 0.0, exy = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+      efx += red[m & 1][w][0]; efy += red[m & 1][w][1];
+      exx += red[m & 1][w][2]; exy += red[m & 1][w][3];
+    }
+    const double d = 1.0 - (efx * efx + efy * efy);
+    if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }  // uniform: every thread sees the same sums
+    const double al = 1.0 / d;
+    const double2 bm = bv[m];
+    const double cx = bm.x - exx, cy = bm.y - exy;
+    // [D] update own elements i <= m
+    for (int i = tid; i <= m; i += kSolveThreads) {
+      const double2 fi = (i < m) ? fc[i] : make_double2(0.0, 0.0);
+      const double2 fmi = (i >= 1) ? fc[m - i] : make_double2(0.0, 0.0);
+      // f'[i]   = al (f[i]   - eps_f conj(f[m-i]))
+      // f'[m-i] = al (f[m-i] - eps_f conj(f[i]))
+      double2 fni, fnm;
+      fni.x = al * (fi.x - (efx * fmi.x + efy * fmi.y));
+      fni.y = al * (fi.y - (efy * fmi.x - efx * fmi.y));
+      fnm.x = al * (fmi.x - (efx * fi.x + efy * fi.y));
+      fnm.y = al * (fmi.y - (efy * fi.x - efx * fi.y));
+      fn[i] = fni;
+      // x'[i] = x[i] + c conj(f'[m-i])
+      double2 xi = (i < m) ? xv[i] : make_double2(0.0, 0.0);
+      xi.x += cx * fnm.x + cy * fnm.y;
+      xi.y += cy * fnm.x - cx * fnm.y;
+      xv[i] = xi;
+    }
+    double2 *tmp = fc; fc = fn; fn = tmp;
+    // no barrier: the next [A] reads only elements this thread wrote itself
+  }
+  __syncthreads();
+  for (int k = tid; k < n; k += kSolveThreads) s.w_out[k] = ok ? xv[k] : make_double2(0.0, 0.0);
+  if (tid == 0) *s.status = ok ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------
+// spectrum of the zero-padded weights (position order), once per CPI
+// ---------------------------------------------------------------------------------
+template <int LOG2M>
+__global__ void __launch_bounds__(Plan<LOG2M>::NT, 1) wh_wspec_kernel(const double2 *w, int nBins, double2 *what,
+                                                                        const double2 *tw) {
+  using P = Plan<LOG2M>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *A = reinterpret_cast<double2 *>(smem_raw);
+  const int tid = threadIdx.x;
+  double2 v[16];
+  fwd_fft_regs<LOG2M>(A, tw, tid, [&](int i) { return i < nBins ? w[i] : make_double2(0.0, 0.0); }, v);
+#pragma unroll
+  for (int r = 0; r < 16; r++) what[16 * tid + brev<16>(r)] = v[r];
+}
+
+struct ApplyArgs {
+  const void *x;
+  const void *y;
+  void *y_out;
+  const double2 *what;
+  const double2 *tw;
+  const int *status;
+  uint32_t N;
+  int32_t delayMin;
+  int nBins, Lout;
+};
+
+template <class TOUT> __device__ __forceinline__ void st_iq(TOUT *p, uint32_t i, double2 v);
+template <> __device__ __forceinline__ void st_iq<float2>(float2 *p, uint32_t i, double2 v) {
+  p[i] = make_float2((float)v.x, (float)v.y);
+}
+template <> __device__ __forceinline__ void st_iq<double2>(double2 *p, uint32_t i, double2 v) { p[i] = v; }
+
+// one CTA per block of Lout outputs: window of M = Lout + nBins - 1 shifted-reference samples
+template <int LOG2M, class TIN>
+__global__ void __launch_bounds__(Plan<LOG2M>::NT, 1) wh_apply_kernel(ApplyArgs a) {
+  using P = Plan<LOG2M>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *A = reinterpret_cast<double2 *>(smem_raw);
+  const int tid = threadIdx.x;
+  const TIN *__restrict__ x = reinterpret_cast<const TIN *>(a.x);
+  const TIN *__restrict__ y = reinterpret_cast<const TIN *>(a.y);
+  TIN *__restrict__ yo = reinterpret_cast<TIN *>(a.y_out);
+  const uint32_t i0 = (uint32_t)blockIdx.x * (uint32_t)a.Lout;
+  const int nOut = (int)min((uint32_t)a.Lout, a.N - i0);
+  if (*a.status != 0) {  // failed solve: surveillance channel passes through untouched
+    for (int m = tid; m < nOut; m += P::NT) st_iq<TIN>(yo, i0 + m, ld_iq(y, i0 + m));
+    return;
+  }
+  const int hist = a.nBins - 1;
+  const double2 zero = make_double2(0.0, 0.0);
+  // window element m <-> shifted-reference index i0 - hist + m (zero history before sample 0)
+  auto ldw = [&](int m) {
+    const int64_t i = (int64_t)i0 - hist + m;
+    return (i >= 0 && i < (int64_t)a.N && m < hist + nOut) ? ld_iq(x, xs_index((uint32_t)i, a.delayMin, a.N)) : zero;
+  };
+  double2 v[16];
+  fwd_fft_regs<LOG2M>(A, a.tw, tid, ldw, v);
+#pragma unroll
+  for (int r = 0; r < 16; r++) v[r] = cmul(v[r], a.what[16 * tid + brev<16>(r)]);
+  __syncthreads();
+  const double scale = 1.0 / (double)P::M;
+  // conv[m] valid for m >= hist; output i = i0 + m - hist
+  inv_fft_from_regs<LOG2M>(A, a.tw, tid, v, P::M, [&](int m, double2 val) {
+    const int o = m - hist;
+    if (o >= 0 && o < nOut) {
+      const double2 yy = ld_iq(y, i0 + o);
+      st_iq<TIN>(yo, i0 + o, make_double2(yy.x - val.x * scale, yy.y - val.y * scale));
+    }
+  });
+}
+
+std::vector<double2> twiddle_table_f64(int M) {
+  std::vector<double2> t(M);
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  for (int j = 0; j < M; j++) {
+    long double ang = two_pi * (long double)j / (long double)M;
+    t[j] = make_double2((double)cosl(ang), (double)(-sinl(ang)));
+  }
+  return t;
+}
+
+}  // namespace
+
+struct b200dd_wh {
+  int32_t delayMin = 0, delayMax = 0;
+  uint32_t N = 0;
+  int nBins = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int log2m = 12;
+  int L = 0, nSeg = 0, segPerCta = 1, gridCorr = 1;  // correlation stage
+  int Lout = 0, gridApply = 1;                       // filter stage
+  double2 *d_tw = nullptr, *d_partial = nullptr, *d_a = nullptr, *d_b = nullptr, *d_w = nullptr, *d_what = nullptr;
+  int *d_status = nullptr;
+  double2 *d_xd = nullptr, *d_yd = nullptr;  // host path staging (complex128)
+  int num_sms = 148;
+  bool attr_f32 = false, attr_f64 = false;
+};
+
+namespace {
+
+template <int LOG2M> size_t corr_smem() { return (size_t)(Plan<LOG2M>::MP + 2 * Plan<LOG2M>::M) * sizeof(double2); }
+template <int LOG2M> size_t fft_smem() { return (size_t)Plan<LOG2M>::MP * sizeof(double2); }
+
+template <int LOG2M, class TIN> int wh_launch_all(b200dd_wh *h, const void *x, const void *y, void *y_out, cudaStream_t st) {
+  using P = Plan<LOG2M>;
+  const size_t solve_smem = (size_t)5 * h->nBins * sizeof(double2);
+  bool &done = sizeof(typename std::remove_pointer<decltype(TIN::x) *>::type) == 4 ? h->attr_f32 : h->attr_f64;
+  if (!done) {
+    B2_CUDA(cudaFuncSetAttribute(wh_corr_kernel<LOG2M, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_smem<LOG2M>()));
+    B2_CUDA(cudaFuncSetAttribute(wh_apply_kernel<LOG2M, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M>()));
+    B2_CUDA(cudaFuncSetAttribute(wh_wspec_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M>()));
+    B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+    done = true;
+  }
+  CorrArgs ca;
+  ca.x = x; ca.y = y; ca.partial = h->d_partial; ca.tw = h->d_tw; ca.N = h->N; ca.delayMin = h->delayMin;
+  ca.nBins = h->nBins; ca.L = h->L; ca.nSegTotal = h->nSeg; ca.segPerCta = h->segPerCta;
+  wh_corr_kernel<LOG2M, TIN><<<h->gridCorr, P::NT, corr_smem<LOG2M>(), st>>>(ca);
+  B2_LAUNCH_CHECK();
+  SolveArgs sa;
+  sa.partial = h->d_partial; sa.nPartial = h->gridCorr; sa.nBins = h->nBins;
+  sa.a_out = h->d_a; sa.b_out = h->d_b; sa.w_out = h->d_w; sa.status = h->d_status;
+  wh_solve_kernel<<<1, kSolveThreads, solve_smem, st>>>(sa);
+  B2_LAUNCH_CHECK();
+  wh_wspec_kernel<LOG2M><<<1, P::NT, fft_smem<LOG2M>(), st>>>(h->d_w, h->nBins, h->d_what, h->d_tw);
+  B2_LAUNCH_CHECK();
+  ApplyArgs aa;
+  aa.x = x; aa.y = y; aa.y_out = y_out; aa.what = h->d_what; aa.tw = h->d_tw; aa.status = h->d_status;
+  aa.N = h->N; aa.delayMin = h->delayMin; aa.nBins = h->nBins; aa.Lout = h->Lout;
+  wh_apply_kernel<LOG2M, TIN><<<h->gridApply, P::NT, fft_smem<LOG2M>(), st>>>(aa);
+  B2_LAUNCH_CHECK();
+  return B200DD_OK;
+}
+
+template <class TIN> int wh_dispatch(b200dd_wh *h, const void *x, const void *y, void *y_out, cudaStream_t st) {
+  switch (h->log2m) {
+    case 9: return wh_launch_all<9, TIN>(h, x, y, y_out, st);
+    case 10: return wh_launch_all<10, TIN>(h, x, y, y_out, st);
+    case 11: return wh_launch_all<11, TIN>(h, x, y, y_out, st);
+    case 12: return wh_launch_all<12, TIN>(h, x, y, y_out, st);
+  }
+  return geom_fail("WienerHopf FFT length out of range");
+}
+
+void wh_plan(b200dd_wh *h) {
+  int forced = 0;
+  if (const char *e = getenv("B200DD_WH_LOG2M")) forced = atoi(e);
+  double best = 1e300;
+  int best_l = 0;
+  for (int l = 9; l <= 12; l++) {
+    const int M = 1 << l;
+    const int L = M - h->nBins + 1;
+    if (L < M / 8) continue;
+    double cost = (double)M * l / (double)L;
+    if (forced == l) cost = -1.0;
+    if (cost < best) { best = cost; best_l = l; }
+  }
+  h->log2m = best_l;
+  if (!best_l) return;
+  const int M = 1 << best_l;
+  h->L = M - h->nBins + 1;
+  h->nSeg = (int)(((uint64_t)h->N + h->L - 1) / h->L);
+  // CTAs resident at once: shared memory allows 1 (M=4096) or 2+ (smaller) per SM
+  const size_t smem = (size_t)(M + M / 16 + 2 * M) * sizeof(double2);
+  int per_sm = (int)((227 * 1024) / smem);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2) per_sm = 2;
+  int slots = h->num_sms * per_sm;
+  h->segPerCta = (h->nSeg + slots - 1) / slots;
+  if (h->segPerCta < 1) h->segPerCta = 1;
+  h->gridCorr = (h->nSeg + h->segPerCta - 1) / h->segPerCta;
+  h->Lout = h->L;
+  h->gridApply = h->nSeg;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200dd_wh_create(int32_t delay_min, int32_t delay_max, uint32_t n_samples, int32_t device, b200dd_wh **out) {
+  if (!out) return arg_fail("b200dd_wh_create: null argument");
+  *out = nullptr;
+  if (n_samples == 0) return arg_fail("b200dd_wh_create: n_samples must be > 0");
+  const int64_t nb = (int64_t)delay_max - (int64_t)delay_min;  // WienerHopf.cpp:12 (no +1)
+  if (nb < 1) return geom_fail("b200dd_wh_create: delayMax - delayMin must be >= 1");
+  if (nb > kMaxBins) return geom_fail("b200dd_wh_create: more than 2048 filter taps unsupported");
+  if ((uint64_t)nb > n_samples) return geom_fail("b200dd_wh_create: more taps than samples");
+  b200dd_wh *h = new (std::nothrow) b200dd_wh();
+  if (!h) return arg_fail("b200dd_wh_create: out of host memory");
+  h->delayMin = delay_min;
+  h->delayMax = delay_max;
+  h->N = n_samples;
+  h->nBins = (int)nb;
+  auto fail = [&](int rc) { b200dd_wh_destroy(h); return rc; };
+  int dev = device;
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaGetDevice", __FILE__, __LINE__));
+  h->device = dev;
+  DeviceGuard guard(dev);
+  if (!guard.ok) return fail(cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__));
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaGetDeviceProperties", __FILE__, __LINE__));
+  h->num_sms = prop.multiProcessorCount;
+  wh_plan(h);
+  if (!h->log2m) return fail(geom_fail("b200dd_wh_create: too many taps for the FFT plan"));
+  auto body = [&]() -> int {
+    B2_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const int M = 1 << h->log2m;
+    auto tw = twiddle_table_f64(M);
+    B2_CUDA(cudaMalloc(&h->d_tw, sizeof(double2) * M));
+    B2_CUDA(cudaMemcpy(h->d_tw, tw.data(), sizeof(double2) * M, cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMalloc(&h->d_partial, sizeof(double2) * (size_t)h->gridCorr * 2 * h->nBins));
+    B2_CUDA(cudaMalloc(&h->d_a, sizeof(double2) * h->nBins));
+    B2_CUDA(cudaMalloc(&h->d_b, sizeof(double2) * h->nBins));
+    B2_CUDA(cudaMalloc(&h->d_w, sizeof(double2) * h->nBins));
+    B2_CUDA(cudaMalloc(&h->d_what, sizeof(double2) * M));
+    B2_CUDA(cudaMalloc(&h->d_status, sizeof(int)));
+    B2_CUDA(cudaMemset(h->d_status, 0, sizeof(int)));
+    return B200DD_OK;
+  };
+  int rc = body();
+  if (rc != B200DD_OK) return fail(rc);
+  *out = h;
+  return B200DD_OK;
+}
+
+void b200dd_wh_destroy(b200dd_wh *h) {
+  if (!h) return;
+  {
+    DeviceGuard guard(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_dev(h->d_tw);
+    free_dev(h->d_partial);
+    free_dev(h->d_a);
+    free_dev(h->d_b);
+    free_dev(h->d_w);
+    free_dev(h->d_what);
+    free_dev(h->d_status);
+    free_dev(h->d_xd);
+    free_dev(h->d_yd);
+    if (h->stream) cudaStreamDestroy(h->stream);
+  }
+  delete h;
+}
+
+int b200dd_wh_process_device(b200dd_wh *h, const void *d_x, const void *d_y, void *d_y_out, void *stream) {
+  if (!h || !d_x || !d_y || !d_y_out) return arg_fail("b200dd_wh_process_device: null argument");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  return wh_dispatch<float2>(h, d_x, d_y, d_y_out, st);
+}
+
+int b200dd_wh_last_status(b200dd_wh *h) {
+  if (!h) return arg_fail("b200dd_wh_last_status: null handle");
+  DeviceGuard guard(h->device);
+  int st = 0;
+  B2_CUDA(cudaDeviceSynchronize());
+  B2_CUDA(cudaMemcpy(&st, h->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+  return st == 0 ? B200DD_OK : B200DD_FILTER_FAILED;
+}
+
+int b200dd_wh_process_host(b200dd_wh *h, const double *x, double *y) {
+  if (!h || !x || !y) return arg_fail("b200dd_wh_process_host: null argument");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = h->stream;
+  if (!h->d_xd) {
+    B2_CUDA(cudaMalloc(&h->d_xd, sizeof(double2) * h->N));
+    B2_CUDA(cudaMalloc(&h->d_yd, sizeof(double2) * h->N));
+  }
+  B2_CUDA(cudaMemcpyAsync(h->d_xd, x, sizeof(double2) * h->N, cudaMemcpyHostToDevice, st));
+  B2_CUDA(cudaMemcpyAsync(h->d_yd, y, sizeof(double2) * h->N, cudaMemcpyHostToDevice, st));
+  int rc = wh_dispatch<double2>(h, h->d_xd, h->d_yd, h->d_yd, st);  // in place: each CTA reads y[i] then writes y'[i]
+  if (rc != B200DD_OK) return rc;
+  int status = 0;
+  B2_CUDA(cudaMemcpyAsync(&status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  if (status != 0) {
+    set_last_error("Chol decomposition failed, skip clutter filter");  // reference message, WienerHopf.cpp:114
+    return B200DD_FILTER_FAILED;
+  }
+  B2_CUDA(cudaMemcpyAsync(y, h->d_yd, sizeof(double2) * h->N, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  return B200DD_OK;
+}
+
+int b200dd_wh_debug_weights(b200dd_wh *h, double *w, double *a, double *b) {
+  if (!h) return arg_fail("b200dd_wh_debug_weights: null handle");
+  DeviceGuard guard(h->device);
+  B2_CUDA(cudaDeviceSynchronize());
+  if (w) B2_CUDA(cudaMemcpy(w, h->d_w, sizeof(double2) * h->nBins, cudaMemcpyDeviceToHost));
+  if (a) B2_CUDA(cudaMemcpy(a, h->d_a, sizeof(double2) * h->nBins, cudaMemcpyDeviceToHost));
+  if (b) B2_CUDA(cudaMemcpy(b, h->d_b, sizeof(double2) * h->nBins, cudaMemcpyDeviceToHost));
+  return B200DD_OK;
+}
+
+uint32_t b200dd_wh_n_bins(const b200dd_wh *h) { return h ? (uint32_t)h->nBins : 0; }
+void *b200dd_wh_stream(b200dd_wh *h) { return h ? (void *)h->stream : nullptr; }
+
+}  // extern "C"

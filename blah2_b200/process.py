@@ -137,3 +137,189 @@ class Ambiguity:
             self.close()
         except Exception:
             pass
+
+
+class WienerHopf:
+    """WienerHopf(delayMin, delayMax, nSamples) -- src/process/clutter/WienerHopf.h:68."""
+
+    def __init__(self, delayMin, delayMax, nSamples, device=-1):
+        lib = capi.load()
+        h = C.c_void_p()
+        capi.check(lib.b200dd_wh_create(int(delayMin), int(delayMax), int(nSamples), int(device), C.byref(h)))
+        self._lib, self._h = lib, h
+        self.nSamples = int(nSamples)
+        self.nBins = int(lib.b200dd_wh_n_bins(h))
+
+    def process(self, x, y):
+        """Host path.  Returns (ok, y_filtered): ok False <=> the reference returns false
+        (Cholesky failure) and leaves y untouched (WienerHopf.cpp:111-122)."""
+        x = _c128(x)
+        y = _c128(y).copy()
+        if x.shape[0] != self.nSamples or y.shape[0] != self.nSamples:
+            raise ValueError("x and y must hold nSamples samples")
+        rc = capi.check(self._lib.b200dd_wh_process_host(self._h, capi.ptr(x), capi.ptr(y)),
+                        allow=(capi.FILTER_FAILED,))
+        return rc == capi.OK, y
+
+    def process_device(self, d_x, d_y, d_y_out=None, stream=None):
+        out = d_y if d_y_out is None else d_y_out
+        capi.check(self._lib.b200dd_wh_process_device(self._h, capi.ptr(d_x), capi.ptr(d_y), capi.ptr(out),
+                                                      capi.ptr(stream) if stream else None))
+
+    def last_status(self) -> bool:
+        rc = capi.check(self._lib.b200dd_wh_last_status(self._h), allow=(capi.FILTER_FAILED,))
+        return rc == capi.OK
+
+    def debug_weights(self):
+        w = np.empty(self.nBins, dtype=np.complex128)
+        a = np.empty(self.nBins, dtype=np.complex128)
+        b = np.empty(self.nBins, dtype=np.complex128)
+        capi.check(self._lib.b200dd_wh_debug_weights(self._h, capi.ptr(w), capi.ptr(a), capi.ptr(b)))
+        return w, a, b
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200dd_wh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _DetHandle:
+    """One b200dd_det handle shared by the three detection classes of a pipeline."""
+
+    def __init__(self, pfa=1e-5, nGuard=0, nTrain=0, minDelay=0, minDoppler=0.0, nCentroidDelay=0,
+                 nCentroidDoppler=0, resolutionDoppler=1.0, doDelay=True, doDoppler=True, max_doppler_bins=8192,
+                 max_delay_bins=2048, device=-1):
+        lib = capi.load()
+        p = capi.DetParams(float(pfa), int(nGuard), int(nTrain), int(minDelay), float(minDoppler),
+                           int(nCentroidDelay), int(nCentroidDoppler), float(resolutionDoppler), int(bool(doDelay)),
+                           int(bool(doDoppler)), int(device))
+        h = C.c_void_p()
+        capi.check(lib.b200dd_det_create(C.byref(p), int(max_doppler_bins), int(max_delay_bins), C.byref(h)))
+        self._lib, self._h = lib, h
+        self.cap = min(int(max_doppler_bins) * int(max_delay_bins), 1 << 18)
+
+    def _bufs(self, cap):
+        return [np.empty(max(1, cap), dtype=np.float64) for _ in range(3)]
+
+    def process_map(self, m: Map, last_stage: int) -> Detection:
+        data = _c128(m.data)
+        delay = np.ascontiguousarray(m.delay, dtype=np.int32)
+        doppler = np.ascontiguousarray(m.doppler, dtype=np.float64)
+        od, of, os_ = self._bufs(self.cap)
+        n = C.c_uint32()
+        capi.check(self._lib.b200dd_det_process_host(self._h, last_stage, capi.ptr(data), data.shape[0],
+                                                     data.shape[1], capi.ptr(delay), capi.ptr(doppler),
+                                                     float(m.noisePower), capi.ptr(od), capi.ptr(of), capi.ptr(os_),
+                                                     self.cap, C.byref(n)))
+        k = n.value
+        return Detection(od[:k].copy(), of[:k].copy(), os_[:k].copy())
+
+    def process_device_map(self, d_map, nDop, nDel, delay, doppler, noisePower, last_stage, stream=None) -> Detection:
+        delay = np.ascontiguousarray(delay, dtype=np.int32)
+        doppler = np.ascontiguousarray(doppler, dtype=np.float64)
+        od, of, os_ = self._bufs(self.cap)
+        n = C.c_uint32()
+        capi.check(self._lib.b200dd_det_process_device(self._h, last_stage, capi.ptr(d_map), int(nDop), int(nDel),
+                                                       capi.ptr(delay), capi.ptr(doppler), float(noisePower),
+                                                       capi.ptr(od), capi.ptr(of), capi.ptr(os_), self.cap,
+                                                       C.byref(n), capi.ptr(stream) if stream else None))
+        k = n.value
+        return Detection(od[:k].copy(), of[:k].copy(), os_[:k].copy())
+
+    def set_metrics_device(self, d_map, nDop, nDel, stream=None):
+        out = np.empty(2, dtype=np.float64)
+        capi.check(self._lib.b200dd_det_set_metrics_device(self._h, capi.ptr(d_map), int(nDop), int(nDel),
+                                                           capi.ptr(out), capi.ptr(stream) if stream else None))
+        return float(out[0]), float(out[1])
+
+    def centroid(self, det: Detection) -> Detection:
+        d = np.ascontiguousarray(det.delay, dtype=np.float64)
+        f = np.ascontiguousarray(det.doppler, dtype=np.float64)
+        s = np.ascontiguousarray(det.snr, dtype=np.float64)
+        cap = max(1, d.shape[0])
+        od, of, os_ = self._bufs(cap)
+        n = C.c_uint32()
+        capi.check(self._lib.b200dd_det_centroid_host(self._h, capi.ptr(d), capi.ptr(f), capi.ptr(s), d.shape[0],
+                                                      capi.ptr(od), capi.ptr(of), capi.ptr(os_), cap, C.byref(n)))
+        k = n.value
+        return Detection(od[:k].copy(), of[:k].copy(), os_[:k].copy())
+
+    def interpolate(self, det: Detection, m: Map) -> Detection:
+        d = np.ascontiguousarray(det.delay, dtype=np.float64)
+        f = np.ascontiguousarray(det.doppler, dtype=np.float64)
+        s = np.ascontiguousarray(det.snr, dtype=np.float64)
+        data = _c128(m.data)
+        delay = np.ascontiguousarray(m.delay, dtype=np.int32)
+        doppler = np.ascontiguousarray(m.doppler, dtype=np.float64)
+        cap = max(1, d.shape[0])
+        od, of, os_ = self._bufs(cap)
+        n = C.c_uint32()
+        capi.check(self._lib.b200dd_det_interpolate_host(self._h, capi.ptr(d), capi.ptr(f), capi.ptr(s), d.shape[0],
+                                                         capi.ptr(data), data.shape[0], data.shape[1],
+                                                         capi.ptr(delay), capi.ptr(doppler), float(m.noisePower),
+                                                         capi.ptr(od), capi.ptr(of), capi.ptr(os_), cap, C.byref(n)))
+        k = n.value
+        return Detection(od[:k].copy(), of[:k].copy(), os_[:k].copy())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200dd_det_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CfarDetector1D:
+    """CfarDetector1D(pfa, nGuard, nTrain, minDelay, minDoppler) -- CfarDetector1D.h:46."""
+
+    def __init__(self, pfa, nGuard, nTrain, minDelay, minDoppler, max_doppler_bins=8192, max_delay_bins=2048,
+                 device=-1):
+        self._d = _DetHandle(pfa=pfa, nGuard=nGuard, nTrain=nTrain, minDelay=minDelay, minDoppler=minDoppler,
+                             max_doppler_bins=max_doppler_bins, max_delay_bins=max_delay_bins, device=device)
+
+    def process(self, m: Map) -> Detection:
+        return self._d.process_map(m, capi.DET_CFAR)
+
+
+class Centroid:
+    """Centroid(nDelay, nDoppler, resolutionDoppler) -- Centroid.h:35."""
+
+    def __init__(self, nDelay, nDoppler, resolutionDoppler, device=-1):
+        self._d = _DetHandle(nCentroidDelay=nDelay, nCentroidDoppler=nDoppler, resolutionDoppler=resolutionDoppler,
+                             max_doppler_bins=512, max_delay_bins=512, device=device)
+
+    def process(self, det: Detection) -> Detection:
+        return self._d.centroid(det)
+
+
+class Interpolate:
+    """Interpolate(doDelay, doDoppler) -- Interpolate.h:36."""
+
+    def __init__(self, doDelay, doDoppler, max_doppler_bins=8192, max_delay_bins=2048, device=-1):
+        self._d = _DetHandle(doDelay=doDelay, doDoppler=doDoppler, max_doppler_bins=max_doppler_bins,
+                             max_delay_bins=max_delay_bins, device=device)
+
+    def process(self, det: Detection, m: Map) -> Detection:
+        return self._d.interpolate(det, m)
+
+
+def set_metrics(m: Map) -> Map:
+    """Map::set_metrics (Map.cpp:188-206) evaluated on the GPU for a host Map."""
+    import torch  # device memory plumbing only
+
+    d = _DetHandle(max_doppler_bins=m.data.shape[0], max_delay_bins=m.data.shape[1])
+    t = torch.from_numpy(np.ascontiguousarray(m.data.astype(np.complex64))).cuda()
+    m.noisePower, m.maxPower = d.set_metrics_device(t, m.data.shape[0], m.data.shape[1])
+    torch.cuda.synchronize()
+    d.close()
+    return m

@@ -1,0 +1,119 @@
+"""GPU parity: CUDA Wiener-Hopf clutter canceller (through the C ABI) vs the oracle.
+
+The reference has NO test for WienerHopf, so the pins are the oracle
+(oracle/blah2_oracle.py, itself checked against the compiled reference source + the
+Armadillo/LAPACK restatement) and size-independent properties.
+"""
+import numpy as np
+import pytest
+
+from blah2_b200.process import Ambiguity, WienerHopf
+from blah2_b200.scene import make_scene, Target
+from oracle import blah2_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# (n, delayMin, delayMax, seed)
+CASES = [
+    (5000, -3, 20, 1),
+    (20011, -10, 40, 2),        # prime-ish length: segments do not divide N
+    (65536, 0, 100, 3),         # delayMin = 0
+    (200000, -10, 400, 4),      # the reference's default clutter window (config/config.yml:29-32)
+    (100000, 2, 60, 5),         # delayMin > 0 (reference's uint32 wrap semantics)
+    (300000, -10, 1200, 6),     # many taps -> longer FFT plan
+]
+
+
+def _scene(n, seed):
+    return make_scene(n, 2e6, seed=seed, targets=[Target(25, 300.0, -40.0)])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_filter_matches_oracle_fp64_host_path(case, relerr):
+    n, dm, dM, seed = case
+    sc = _scene(n, seed)
+    wh = WienerHopf(dm, dM, n)
+    ok, y = wh.process(sc.x, sc.y)
+    ok_ref, w_ref, a_ref, b_ref, xs = O.wienerhopf_weights(sc.x, sc.y, dm, dM)
+    assert ok and ok_ref
+    w, a, b = wh.debug_weights()
+    assert relerr(a, a_ref)[0] < 1e-12, "auto-correlation"
+    assert relerr(b, b_ref)[0] < 1e-12, "cross-correlation"
+    assert relerr(w, w_ref)[0] < 1e-9, "weights"
+    y_ref = O.wienerhopf_apply(xs, sc.y, w_ref)
+    e = relerr(y, y_ref)
+    assert e[0] < 1e-9 and e[1] < 1e-9, f"filtered surveillance {e}"
+    # it must actually cancel clutter
+    assert np.linalg.norm(y) < 0.1 * np.linalg.norm(sc.y)
+
+
+def test_cholesky_failure_leaves_y_untouched():
+    n = 4096
+    wh = WienerHopf(-2, 10, n)
+    y0 = np.ones(n, dtype=np.complex128) * (1 + 2j)
+    ok, y = wh.process(np.zeros(n, dtype=np.complex128), y0)   # A = 0 -> not positive definite
+    assert not ok
+    assert np.array_equal(y, y0)
+    assert not O.wienerhopf_process(np.zeros(n), y0, -2, 10)[0]
+
+
+def test_device_path_complex64(relerr):
+    import torch
+    n, dm, dM = 200000, -10, 400
+    sc = _scene(n, 7)
+    wh = WienerHopf(dm, dM, n)
+    dx = torch.from_numpy(sc.x.astype(np.complex64)).cuda()
+    dy = torch.from_numpy(sc.y.astype(np.complex64)).cuda()
+    out = torch.empty_like(dy)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        wh.process_device(dx, dy, out, s.cuda_stream)
+    s.synchronize()
+    assert wh.last_status()
+    ok, y_ref = O.wienerhopf_process(sc.x, sc.y, dm, dM)
+    e = relerr(out.cpu().numpy().astype(np.complex128), y_ref)
+    assert e[0] < 1e-6 and e[1] < 1e-6, f"{e}"   # float32 rounding of the output only
+    # in-place (d_y_out aliasing d_y)
+    with torch.cuda.stream(s):
+        wh.process_device(dx, dy, dy, s.cuda_stream)
+    s.synchronize()
+    assert torch.equal(dy, out)
+
+
+def test_clutter_filter_then_ambiguity_map_matches_oracle(relerr):
+    """BASELINE config 2 shape at reduced size: WienerHopf -> Ambiguity, map within 1e-5."""
+    fs, n = 2000000, 400000
+    geom = (-10, 120, -300, 300, fs, n, True)
+    sc = make_scene(n, fs, seed=9, targets=[Target(37, 110.0, -50.0), Target(92, -205.0, -55.0)])
+    wh = WienerHopf(-10, 60, n)
+    ok, yf = wh.process(sc.x, sc.y)
+    assert ok
+    m = Ambiguity(*geom).process(sc.x, yf)
+    g = O.ambiguity_geometry(*geom)
+    out = O.chain(sc.x, sc.y, g, clutter=(-10, 60))
+    e = relerr(m.data, out["map"])
+    assert e[0] < 1e-5 and e[1] < 1e-5, f"{e}"
+
+
+def test_full_size_config2_against_oracle(relerr):
+    """N = 2e6, 410 taps: the oracle still finishes in seconds at this size."""
+    fs, n = 2000000, 2000000
+    sc = make_scene(n, fs, seed=20260923)
+    wh = WienerHopf(-10, 400, n)
+    ok, y = wh.process(sc.x, sc.y)
+    ok_ref, y_ref = O.wienerhopf_process(sc.x, sc.y, -10, 400)
+    assert ok and ok_ref
+    e = relerr(y, y_ref)
+    assert e[0] < 1e-9 and e[1] < 1e-9, f"{e}"
+
+
+def test_linearity_in_y_for_fixed_weights_property():
+    """Idempotence-style property: filtering an already clutter-free y (pure noise,
+    uncorrelated with x) changes it by at most the estimation noise of w."""
+    n = 500000
+    rng = np.random.default_rng(1)
+    x = np.round(rng.standard_normal(n) * 1000) + 1j * np.round(rng.standard_normal(n) * 1000)
+    y = np.round(rng.standard_normal(n) * 30) + 1j * np.round(rng.standard_normal(n) * 30)
+    ok, yf = WienerHopf(-5, 100, n).process(x, y)
+    assert ok
+    assert np.linalg.norm(yf - y) < 0.05 * np.linalg.norm(y)

@@ -22,15 +22,17 @@ def run(name, log2m=None, iters=20, nbuf=8):
     xs = [torch.randn(n, dtype=torch.complex64, device="cuda") for _ in range(nbuf)]
     ys = [torch.randn(n, dtype=torch.complex64, device="cuda") for _ in range(nbuf)]
     out = torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
-    for i in range(3):
-        amb.process_device(xs[i % nbuf], ys[i % nbuf], out, st)
+    stream = torch.cuda.Stream()
+    st = stream.cuda_stream
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters):
-        amb.process_device(xs[i % nbuf], ys[i % nbuf], out, st)
-    e1.record()
+    with torch.cuda.stream(stream):
+        for i in range(3):
+            amb.process_device(xs[i % nbuf], ys[i % nbuf], out, st)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(iters):
+            amb.process_device(xs[i % nbuf], ys[i % nbuf], out, st)
+        e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     byts = 16 * g.n_used + 8 * g.n_doppler_bins * g.n_delay_bins
