@@ -52,6 +52,16 @@ class DetParams(C.Structure):
                 ("device", C.c_int32)]
 
 
+class PipelineParams(C.Structure):
+    _fields_ = [("caf", CafParams), ("clutter_enable", C.c_int32), ("clutter_delay_min", C.c_int32),
+                ("clutter_delay_max", C.c_int32), ("detection_enable", C.c_int32), ("det", DetParams)]
+
+
+class CpiResult(C.Structure):
+    _fields_ = [("filter_status", C.c_int32), ("n_detections", C.c_uint32), ("noise_power", C.c_double),
+                ("max_power", C.c_double)]
+
+
 # every symbol include/b200dd.h declares: (name, restype, argtypes)
 _VP = C.c_void_p
 SIGNATURES = [
@@ -65,6 +75,8 @@ SIGNATURES = [
     ("b200dd_caf_get_axes", C.c_int, [_VP, _VP, _VP]),
     ("b200dd_caf_process_host", C.c_int, [_VP, _VP, _VP, C.c_uint32, _VP]),
     ("b200dd_caf_process_device", C.c_int, [_VP, _VP, _VP, C.c_uint32, _VP, _VP]),
+    ("b200dd_caf_profile_device", C.c_int, [_VP, _VP, _VP, C.c_uint32, _VP, _VP, C.POINTER(C.c_float),
+                                            C.POINTER(C.c_float)]),
     ("b200dd_caf_debug_range_matrix", C.c_int, [_VP, _VP]),
     ("b200dd_caf_device_map", _VP, [_VP]),
     ("b200dd_caf_stream", _VP, [_VP]),
@@ -73,6 +85,10 @@ SIGNATURES = [
     ("b200dd_wh_process_host", C.c_int, [_VP, _VP, _VP]),
     ("b200dd_wh_process_device", C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     ("b200dd_wh_last_status", C.c_int, [_VP]),
+    ("b200dd_wh_process_device_f64", C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    ("b200dd_wh_device_status", _VP, [_VP]),
+    ("b200dd_wh_profile_device", C.c_int, [_VP, _VP, _VP, _VP, _VP, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                           C.POINTER(C.c_float)]),
     ("b200dd_wh_debug_weights", C.c_int, [_VP, _VP, _VP, _VP]),
     ("b200dd_wh_n_bins", C.c_uint32, [_VP]),
     ("b200dd_wh_stream", _VP, [_VP]),
@@ -81,12 +97,23 @@ SIGNATURES = [
     ("b200dd_det_set_metrics_device", C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, _VP, _VP]),
     ("b200dd_det_process_device", C.c_int, [_VP, C.c_int, _VP, C.c_uint32, C.c_uint32, _VP, _VP, C.c_double, _VP,
                                             _VP, _VP, C.c_uint32, C.POINTER(C.c_uint32), _VP]),
+    ("b200dd_det_chain_device_async", C.c_int, [_VP, C.c_int, _VP, C.c_uint32, C.c_uint32, _VP, _VP, _VP]),
+    ("b200dd_det_chain_fetch", C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_uint32, C.POINTER(C.c_uint32), _VP]),
     ("b200dd_det_process_host", C.c_int, [_VP, C.c_int, _VP, C.c_uint32, C.c_uint32, _VP, _VP, C.c_double, _VP, _VP,
                                           _VP, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("b200dd_det_centroid_host", C.c_int, [_VP, _VP, _VP, _VP, C.c_uint32, _VP, _VP, _VP, C.c_uint32,
                                            C.POINTER(C.c_uint32)]),
     ("b200dd_det_interpolate_host", C.c_int, [_VP, _VP, _VP, _VP, C.c_uint32, _VP, C.c_uint32, C.c_uint32, _VP, _VP,
                                               C.c_double, _VP, _VP, _VP, C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("b200dd_pipeline_create", C.c_int, [C.POINTER(PipelineParams), C.POINTER(_VP)]),
+    ("b200dd_pipeline_destroy", None, [_VP]),
+    ("b200dd_pipeline_get_geometry", C.c_int, [_VP, C.POINTER(CafGeometry)]),
+    ("b200dd_pipeline_get_axes", C.c_int, [_VP, _VP, _VP]),
+    ("b200dd_pipeline_process_host", C.c_int, [_VP, _VP, _VP, C.c_uint32, _VP, C.POINTER(CpiResult), _VP, _VP, _VP,
+                                               C.c_uint32]),
+    ("b200dd_pipeline_submit_device", C.c_int, [_VP, _VP, _VP, C.c_uint32, _VP, _VP]),
+    ("b200dd_pipeline_fetch", C.c_int, [_VP, C.POINTER(CpiResult), _VP, _VP, _VP, C.c_uint32, _VP]),
+    ("b200dd_pipeline_stream", _VP, [_VP]),
 ]
 
 _lib = None

@@ -487,7 +487,8 @@ int caf_setup_device(b200dd_caf *h) {
   return B200DD_OK;
 }
 
-int caf_run_device(b200dd_caf *h, const float2 *d_x, const float2 *d_y, float2 *d_map, cudaStream_t st) {
+int caf_run_device(b200dd_caf *h, const float2 *d_x, const float2 *d_y, float2 *d_map, cudaStream_t st,
+                   cudaEvent_t *ev = nullptr) {
   const HostGeom &g = h->g;
   RangeArgs ra;
   ra.x = d_x;
@@ -499,8 +500,10 @@ int caf_run_device(b200dd_caf *h, const float2 *d_x, const float2 *d_y, float2 *
   ra.lagMin = g.delayMin;
   ra.nSeg = h->nSeg;
   ra.L = h->L;
+  if (ev) B2_CUDA(cudaEventRecord(ev[0], st));
   int rc = dispatch_range(h->log2m, ra, (int)g.nDop, st);
   if (rc != B200DD_OK) return rc;
+  if (ev) B2_CUDA(cudaEventRecord(ev[1], st));
   DopplerArgs da;
   da.R = h->d_R;
   da.out = d_map;
@@ -509,7 +512,10 @@ int caf_run_device(b200dd_caf *h, const float2 *d_x, const float2 *d_y, float2 *
   da.tw = h->d_tw2;
   da.nDop = (int)g.nDop;
   da.nDel = (int)g.nDel;
-  return dispatch_doppler(h->log2m2, da, st);
+  rc = dispatch_doppler(h->log2m2, da, st);
+  if (rc != B200DD_OK) return rc;
+  if (ev) B2_CUDA(cudaEventRecord(ev[2], st));
+  return B200DD_OK;
 }
 
 inline int grid_for(uint32_t n) {
@@ -652,6 +658,25 @@ int b200dd_caf_process_host(b200dd_caf *h, const double *x, const double *y, uin
   B2_CUDA(cudaMemcpyAsync(map_out, h->d_mapd, sizeof(double2) * cells, cudaMemcpyDeviceToHost, st));
   B2_CUDA(cudaStreamSynchronize(st));
   return B200DD_OK;
+}
+
+int b200dd_caf_profile_device(b200dd_caf *h, const void *d_x, const void *d_y, uint32_t n, void *d_map, void *stream,
+                              float *ms_range, float *ms_doppler) {
+  if (!h || !d_x || !d_y || !ms_range || !ms_doppler) return arg_fail("b200dd_caf_profile_device: null argument");
+  if (n < h->g.nDop * h->g.nCorr) return arg_fail("b200dd_caf_profile_device: too few samples");
+  if (h->g.dopplerMiddle != 0.0) return arg_fail("b200dd_caf_profile_device: symmetric Doppler windows only");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  cudaEvent_t ev[3];
+  for (int i = 0; i < 3; i++) B2_CUDA(cudaEventCreate(&ev[i]));
+  int rc = caf_run_device(h, (const float2 *)d_x, (const float2 *)d_y, d_map ? (float2 *)d_map : h->d_map, st, ev);
+  if (rc == B200DD_OK) {
+    B2_CUDA(cudaEventSynchronize(ev[2]));
+    B2_CUDA(cudaEventElapsedTime(ms_range, ev[0], ev[1]));
+    B2_CUDA(cudaEventElapsedTime(ms_doppler, ev[1], ev[2]));
+  }
+  for (int i = 0; i < 3; i++) cudaEventDestroy(ev[i]);
+  return rc;
 }
 
 int b200dd_caf_debug_range_matrix(b200dd_caf *h, float *out) {

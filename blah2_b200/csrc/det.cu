@@ -99,14 +99,26 @@ __global__ void __launch_bounds__(kBlock) metrics_partial_kernel(const TMAP *map
   }
 }
 
-__global__ void metrics_final_kernel(const double *part_sum, const double *part_max, int nPart, double cells,
-                                     double *out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double s = 0.0, m = 0.0;
-    for (int i = 0; i < nPart; i++) { s += part_sum[i]; m = (m < part_max[i]) ? part_max[i] : m; }
-    const double noise = s / cells;
-    out[0] = noise;       // noisePower  (Map.cpp:203-204)
-    out[1] = m - noise;   // maxPower    (Map.cpp:205)
+__global__ void __launch_bounds__(kBlock) metrics_final_kernel(const double *part_sum, const double *part_max, int nPart,
+                                                                double cells, double *out) {
+  // fixed-order tree over at most 1024 partials: deterministic
+  __shared__ double ssum[kBlock], smax[kBlock];
+  double s = 0.0, m = 0.0;
+  for (int i = threadIdx.x; i < nPart; i += kBlock) { s += part_sum[i]; m = (m < part_max[i]) ? part_max[i] : m; }
+  ssum[threadIdx.x] = s;
+  smax[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = kBlock / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      ssum[threadIdx.x] += ssum[threadIdx.x + o];
+      smax[threadIdx.x] = (smax[threadIdx.x] < smax[threadIdx.x + o]) ? smax[threadIdx.x + o] : smax[threadIdx.x];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double noise = ssum[0] / cells;
+    out[0] = noise;             // noisePower  (Map.cpp:203-204)
+    out[1] = smax[0] - noise;   // maxPower    (Map.cpp:205)
   }
 }
 
@@ -194,6 +206,7 @@ struct EmitArgs {
   const int32_t *delay;
   const double *doppler;
   double noisePower;
+  const double *noise_dev;  // when non-null overrides noisePower (device-resident chain)
   const uint32_t *mask, *off;
   DetList out;
   uint32_t cap;
@@ -205,6 +218,7 @@ template <class TMAP> __global__ void __launch_bounds__(kBlock) cfar_emit_kernel
   const uint32_t row_off = a.off[i];
   if (a.off[i + 1] == row_off) return;  // uniform per block
   const TMAP *row = reinterpret_cast<const TMAP *>(a.map) + (size_t)i * a.nDel;
+  const double noisePower = a.noise_dev ? *a.noise_dev : a.noisePower;
   uint32_t running = 0;
   for (int wbase = 0; wbase < a.words; wbase += kBlock) {
     const int w = wbase + tid;
@@ -220,7 +234,7 @@ template <class TMAP> __global__ void __launch_bounds__(kBlock) cfar_emit_kernel
       if (o < a.cap) {
         a.out.delay[o] = (double)(j + a.delay[0]);              // CfarDetector1D.cpp:88
         a.out.doppler[o] = a.doppler[i];                        // :89
-        a.out.snr[o] = db_abs(ld_cell(row, j)) - a.noisePower;  // :48,90
+        a.out.snr[o] = db_abs(ld_cell(row, j)) - noisePower;  // :48,90
       }
     }
     running += tot;
@@ -269,6 +283,7 @@ struct InterpArgs {
   const int32_t *delay;
   const double *doppler;
   double noisePower;
+  const double *noise_dev;
   int doDelay, doDoppler;
   uint8_t *keep;
 };
@@ -289,6 +304,7 @@ __device__ __forceinline__ int hz_to_bin(const double *axis, int n, double hz) {
 template <class TMAP> __global__ void __launch_bounds__(kBlock) interp_kernel(InterpArgs a) {
   const uint32_t n = min(*a.n, a.cap);
   const TMAP *map = reinterpret_cast<const TMAP *>(a.map);
+  const double noisePower = a.noise_dev ? *a.noise_dev : a.noisePower;
   for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
     const double d = a.in.delay[i], f = a.in.doppler[i], s = a.in.snr[i];
     double intDelay = d, intDoppler = f, intSnrDelay = s;
@@ -296,7 +312,7 @@ template <class TMAP> __global__ void __launch_bounds__(kBlock) interp_kernel(In
     bool keep = true;
     const int row = hz_to_bin(a.doppler, a.nDop, f);
     const double d0 = (double)a.delay[0];
-    auto db = [&](int r, int c) { return db_abs(ld_cell(map, (size_t)r * a.nDel + c)) - a.noisePower; };
+    auto db = [&](int r, int c) { return db_abs(ld_cell(map, (size_t)r * a.nDel + c)) - noisePower; };
     if (a.doDelay) {
       if (d == d0 || d == (double)a.delay[a.nDel - 1]) keep = false;  // :46-49
       if (keep) {
@@ -391,6 +407,9 @@ struct b200dd_det {
   size_t mapd_cells = 0;
   double *d_part = nullptr, *d_metrics = nullptr;
   int nPart = 592;
+  std::vector<int32_t> axes_delay;   // host copies of what d_delay / d_doppler hold
+  std::vector<double> axes_doppler;
+  int chain_buf = 0, chain_slot = 0;  // where the last async chain left its results
 };
 
 namespace {
@@ -399,9 +418,17 @@ inline DetList list_of(b200dd_det *h, int which) { return DetList{h->d_buf[which
 
 template <class TMAP>
 int run_chain(b200dd_det *h, int last_stage, const TMAP *d_map, uint32_t nDop, uint32_t nDel, const int32_t *delay,
-              const double *doppler, double noisePower, cudaStream_t st, int *final_buf, int *count_slot_out) {
-  B2_CUDA(cudaMemcpyAsync(h->d_delay, delay, sizeof(int32_t) * nDel, cudaMemcpyHostToDevice, st));
-  B2_CUDA(cudaMemcpyAsync(h->d_doppler, doppler, sizeof(double) * nDop, cudaMemcpyHostToDevice, st));
+              const double *doppler, double noisePower, const double *noise_dev, cudaStream_t st, int *final_buf,
+              int *count_slot_out) {
+  // axes: upload only when they changed (tiny, but keeps the async chain free of host copies)
+  if (h->axes_delay.size() != nDel || memcmp(h->axes_delay.data(), delay, sizeof(int32_t) * nDel) != 0) {
+    h->axes_delay.assign(delay, delay + nDel);
+    B2_CUDA(cudaMemcpyAsync(h->d_delay, h->axes_delay.data(), sizeof(int32_t) * nDel, cudaMemcpyHostToDevice, st));
+  }
+  if (h->axes_doppler.size() != nDop || memcmp(h->axes_doppler.data(), doppler, sizeof(double) * nDop) != 0) {
+    h->axes_doppler.assign(doppler, doppler + nDop);
+    B2_CUDA(cudaMemcpyAsync(h->d_doppler, h->axes_doppler.data(), sizeof(double) * nDop, cudaMemcpyHostToDevice, st));
+  }
   const int words = (int)((nDel + 31) / 32);
   CfarArgs ca;
   ca.map = d_map; ca.nDop = (int)nDop; ca.nDel = (int)nDel; ca.words = words;
@@ -414,7 +441,7 @@ int run_chain(b200dd_det *h, int last_stage, const TMAP *d_map, uint32_t nDop, u
   B2_LAUNCH_CHECK();
   EmitArgs ea;
   ea.map = d_map; ea.nDop = (int)nDop; ea.nDel = (int)nDel; ea.words = words;
-  ea.delay = h->d_delay; ea.doppler = h->d_doppler; ea.noisePower = noisePower;
+  ea.delay = h->d_delay; ea.doppler = h->d_doppler; ea.noisePower = noisePower; ea.noise_dev = noise_dev;
   ea.mask = h->d_mask; ea.off = h->d_off; ea.out = list_of(h, 0); ea.cap = h->cap;
   cfar_emit_kernel<TMAP><<<nDop, kBlock, 0, st>>>(ea);
   B2_LAUNCH_CHECK();
@@ -439,7 +466,7 @@ int run_chain(b200dd_det *h, int last_stage, const TMAP *d_map, uint32_t nDop, u
     InterpArgs ia;
     ia.in = list_of(h, 1); ia.out = list_of(h, 1); ia.n = h->d_n + 1; ia.cap = h->cap; ia.map = d_map;
     ia.nDop = (int)nDop; ia.nDel = (int)nDel; ia.delay = h->d_delay; ia.doppler = h->d_doppler;
-    ia.noisePower = noisePower; ia.doDelay = h->p.interp_delay; ia.doDoppler = h->p.interp_doppler;
+    ia.noisePower = noisePower; ia.noise_dev = noise_dev; ia.doDelay = h->p.interp_delay; ia.doDoppler = h->p.interp_doppler;
     ia.keep = h->d_keep;
     interp_kernel<TMAP><<<148, kBlock, 0, st>>>(ia);
     B2_LAUNCH_CHECK();
@@ -571,7 +598,7 @@ int b200dd_det_set_metrics_device(b200dd_det *h, const void *d_map, uint32_t n_d
   if (grid > h->nPart) grid = h->nPart;
   metrics_partial_kernel<float2><<<grid, kBlock, 0, st>>>((const float2 *)d_map, cells, h->d_part, h->d_part + h->nPart);
   B2_LAUNCH_CHECK();
-  metrics_final_kernel<<<1, 32, 0, st>>>(h->d_part, h->d_part + h->nPart, grid, (double)cells, h->d_metrics);
+  metrics_final_kernel<<<1, kBlock, 0, st>>>(h->d_part, h->d_part + h->nPart, grid, (double)cells, h->d_metrics);
   B2_LAUNCH_CHECK();
   B2_CUDA(cudaMemcpyAsync(metrics, h->d_metrics, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
   B2_CUDA(cudaStreamSynchronize(st));
@@ -589,9 +616,38 @@ int b200dd_det_process_device(b200dd_det *h, int last_stage, const void *d_map, 
   DeviceGuard guard(h->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   int buf = 0, slot = 0;
-  rc = run_chain<float2>(h, last_stage, (const float2 *)d_map, n_dop, n_del, delay, doppler, noise_power, st, &buf, &slot);
+  rc = run_chain<float2>(h, last_stage, (const float2 *)d_map, n_dop, n_del, delay, doppler, noise_power, nullptr, st, &buf, &slot);
   if (rc != B200DD_OK) return rc;
   return fetch_results(h, buf, slot, o_delay, o_doppler, o_snr, cap, n_out, st);
+}
+
+int b200dd_det_chain_device_async(b200dd_det *h, int last_stage, const void *d_map, uint32_t n_dop, uint32_t n_del,
+                                  const int32_t *delay, const double *doppler, void *stream) {
+  if (!h || !d_map || !delay || !doppler) return arg_fail("b200dd_det_chain_device_async: null argument");
+  if (last_stage < B200DD_DET_CFAR || last_stage > B200DD_DET_INTERPOLATE) return arg_fail("b200dd_det_chain_device_async: bad stage");
+  int rc = check_dims(h, n_dop, n_del);
+  if (rc != B200DD_OK) return rc;
+  DeviceGuard guard(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const size_t cells = (size_t)n_dop * n_del;
+  int grid = (int)((cells + kBlock - 1) / kBlock);
+  if (grid > h->nPart) grid = h->nPart;
+  metrics_partial_kernel<float2><<<grid, kBlock, 0, st>>>((const float2 *)d_map, cells, h->d_part, h->d_part + h->nPart);
+  B2_LAUNCH_CHECK();
+  metrics_final_kernel<<<1, kBlock, 0, st>>>(h->d_part, h->d_part + h->nPart, grid, (double)cells, h->d_metrics);
+  B2_LAUNCH_CHECK();
+  return run_chain<float2>(h, last_stage, (const float2 *)d_map, n_dop, n_del, delay, doppler, 0.0, h->d_metrics, st,
+                           &h->chain_buf, &h->chain_slot);
+}
+
+int b200dd_det_chain_fetch(b200dd_det *h, double *metrics, double *o_delay, double *o_doppler, double *o_snr,
+                           uint32_t cap, uint32_t *n_out, void *stream) {
+  if (!h) return arg_fail("b200dd_det_chain_fetch: null handle");
+  if (cap && (!o_delay || !o_doppler || !o_snr)) return arg_fail("b200dd_det_chain_fetch: null output");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  if (metrics) B2_CUDA(cudaMemcpyAsync(metrics, h->d_metrics, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+  return fetch_results(h, h->chain_buf, h->chain_slot, o_delay, o_doppler, o_snr, cap, n_out, st);
 }
 
 int b200dd_det_process_host(b200dd_det *h, int last_stage, const double *map, uint32_t n_dop, uint32_t n_del,
@@ -611,7 +667,7 @@ int b200dd_det_process_host(b200dd_det *h, int last_stage, const double *map, ui
   }
   B2_CUDA(cudaMemcpyAsync(h->d_mapd, map, sizeof(double2) * (size_t)n_dop * n_del, cudaMemcpyHostToDevice, st));
   int buf = 0, slot = 0;
-  rc = run_chain<double2>(h, last_stage, h->d_mapd, n_dop, n_del, delay, doppler, noise_power, st, &buf, &slot);
+  rc = run_chain<double2>(h, last_stage, h->d_mapd, n_dop, n_del, delay, doppler, noise_power, nullptr, st, &buf, &slot);
   if (rc != B200DD_OK) return rc;
   return fetch_results(h, buf, slot, o_delay, o_doppler, o_snr, cap, n_out, st);
 }
@@ -660,6 +716,8 @@ int b200dd_det_interpolate_host(b200dd_det *h, const double *delay, const double
     h->mapd_cells = (size_t)n_dop * n_del;
   }
   B2_CUDA(cudaMemcpyAsync(h->d_mapd, map, sizeof(double2) * (size_t)n_dop * n_del, cudaMemcpyHostToDevice, st));
+  h->axes_delay.clear();
+  h->axes_doppler.clear();
   B2_CUDA(cudaMemcpyAsync(h->d_delay, mdelay, sizeof(int32_t) * n_del, cudaMemcpyHostToDevice, st));
   B2_CUDA(cudaMemcpyAsync(h->d_doppler, mdoppler, sizeof(double) * n_dop, cudaMemcpyHostToDevice, st));
   if (n) {
@@ -671,7 +729,7 @@ int b200dd_det_interpolate_host(b200dd_det *h, const double *delay, const double
   InterpArgs ia;
   ia.in = list_of(h, 1); ia.out = list_of(h, 1); ia.n = h->d_n + 1; ia.cap = h->cap; ia.map = h->d_mapd;
   ia.nDop = (int)n_dop; ia.nDel = (int)n_del; ia.delay = h->d_delay; ia.doppler = h->d_doppler;
-  ia.noisePower = noise_power; ia.doDelay = h->p.interp_delay; ia.doDoppler = h->p.interp_doppler; ia.keep = h->d_keep;
+  ia.noisePower = noise_power; ia.noise_dev = nullptr; ia.doDelay = h->p.interp_delay; ia.doDoppler = h->p.interp_doppler; ia.keep = h->d_keep;
   interp_kernel<double2><<<148, kBlock, 0, st>>>(ia);
   B2_LAUNCH_CHECK();
   CompactArgs co;

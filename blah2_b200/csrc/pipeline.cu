@@ -1,0 +1,227 @@
+// pipeline.cu -- one CPI through WienerHopf -> Ambiguity -> set_metrics -> detection with all
+// intermediates resident in HBM (the body of the reference's process thread, src/blah2.cpp:268-287).
+// Composes the per-class handles of caf.cu / wh.cu / det.cu through their C ABI; the only kernels
+// defined here are the complex128 <-> complex64 conversions of the host entry point.
+#include "common.cuh"
+
+#include <new>
+#include <vector>
+
+using namespace b2;
+
+namespace {
+
+__global__ void pl_narrow_kernel(const double2 *__restrict__ in, float2 *__restrict__ out, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double2 v = in[i];
+    out[i] = make_float2((float)v.x, (float)v.y);
+  }
+}
+
+__global__ void pl_widen_kernel(const float2 *__restrict__ in, double2 *__restrict__ out, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float2 f = in[i];
+    out[i] = make_double2((double)f.x, (double)f.y);
+  }
+}
+
+inline int grid_for(uint32_t n) {
+  int b = (int)((n + 255u) / 256u);
+  return b > 148 * 8 ? 148 * 8 : (b < 1 ? 1 : b);
+}
+
+}  // namespace
+
+struct b200dd_pipeline {
+  b200dd_pipeline_params p;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  b200dd_caf *caf = nullptr;
+  b200dd_wh *wh = nullptr;
+  b200dd_det *det = nullptr;
+  b200dd_caf_geometry g;
+  std::vector<int32_t> delay;
+  std::vector<double> doppler;
+  float2 *d_yf = nullptr;                    // filtered surveillance channel (device path)
+  double2 *d_xd = nullptr, *d_yd = nullptr;  // host path staging
+  float2 *d_xf = nullptr, *d_yf2 = nullptr;
+  double2 *d_mapd = nullptr;
+  float2 *d_map = nullptr;
+  bool last_had_filter = false;
+};
+
+extern "C" {
+
+int b200dd_pipeline_create(const b200dd_pipeline_params *params, b200dd_pipeline **out) {
+  if (!params || !out) return arg_fail("b200dd_pipeline_create: null argument");
+  *out = nullptr;
+  b200dd_pipeline *h = new (std::nothrow) b200dd_pipeline();
+  if (!h) return arg_fail("b200dd_pipeline_create: out of host memory");
+  h->p = *params;
+  auto fail = [&](int rc) { b200dd_pipeline_destroy(h); return rc; };
+  int dev = params->caf.device;
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaGetDevice", __FILE__, __LINE__));
+  h->device = dev;
+  DeviceGuard guard(dev);
+  if (!guard.ok) return fail(cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__));
+  b200dd_caf_params cp = params->caf;
+  cp.device = dev;
+  int rc = b200dd_caf_create(&cp, &h->caf);
+  if (rc != B200DD_OK) return fail(rc);
+  b200dd_caf_get_geometry(h->caf, &h->g);
+  h->delay.resize(h->g.n_delay_bins);
+  h->doppler.resize(h->g.n_doppler_bins);
+  b200dd_caf_get_axes(h->caf, h->delay.data(), h->doppler.data());
+  if (params->clutter_enable) {
+    rc = b200dd_wh_create(params->clutter_delay_min, params->clutter_delay_max, params->caf.n_samples, dev, &h->wh);
+    if (rc != B200DD_OK) return fail(rc);
+  }
+  b200dd_det_params dp = params->det;
+  dp.device = dev;
+  rc = b200dd_det_create(&dp, h->g.n_doppler_bins, h->g.n_delay_bins, &h->det);  // also serves set_metrics
+  if (rc != B200DD_OK) return fail(rc);
+  auto body = [&]() -> int {
+    B2_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    B2_CUDA(cudaMalloc(&h->d_map, sizeof(float2) * (size_t)h->g.n_doppler_bins * h->g.n_delay_bins));
+    if (h->wh) B2_CUDA(cudaMalloc(&h->d_yf, sizeof(float2) * params->caf.n_samples));
+    return B200DD_OK;
+  };
+  rc = body();
+  if (rc != B200DD_OK) return fail(rc);
+  *out = h;
+  return B200DD_OK;
+}
+
+void b200dd_pipeline_destroy(b200dd_pipeline *h) {
+  if (!h) return;
+  {
+    DeviceGuard guard(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    b200dd_caf_destroy(h->caf);
+    b200dd_wh_destroy(h->wh);
+    b200dd_det_destroy(h->det);
+    free_dev(h->d_yf);
+    free_dev(h->d_xd);
+    free_dev(h->d_yd);
+    free_dev(h->d_xf);
+    free_dev(h->d_yf2);
+    free_dev(h->d_mapd);
+    free_dev(h->d_map);
+    if (h->stream) cudaStreamDestroy(h->stream);
+  }
+  delete h;
+}
+
+int b200dd_pipeline_get_geometry(const b200dd_pipeline *h, b200dd_caf_geometry *out) {
+  if (!h || !out) return arg_fail("b200dd_pipeline_get_geometry: null argument");
+  *out = h->g;
+  return B200DD_OK;
+}
+
+int b200dd_pipeline_get_axes(const b200dd_pipeline *h, int32_t *delay, double *doppler) {
+  if (!h) return arg_fail("b200dd_pipeline_get_axes: null handle");
+  return b200dd_caf_get_axes(h->caf, delay, doppler);
+}
+
+void *b200dd_pipeline_stream(b200dd_pipeline *h) { return h ? (void *)h->stream : nullptr; }
+
+int b200dd_pipeline_submit_device(b200dd_pipeline *h, const void *d_x, const void *d_y, uint32_t n, void *d_map,
+                                  void *stream) {
+  if (!h || !d_x || !d_y) return arg_fail("b200dd_pipeline_submit_device: null argument");
+  if (h->wh && n != h->p.caf.n_samples) return arg_fail("b200dd_pipeline_submit_device: the clutter filter needs exactly n_samples");
+  DeviceGuard guard(h->device);
+  void *st = stream ? stream : (void *)h->stream;
+  const void *y = d_y;
+  int rc;
+  if (h->wh) {
+    rc = b200dd_wh_process_device(h->wh, d_x, d_y, h->d_yf, st);  // failed solve -> y passes through
+    if (rc != B200DD_OK) return rc;
+    y = h->d_yf;
+  }
+  h->last_had_filter = h->wh != nullptr;
+  float2 *map = d_map ? (float2 *)d_map : h->d_map;
+  rc = b200dd_caf_process_device(h->caf, d_x, y, n, map, st);
+  if (rc != B200DD_OK) return rc;
+  const int last = h->p.detection_enable ? B200DD_DET_INTERPOLATE : 0;
+  if (last) {
+    rc = b200dd_det_chain_device_async(h->det, last, map, h->g.n_doppler_bins, h->g.n_delay_bins, h->delay.data(),
+                                       h->doppler.data(), st);
+    if (rc != B200DD_OK) return rc;
+  }
+  return B200DD_OK;
+}
+
+int b200dd_pipeline_fetch(b200dd_pipeline *h, b200dd_cpi_result *result, double *o_delay, double *o_doppler,
+                          double *o_snr, uint32_t cap, void *stream) {
+  if (!h || !result) return arg_fail("b200dd_pipeline_fetch: null argument");
+  DeviceGuard guard(h->device);
+  void *st = stream ? stream : (void *)h->stream;
+  result->filter_status = B200DD_OK;
+  result->n_detections = 0;
+  result->noise_power = 0.0;
+  result->max_power = 0.0;
+  int rc = B200DD_OK;
+  if (h->p.detection_enable) {
+    double metrics[2] = {0.0, 0.0};
+    uint32_t n = 0;
+    rc = b200dd_det_chain_fetch(h->det, metrics, o_delay, o_doppler, o_snr, cap, &n, st);
+    result->n_detections = n;
+    result->noise_power = metrics[0];
+    result->max_power = metrics[1];
+  } else {
+    B2_CUDA(cudaStreamSynchronize((cudaStream_t)st));
+  }
+  if (h->last_had_filter) {
+    int s = 0;
+    B2_CUDA(cudaMemcpy(&s, b200dd_wh_device_status(h->wh), sizeof(int), cudaMemcpyDeviceToHost));
+    if (s != 0) result->filter_status = B200DD_FILTER_FAILED;
+  }
+  return rc;
+}
+
+int b200dd_pipeline_process_host(b200dd_pipeline *h, const double *x, const double *y, uint32_t n, double *map_out,
+                                 b200dd_cpi_result *result, double *o_delay, double *o_doppler, double *o_snr,
+                                 uint32_t cap) {
+  if (!h || !x || !y || !result) return arg_fail("b200dd_pipeline_process_host: null argument");
+  const uint32_t N = h->p.caf.n_samples;
+  const uint32_t need = h->wh ? N : h->g.n_used;
+  if (h->wh ? (n != N) : (n < need)) return arg_fail("b200dd_pipeline_process_host: wrong number of samples");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = h->stream;
+  if (!h->d_xd) {
+    B2_CUDA(cudaMalloc(&h->d_xd, sizeof(double2) * N));
+    B2_CUDA(cudaMalloc(&h->d_yd, sizeof(double2) * N));
+    B2_CUDA(cudaMalloc(&h->d_xf, sizeof(float2) * N));
+    B2_CUDA(cudaMalloc(&h->d_yf2, sizeof(float2) * N));
+    B2_CUDA(cudaMalloc(&h->d_mapd, sizeof(double2) * (size_t)h->g.n_doppler_bins * h->g.n_delay_bins));
+  }
+  B2_CUDA(cudaMemcpyAsync(h->d_xd, x, sizeof(double2) * need, cudaMemcpyHostToDevice, st));
+  B2_CUDA(cudaMemcpyAsync(h->d_yd, y, sizeof(double2) * need, cudaMemcpyHostToDevice, st));
+  int rc;
+  if (h->wh) {
+    // the filter sees the caller's complex128 samples unrounded (FP64 kernels, in place)
+    rc = b200dd_wh_process_device_f64(h->wh, h->d_xd, h->d_yd, h->d_yd, st);
+    if (rc != B200DD_OK) return rc;
+  }
+  h->last_had_filter = h->wh != nullptr;
+  pl_narrow_kernel<<<grid_for(need), 256, 0, st>>>(h->d_xd, h->d_xf, need);
+  B2_LAUNCH_CHECK();
+  pl_narrow_kernel<<<grid_for(need), 256, 0, st>>>(h->d_yd, h->d_yf2, need);
+  B2_LAUNCH_CHECK();
+  rc = b200dd_caf_process_device(h->caf, h->d_xf, h->d_yf2, need, h->d_map, st);
+  if (rc != B200DD_OK) return rc;
+  if (h->p.detection_enable) {
+    rc = b200dd_det_chain_device_async(h->det, B200DD_DET_INTERPOLATE, h->d_map, h->g.n_doppler_bins,
+                                       h->g.n_delay_bins, h->delay.data(), h->doppler.data(), st);
+    if (rc != B200DD_OK) return rc;
+  }
+  if (map_out) {
+    const uint32_t cells = h->g.n_doppler_bins * h->g.n_delay_bins;
+    pl_widen_kernel<<<grid_for(cells), 256, 0, st>>>(h->d_map, h->d_mapd, cells);
+    B2_LAUNCH_CHECK();
+    B2_CUDA(cudaMemcpyAsync(map_out, h->d_mapd, sizeof(double2) * cells, cudaMemcpyDeviceToHost, st));
+  }
+  return b200dd_pipeline_fetch(h, result, o_delay, o_doppler, o_snr, cap, st);
+}
+
+}  // extern "C"

@@ -396,7 +396,8 @@ namespace {
 template <int LOG2M> size_t corr_smem() { return (size_t)(Plan<LOG2M>::MP + 2 * Plan<LOG2M>::M) * sizeof(double2); }
 template <int LOG2M> size_t fft_smem() { return (size_t)Plan<LOG2M>::MP * sizeof(double2); }
 
-template <int LOG2M, class TIN> int wh_launch_all(b200dd_wh *h, const void *x, const void *y, void *y_out, cudaStream_t st) {
+template <int LOG2M, class TIN> int wh_launch_all(b200dd_wh *h, const void *x, const void *y, void *y_out, cudaStream_t st,
+                                                  cudaEvent_t *ev) {
   using P = Plan<LOG2M>;
   const size_t solve_smem = (size_t)5 * h->nBins * sizeof(double2);
   bool &done = sizeof(typename std::remove_pointer<decltype(TIN::x) *>::type) == 4 ? h->attr_f32 : h->attr_f64;
@@ -410,13 +411,16 @@ template <int LOG2M, class TIN> int wh_launch_all(b200dd_wh *h, const void *x, c
   CorrArgs ca;
   ca.x = x; ca.y = y; ca.partial = h->d_partial; ca.tw = h->d_tw; ca.N = h->N; ca.delayMin = h->delayMin;
   ca.nBins = h->nBins; ca.L = h->L; ca.nSegTotal = h->nSeg; ca.segPerCta = h->segPerCta;
+  if (ev) B2_CUDA(cudaEventRecord(ev[0], st));
   wh_corr_kernel<LOG2M, TIN><<<h->gridCorr, P::NT, corr_smem<LOG2M>(), st>>>(ca);
   B2_LAUNCH_CHECK();
+  if (ev) B2_CUDA(cudaEventRecord(ev[1], st));
   SolveArgs sa;
   sa.partial = h->d_partial; sa.nPartial = h->gridCorr; sa.nBins = h->nBins;
   sa.a_out = h->d_a; sa.b_out = h->d_b; sa.w_out = h->d_w; sa.status = h->d_status;
   wh_solve_kernel<<<1, kSolveThreads, solve_smem, st>>>(sa);
   B2_LAUNCH_CHECK();
+  if (ev) B2_CUDA(cudaEventRecord(ev[2], st));
   wh_wspec_kernel<LOG2M><<<1, P::NT, fft_smem<LOG2M>(), st>>>(h->d_w, h->nBins, h->d_what, h->d_tw);
   B2_LAUNCH_CHECK();
   ApplyArgs aa;
@@ -424,15 +428,17 @@ template <int LOG2M, class TIN> int wh_launch_all(b200dd_wh *h, const void *x, c
   aa.N = h->N; aa.delayMin = h->delayMin; aa.nBins = h->nBins; aa.Lout = h->Lout;
   wh_apply_kernel<LOG2M, TIN><<<h->gridApply, P::NT, fft_smem<LOG2M>(), st>>>(aa);
   B2_LAUNCH_CHECK();
+  if (ev) B2_CUDA(cudaEventRecord(ev[3], st));
   return B200DD_OK;
 }
 
-template <class TIN> int wh_dispatch(b200dd_wh *h, const void *x, const void *y, void *y_out, cudaStream_t st) {
+template <class TIN> int wh_dispatch(b200dd_wh *h, const void *x, const void *y, void *y_out, cudaStream_t st,
+                                     cudaEvent_t *ev = nullptr) {
   switch (h->log2m) {
-    case 9: return wh_launch_all<9, TIN>(h, x, y, y_out, st);
-    case 10: return wh_launch_all<10, TIN>(h, x, y, y_out, st);
-    case 11: return wh_launch_all<11, TIN>(h, x, y, y_out, st);
-    case 12: return wh_launch_all<12, TIN>(h, x, y, y_out, st);
+    case 9: return wh_launch_all<9, TIN>(h, x, y, y_out, st, ev);
+    case 10: return wh_launch_all<10, TIN>(h, x, y, y_out, st, ev);
+    case 11: return wh_launch_all<11, TIN>(h, x, y, y_out, st, ev);
+    case 12: return wh_launch_all<12, TIN>(h, x, y, y_out, st, ev);
   }
   return geom_fail("WienerHopf FFT length out of range");
 }
@@ -543,6 +549,33 @@ int b200dd_wh_process_device(b200dd_wh *h, const void *d_x, const void *d_y, voi
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   return wh_dispatch<float2>(h, d_x, d_y, d_y_out, st);
 }
+
+int b200dd_wh_process_device_f64(b200dd_wh *h, const void *d_x, const void *d_y, void *d_y_out, void *stream) {
+  if (!h || !d_x || !d_y || !d_y_out) return arg_fail("b200dd_wh_process_device_f64: null argument");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  return wh_dispatch<double2>(h, d_x, d_y, d_y_out, st);
+}
+
+int b200dd_wh_profile_device(b200dd_wh *h, const void *d_x, const void *d_y, void *d_y_out, void *stream,
+                             float *ms_corr, float *ms_solve, float *ms_apply) {
+  if (!h || !d_x || !d_y || !d_y_out || !ms_corr || !ms_solve || !ms_apply) return arg_fail("b200dd_wh_profile_device: null argument");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  cudaEvent_t ev[4];
+  for (int i = 0; i < 4; i++) B2_CUDA(cudaEventCreate(&ev[i]));
+  int rc = wh_dispatch<float2>(h, d_x, d_y, d_y_out, st, ev);
+  if (rc == B200DD_OK) {
+    B2_CUDA(cudaEventSynchronize(ev[3]));
+    B2_CUDA(cudaEventElapsedTime(ms_corr, ev[0], ev[1]));
+    B2_CUDA(cudaEventElapsedTime(ms_solve, ev[1], ev[2]));
+    B2_CUDA(cudaEventElapsedTime(ms_apply, ev[2], ev[3]));  // weight spectrum + overlap-save filter
+  }
+  for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
+  return rc;
+}
+
+const int *b200dd_wh_device_status(b200dd_wh *h) { return h ? h->d_status : nullptr; }
 
 int b200dd_wh_last_status(b200dd_wh *h) {
   if (!h) return arg_fail("b200dd_wh_last_status: null handle");

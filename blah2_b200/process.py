@@ -115,6 +115,14 @@ class Ambiguity:
         capi.check(self._lib.b200dd_caf_process_device(self._h, capi.ptr(d_x), capi.ptr(d_y), int(n),
                                                        capi.ptr(d_map), capi.ptr(stream) if stream else None))
 
+    def profile_device(self, d_x, d_y, d_map=None, stream=None):
+        """(ms_range, ms_doppler): CUDA-event durations of the two CAF kernels for one CPI."""
+        a, b = C.c_float(), C.c_float()
+        n = d_x.numel() if hasattr(d_x, "numel") else self.geometry.n_used
+        capi.check(self._lib.b200dd_caf_profile_device(self._h, capi.ptr(d_x), capi.ptr(d_y), int(n), capi.ptr(d_map),
+                                                       capi.ptr(stream) if stream else None, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def debug_range_matrix(self):
         g = self.geometry
         out = np.empty((g.n_doppler_bins, g.n_delay_bins), dtype=np.complex64)
@@ -165,6 +173,14 @@ class WienerHopf:
         out = d_y if d_y_out is None else d_y_out
         capi.check(self._lib.b200dd_wh_process_device(self._h, capi.ptr(d_x), capi.ptr(d_y), capi.ptr(out),
                                                       capi.ptr(stream) if stream else None))
+
+    def profile_device(self, d_x, d_y, d_y_out, stream=None):
+        """(ms_corr, ms_solve, ms_apply): CUDA-event durations of the filter's stages."""
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        capi.check(self._lib.b200dd_wh_profile_device(self._h, capi.ptr(d_x), capi.ptr(d_y), capi.ptr(d_y_out),
+                                                      capi.ptr(stream) if stream else None, C.byref(a), C.byref(b),
+                                                      C.byref(c)))
+        return a.value, b.value, c.value
 
     def last_status(self) -> bool:
         rc = capi.check(self._lib.b200dd_wh_last_status(self._h), allow=(capi.FILTER_FAILED,))
@@ -323,3 +339,79 @@ def set_metrics(m: Map) -> Map:
     torch.cuda.synchronize()
     d.close()
     return m
+
+
+class Pipeline:
+    """One CPI through the body of the reference's process thread (src/blah2.cpp:268-287):
+    [WienerHopf] -> Ambiguity -> Map::set_metrics -> [CfarDetector1D -> Centroid -> Interpolate],
+    intermediates resident on the device.  Parameters are named like config/config.yml."""
+
+    def __init__(self, delayMin, delayMax, dopplerMin, dopplerMax, fs, nSamples, roundHamming=True, clutter=None,
+                 detection=None, device=-1, max_detections=4096):
+        lib = capi.load()
+        p = capi.PipelineParams()
+        p.caf = capi.CafParams(int(delayMin), int(delayMax), int(dopplerMin), int(dopplerMax), int(fs),
+                               int(nSamples), int(bool(roundHamming)), int(device))
+        p.clutter_enable = int(clutter is not None)
+        if clutter is not None:
+            p.clutter_delay_min, p.clutter_delay_max = int(clutter[0]), int(clutter[1])
+        p.detection_enable = int(detection is not None)
+        d = detection or {}
+        tcpi = float(nSamples) / float(fs)
+        p.det = capi.DetParams(float(d.get("pfa", 1e-5)), int(d.get("nGuard", 2)), int(d.get("nTrain", 6)),
+                               int(d.get("minDelay", 5)), float(d.get("minDoppler", 15.0)),
+                               int(d.get("nCentroid", 6)), int(d.get("nCentroid", 6)), 1.0 / tcpi, 1, 1, int(device))
+        h = C.c_void_p()
+        capi.check(lib.b200dd_pipeline_create(C.byref(p), C.byref(h)))
+        self._lib, self._h = lib, h
+        g = capi.CafGeometry()
+        capi.check(lib.b200dd_pipeline_get_geometry(h, C.byref(g)))
+        self.geometry = g
+        self.delay = np.empty(g.n_delay_bins, dtype=np.int32)
+        self.doppler = np.empty(g.n_doppler_bins, dtype=np.float64)
+        capi.check(lib.b200dd_pipeline_get_axes(h, capi.ptr(self.delay), capi.ptr(self.doppler)))
+        self.cap = int(max_detections)
+        self._od, self._of, self._os = (np.empty(self.cap, dtype=np.float64) for _ in range(3))
+        self.n_samples = int(nSamples)
+
+    def _result(self, res, want_map_arr=None):
+        k = min(res.n_detections, self.cap)
+        det = Detection(self._od[:k].copy(), self._of[:k].copy(), self._os[:k].copy())
+        return dict(skipped=res.filter_status != capi.OK, noisePower=res.noise_power, maxPower=res.max_power,
+                    detections=det, map=want_map_arr)
+
+    def process(self, x, y, want_map=True, map_out=None):
+        """Host path: complex128 arrays (pinned torch tensors / numpy).  Synchronous."""
+        g = self.geometry
+        if map_out is None and want_map:
+            map_out = np.empty((g.n_doppler_bins, g.n_delay_bins), dtype=np.complex128)
+        n = x.numel() if hasattr(x, "numel") else x.shape[0]
+        res = capi.CpiResult()
+        capi.check(self._lib.b200dd_pipeline_process_host(self._h, capi.ptr(x), capi.ptr(y), int(n),
+                                                          capi.ptr(map_out) if map_out is not None else None,
+                                                          C.byref(res), capi.ptr(self._od), capi.ptr(self._of),
+                                                          capi.ptr(self._os), self.cap), allow=(capi.ERR_CAPACITY,))
+        return self._result(res, map_out)
+
+    def submit_device(self, d_x, d_y, d_map=None, stream=None):
+        n = d_x.numel() if hasattr(d_x, "numel") else self.n_samples
+        capi.check(self._lib.b200dd_pipeline_submit_device(self._h, capi.ptr(d_x), capi.ptr(d_y), int(n),
+                                                           capi.ptr(d_map), capi.ptr(stream) if stream else None))
+
+    def fetch(self, stream=None):
+        res = capi.CpiResult()
+        capi.check(self._lib.b200dd_pipeline_fetch(self._h, C.byref(res), capi.ptr(self._od), capi.ptr(self._of),
+                                                   capi.ptr(self._os), self.cap,
+                                                   capi.ptr(stream) if stream else None), allow=(capi.ERR_CAPACITY,))
+        return self._result(res)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200dd_pipeline_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

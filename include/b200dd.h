@@ -120,6 +120,12 @@ B200DD_API int b200dd_caf_process_host(b200dd_caf *h, const double *x, const dou
 B200DD_API int b200dd_caf_process_device(b200dd_caf *h, const void *d_x, const void *d_y, uint32_t n, void *d_map,
                               void *stream);
 
+/* Profiling aid: same as b200dd_caf_process_device but brackets the range-correlation kernel and the
+ * Doppler kernel with CUDA events on the launching stream and returns their durations (ms).
+ * Synchronises the stream.  Used by bench.py for the roofline figures. */
+B200DD_API int b200dd_caf_profile_device(b200dd_caf *h, const void *d_x, const void *d_y, uint32_t n, void *d_map,
+                                         void *stream, float *ms_range, float *ms_doppler);
+
 /* Intermediate range matrix of the last process call (row i = batch i, nDelayBins lags;
  * Ambiguity.cpp:106-149) copied to host as complex64 -- parity tests only. */
 B200DD_API int b200dd_caf_debug_range_matrix(b200dd_caf *h, float *out);
@@ -150,6 +156,14 @@ B200DD_API int b200dd_wh_process_host(b200dd_wh *h, const double *x, double *y);
  * b200dd_wh_last_status() (synchronises the stream) to read it. */
 B200DD_API int b200dd_wh_process_device(b200dd_wh *h, const void *d_x, const void *d_y, void *d_y_out, void *stream);
 B200DD_API int b200dd_wh_last_status(b200dd_wh *h);
+/* Same with complex128 device buffers (double2) in and out -- what the host path and the
+ * pipeline's host entry use so that the filter sees the caller's doubles unrounded. */
+B200DD_API int b200dd_wh_process_device_f64(b200dd_wh *h, const void *d_x, const void *d_y, void *d_y_out, void *stream);
+/* Profiling aid: per-stage CUDA-event durations (ms) of correlation, solve, and weight-spectrum+filter. */
+B200DD_API int b200dd_wh_profile_device(b200dd_wh *h, const void *d_x, const void *d_y, void *d_y_out, void *stream,
+                                        float *ms_corr, float *ms_solve, float *ms_apply);
+/* Device address of the status word (0 ok, 1 failed) for kernels chained after the filter. */
+B200DD_API const int *b200dd_wh_device_status(b200dd_wh *h);
 /* Filter weights w[nBins] / correlations a, b of the last call as complex128 -- parity tests. */
 B200DD_API int b200dd_wh_debug_weights(b200dd_wh *h, double *w, double *a, double *b);
 B200DD_API uint32_t b200dd_wh_n_bins(const b200dd_wh *h);
@@ -195,6 +209,15 @@ B200DD_API int b200dd_det_process_device(b200dd_det *h, int last_stage, const vo
                               const int32_t *delay, const double *doppler, double noise_power, double *o_delay,
                               double *o_doppler, double *o_snr, uint32_t cap, uint32_t *n_out, void *stream);
 
+/* Fully asynchronous variant for device-resident streams of CPIs: Map::set_metrics is evaluated
+ * on the device first (blah2.cpp:279) and its noisePower feeds the detector without a host round
+ * trip; nothing is copied back until b200dd_det_chain_fetch (which synchronises the stream). */
+B200DD_API int b200dd_det_chain_device_async(b200dd_det *h, int last_stage, const void *d_map, uint32_t n_dop,
+                                             uint32_t n_del, const int32_t *delay, const double *doppler,
+                                             void *stream);
+B200DD_API int b200dd_det_chain_fetch(b200dd_det *h, double *metrics, double *o_delay, double *o_doppler,
+                                      double *o_snr, uint32_t cap, uint32_t *n_out, void *stream);
+
 /* Same on a HOST complex128 map (what the drop-in classes hold in Map::data). */
 B200DD_API int b200dd_det_process_host(b200dd_det *h, int last_stage, const double *map, uint32_t n_dop, uint32_t n_del,
                             const int32_t *delay, const double *doppler, double noise_power, double *o_delay,
@@ -208,6 +231,53 @@ B200DD_API int b200dd_det_interpolate_host(b200dd_det *h, const double *delay, c
                                 uint32_t n, const double *map, uint32_t n_dop, uint32_t n_del, const int32_t *mdelay,
                                 const double *mdoppler, double noise_power, double *o_delay, double *o_doppler,
                                 double *o_snr, uint32_t cap, uint32_t *n_out);
+
+/* ------------------------------------------------------------------ whole CPI pipeline
+ *
+ * One coherent-processing interval through the body of the reference's process thread
+ * (src/blah2.cpp:268-287): [WienerHopf::process] -> Ambiguity::process -> Map::set_metrics ->
+ * [CfarDetector1D -> Centroid -> Interpolate], with every intermediate (filtered surveillance
+ * channel, range matrix, map, detection lists) staying in device memory.  The per-class entry
+ * points above remain the drop-in boundary; this is the path a maintainer takes when the caller
+ * can hand over a whole CPI at once (INTEGRATION.md "fast path").
+ */
+typedef struct b200dd_pipeline b200dd_pipeline;
+
+typedef struct {
+  b200dd_caf_params caf;
+  int32_t clutter_enable;     /* process.clutter.enable   (config/config.yml:28-32) */
+  int32_t clutter_delay_min;
+  int32_t clutter_delay_max;
+  int32_t detection_enable;   /* process.detection.enable (config/config.yml:33-40) */
+  b200dd_det_params det;      /* det.resolution_doppler = 1 / tCpi as blah2.cpp:183 passes it */
+} b200dd_pipeline_params;
+
+typedef struct {
+  int32_t filter_status;   /* B200DD_OK, or B200DD_FILTER_FAILED: CPI skipped like blah2.cpp:270-273 */
+  uint32_t n_detections;
+  double noise_power;      /* Map::noisePower */
+  double max_power;        /* Map::maxPower   */
+} b200dd_cpi_result;
+
+B200DD_API int b200dd_pipeline_create(const b200dd_pipeline_params *params, b200dd_pipeline **out);
+B200DD_API void b200dd_pipeline_destroy(b200dd_pipeline *h);
+B200DD_API int b200dd_pipeline_get_geometry(const b200dd_pipeline *h, b200dd_caf_geometry *out);
+B200DD_API int b200dd_pipeline_get_axes(const b200dd_pipeline *h, int32_t *delay, double *doppler);
+
+/* HOST buffers: x, y = n complex128 samples (n == n_samples when the clutter filter is enabled,
+ * >= n_used otherwise).  map_out (nullable) = [nDop][nDel] complex128.  Detections into the three
+ * arrays (capacity cap).  Synchronous: returns when the results are in host memory. */
+B200DD_API int b200dd_pipeline_process_host(b200dd_pipeline *h, const double *x, const double *y, uint32_t n,
+                                            double *map_out, b200dd_cpi_result *result, double *o_delay,
+                                            double *o_doppler, double *o_snr, uint32_t cap);
+
+/* DEVICE buffers (float2), asynchronous on `stream` (NULL = the pipeline's stream).  d_map
+ * (nullable) receives the float2 map.  Results stay on the device until b200dd_pipeline_fetch. */
+B200DD_API int b200dd_pipeline_submit_device(b200dd_pipeline *h, const void *d_x, const void *d_y, uint32_t n,
+                                             void *d_map, void *stream);
+B200DD_API int b200dd_pipeline_fetch(b200dd_pipeline *h, b200dd_cpi_result *result, double *o_delay,
+                                     double *o_doppler, double *o_snr, uint32_t cap, void *stream);
+B200DD_API void *b200dd_pipeline_stream(b200dd_pipeline *h);
 
 #ifdef __cplusplus
 }

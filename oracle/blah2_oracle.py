@@ -209,8 +209,12 @@ def wienerhopf_weights(x: np.ndarray, y: np.ndarray, delayMin: int, delayMax: in
     y = np.asarray(y, dtype=np.complex128)
     N = x.shape[0]
     nBins = int(delayMax) - int(delayMin)
-    # :65-69  dataX[i] = x[(i - delayMin) mod N] (uint32 arithmetic; exact for delayMin <= 0)
-    xs = x[(np.arange(N, dtype=np.int64) - int(delayMin)) % N]
+    # :65-69  dataX[i] = xData[(((i - delayMin) % nSamples) + nSamples) % nSamples] with i uint32_t and
+    # delayMin int32_t: the subtraction is done in uint32 (wraps modulo 2^32).  For delayMin <= 0 that
+    # is the circular shift x[(i + |delayMin|) mod N]; for delayMin > 0 the first delayMin samples
+    # come from index (2^32 - (delayMin - i)) mod N -- reproduced literally.
+    t = (np.arange(N, dtype=np.int64) - int(delayMin)) % (1 << 32)
+    xs = x[((t % N) + N) % N]
     ys = y
     X = np.fft.fft(xs)  # :72
     Y = np.fft.fft(ys)  # :73

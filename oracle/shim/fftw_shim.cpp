@@ -220,7 +220,7 @@ void fftw_plan_with_nthreads(int) {}
 void fftw_cleanup_threads(void) {}
 
 // Direct entry for tests of the shim itself (not part of FFTW's API).
-void b200dd_shim_fft(int n, const double *in, double *out, int sign) {
+__attribute__((visibility("default"))) void b200dd_shim_fft(int n, const double *in, double *out, int sign) {
   Fft f(n, sign < 0 ? -1 : +1);
   f.exec(reinterpret_cast<const cd *>(in), reinterpret_cast<cd *>(out));
 }

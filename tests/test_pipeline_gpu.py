@@ -1,0 +1,97 @@
+"""GPU: the whole-CPI pipeline (C ABI b200dd_pipeline_*) against golden fixtures and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from blah2_b200.process import Pipeline, Ambiguity, WienerHopf
+from blah2_b200.scene import make_scene, random_iq, Target
+from oracle import blah2_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+@pytest.mark.parametrize("name", ["caf_a", "caf_b", "caf_c"])
+def test_cuda_ambiguity_vs_reference_golden(name, relerr):
+    d = gold(name)
+    geom = tuple(int(v) for v in d["geom"][:6]) + (bool(d["geom"][6]),)
+    x, y = random_iq(geom[5], int(d["seed"]))
+    m = Ambiguity(*geom).process(x, y)
+    e = relerr(m.data, d["map"])
+    assert e[0] < 1e-5 and e[1] < 1e-5, e
+    assert np.array_equal(m.delay, d["delay"]) and np.array_equal(m.doppler, d["doppler"])
+
+
+@pytest.mark.parametrize("name", ["wh_a", "wh_b"])
+def test_cuda_wienerhopf_vs_reference_golden(name, relerr):
+    d = gold(name)
+    n, dm, dM, seed = (int(v) for v in d["params"])
+    sc = make_scene(n, 2e6, seed=seed, targets=[Target(25, 300.0, -40.0)])
+    ok, y = WienerHopf(dm, dM, n).process(sc.x, sc.y)
+    assert ok == bool(d["ok"])
+    assert relerr(y, d["y"])[0] < 1e-9
+
+
+def _chain_fixture():
+    d = gold("chain_a")
+    geom = tuple(int(v) for v in d["geom"][:6]) + (bool(d["geom"][6]),)
+    pfa, nGuard, nTrain, minDelay, minDoppler, nCentroid = d["det"]
+    det = dict(pfa=float(pfa), nGuard=int(nGuard), nTrain=int(nTrain), minDelay=int(minDelay),
+               minDoppler=float(minDoppler), nCentroid=int(nCentroid))
+    sc = make_scene(geom[5], geom[4], seed=int(d["seed"]), targets=[Target(17, 300.0, -25.0), Target(41, -200.0, -28.0)])
+    return d, geom, det, sc
+
+
+def test_pipeline_host_vs_reference_golden(relerr):
+    d, geom, det, sc = _chain_fixture()
+    pipe = Pipeline(*geom[:6], roundHamming=True, clutter=tuple(int(v) for v in d["clutter"]), detection=det)
+    out = pipe.process(sc.x, sc.y)
+    assert not out["skipped"]
+    e = relerr(out["map"], d["map"])
+    assert e[0] < 1e-5 and e[1] < 1e-5, e
+    assert abs(out["noisePower"] - d["metrics"][0]) < 1e-3 and abs(out["maxPower"] - d["metrics"][1]) < 1e-3
+    det_ref = d["interp"]
+    got = out["detections"]
+    assert got.get_nDetections() == det_ref.shape[1]
+    assert np.max(np.abs(got.delay - det_ref[0])) < 1e-3
+    assert np.max(np.abs(got.doppler - det_ref[1])) < 1e-3 * abs(d["doppler"][1] - d["doppler"][0]) + 1e-6
+    assert np.max(np.abs(got.snr - det_ref[2])) < 1e-3
+
+
+def test_pipeline_device_path_matches_host_path(relerr):
+    import torch
+    d, geom, det, sc = _chain_fixture()
+    pipe = Pipeline(*geom[:6], roundHamming=True, clutter=tuple(int(v) for v in d["clutter"]), detection=det)
+    host = pipe.process(sc.x, sc.y)
+    dx = torch.from_numpy(sc.x.astype(np.complex64)).cuda()
+    dy = torch.from_numpy(sc.y.astype(np.complex64)).cuda()
+    dmap = torch.empty((pipe.geometry.n_doppler_bins, pipe.geometry.n_delay_bins), dtype=torch.complex64, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(3):   # back-to-back submissions reuse the handle's buffers
+            pipe.submit_device(dx, dy, dmap, s.cuda_stream)
+        dev = pipe.fetch(s.cuda_stream)
+    assert relerr(dmap.cpu().numpy().astype(np.complex128), host["map"])[0] < 1e-5
+    assert dev["detections"].get_nDetections() == host["detections"].get_nDetections()
+    assert abs(dev["noisePower"] - host["noisePower"]) < 1e-3
+
+
+def test_pipeline_without_clutter_or_detection(relerr):
+    geom = (-3, 20, -50, 50, 10000, 4000)
+    x, y = random_iq(geom[5], 1)
+    out = Pipeline(*geom, roundHamming=False).process(x, y)
+    ref, _, _ = O.ambiguity_process(x, y, O.ambiguity_geometry(*geom, False))
+    assert relerr(out["map"], ref)[0] < 1e-5
+    assert out["detections"].get_nDetections() == 0 and not out["skipped"]
+
+
+def test_pipeline_filter_failure_is_reported():
+    n = 8192
+    pipe = Pipeline(-3, 20, -50, 50, 10000, n, clutter=(-2, 10), detection=None)
+    out = pipe.process(np.zeros(n, complex), np.ones(n, complex))
+    assert out["skipped"]
