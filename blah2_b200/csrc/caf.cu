@@ -104,9 +104,10 @@ void compute_geometry(const b200dd_caf_params &p, HostGeom &g) {
 struct RangeArgs {
   const float2 *x;
   const float2 *y;
-  float2 *R;         // [nDop][nDel]
+  float2 *R;         // [nParts][nDop][nDel] partial range matrices (summed by the Doppler kernel)
   const float2 *tw;  // exp(-2 pi i j / M)
   int nCorr, nDel, lagMin, nSeg, L;
+  int segPerPart, nDop;
 };
 
 // resident CTAs per SM the register allocator must leave room for (<= 128 regs/thread)
@@ -130,7 +131,12 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, range_min_ctas<LOG2M>()) caf_
 #pragma unroll
   for (int r = 0; r < 16; r++) Z[r] = zero;
 
-  for (int seg = 0; seg < a.nSeg; seg++) {
+  // blockIdx.y = part: a contiguous group of segments of this batch.  Splitting a batch over
+  // several CTAs buys occupancy for small CPIs (257 batches cannot fill 148 SMs); each part ends with
+  // its own inverse FFT and the parts are added, in a fixed order, by the Doppler kernel's loader.
+  const int seg0 = blockIdx.y * a.segPerPart;
+  const int seg1 = min(a.nSeg, seg0 + a.segPerPart);
+  for (int seg = seg0; seg < seg1; seg++) {
     const int n0 = seg * a.L;
     const int len = min(a.L, a.nCorr - n0);
     const int ylen = len + a.nDel - 1;   // window entries that can reach a wanted lag
@@ -142,7 +148,7 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, range_min_ctas<LOG2M>()) caf_
     };
     auto stA = [&](int i, float2 v) { A[pad(i)] = v; };
     auto stB = [&](int i, float2 v) { B[pad(i)] = v; };
-    if (seg > 0) __syncthreads();  // previous segment's last pass has finished reading A/B
+    if (seg > seg0) __syncthreads();  // previous segment's last pass has finished reading A/B
     if constexpr (P::R0 == 16) {
       fft_butterfly<float, 16, -1, LOG2M>(tid, P::log2S(0), a.tw, ldx, stA);
       fft_butterfly<float, 16, -1, LOG2M>(tid, P::log2S(0), a.tw, ldy, stB);
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, range_min_ctas<LOG2M>()) caf_
   }
   // final inverse pass: natural-order lag index m = delay bin; keep m < nDel only
   const float scale = 1.0f / (float)P::M;
-  float2 *__restrict__ Rrow = a.R + (size_t)batch * a.nDel;
+  float2 *__restrict__ Rrow = a.R + ((size_t)blockIdx.y * a.nDop + batch) * a.nDel;
   auto ldA = [&](int i) { return A[pad(i)]; };
   auto stR = [&](int m, float2 v) {
     if (m < a.nDel) Rrow[m] = make_float2(v.x * scale, v.y * scale);
@@ -190,7 +196,8 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, range_min_ctas<LOG2M>()) caf_
 }
 
 struct DopplerArgs {
-  const float2 *R;      // [nDop][nDel] range matrix
+  const float2 *R;      // [nParts][nDop][nDel] partial range matrices
+  int nParts;
   float2 *out;          // [nDop][nDel] map
   const float2 *chirp;  // exp(-i pi k^2 / nDop), k < nDop
   const float2 *bhat;   // FFT_M2 of the wrapped conj chirp, digit-reversed position order
@@ -208,7 +215,14 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT) caf_doppler_kernel(DopplerArg
   const int tid = threadIdx.x;
   const int col = blockIdx.x;
   const float2 zero = make_float2(0.f, 0.f);
-  auto ld0 = [&](int i) { return i < a.nDop ? cmul(__ldg(a.R + (size_t)i * a.nDel + col), __ldg(a.chirp + i)) : zero; };
+  const size_t plane = (size_t)a.nDop * a.nDel;
+  auto ld0 = [&](int i) {
+    if (i >= a.nDop) return zero;
+    const float2 *p = a.R + (size_t)i * a.nDel + col;
+    float2 r = __ldg(p);
+    for (int q = 1; q < a.nParts; q++) r = cadd(r, __ldg(p + q * plane));  // fixed order: deterministic
+    return cmul(r, __ldg(a.chirp + i));
+  };
   auto stA = [&](int i, float2 v) { A[pad(i)] = v; };
 #pragma unroll 1
   for (int b = tid; b < P::M / P::R0; b += P::NT) fft_butterfly<float, P::R0, -1, LOG2M>(b, P::log2S(0), a.tw, ld0, stA);
@@ -310,7 +324,7 @@ __global__ void caf_widen_kernel(const float2 *__restrict__ in, double2 *__restr
 
 // ------------------------------------------------------------------ launch dispatch
 
-template <int LOG2M> int launch_range(const RangeArgs &a, int nDop, cudaStream_t st) {
+template <int LOG2M> int launch_range(const RangeArgs &a, int nDop, int nParts, cudaStream_t st) {
   using P = Plan<LOG2M>;
   const size_t smem = 2 * (size_t)P::MP * sizeof(float2);
   static bool attr_done[64] = {};
@@ -320,7 +334,7 @@ template <int LOG2M> int launch_range(const RangeArgs &a, int nDop, cudaStream_t
     B2_CUDA(cudaFuncSetAttribute(caf_range_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done[dev & 63] = true;
   }
-  caf_range_kernel<LOG2M><<<nDop, P::NT, smem, st>>>(a);
+  caf_range_kernel<LOG2M><<<dim3(nDop, nParts), P::NT, smem, st>>>(a);
   B2_LAUNCH_CHECK();
   return B200DD_OK;
 }
@@ -349,14 +363,14 @@ template <int LOG2M> int launch_fft_forward(const float2 *in, float2 *out, const
   return B200DD_OK;
 }
 
-int dispatch_range(int log2m, const RangeArgs &a, int nDop, cudaStream_t st) {
+int dispatch_range(int log2m, const RangeArgs &a, int nDop, int nParts, cudaStream_t st) {
   switch (log2m) {
-    case 8: return launch_range<8>(a, nDop, st);
-    case 9: return launch_range<9>(a, nDop, st);
-    case 10: return launch_range<10>(a, nDop, st);
-    case 11: return launch_range<11>(a, nDop, st);
-    case 12: return launch_range<12>(a, nDop, st);
-    case 13: return launch_range<13>(a, nDop, st);
+    case 8: return launch_range<8>(a, nDop, nParts, st);
+    case 9: return launch_range<9>(a, nDop, nParts, st);
+    case 10: return launch_range<10>(a, nDop, nParts, st);
+    case 11: return launch_range<11>(a, nDop, nParts, st);
+    case 12: return launch_range<12>(a, nDop, nParts, st);
+    case 13: return launch_range<13>(a, nDop, nParts, st);
   }
   return geom_fail("range FFT length out of range");
 }
@@ -407,7 +421,8 @@ struct b200dd_caf {
   int device = 0;
   cudaStream_t stream = nullptr;
   // range stage plan
-  int log2m = 12, nSeg = 1, L = 0;
+  int log2m = 12, nSeg = 1, L = 0, nParts = 1, segPerPart = 1;
+  int num_sms = 148;
   // doppler stage plan
   int log2m2 = 10;
   float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_chirp = nullptr, *d_bhat = nullptr;
@@ -436,7 +451,7 @@ void plan_range(b200dd_caf *h) {
     const int nSeg = (nCorr + Lmax - 1) / Lmax;
     double cost = (2.0 * nSeg + 1.0) * (double)M * l;
     if (l == 13) cost *= 1.15;  // 512 threads + 139 KB smem: one CTA per SM
-    if (l <= 9) cost *= 1.25;   // tiny CTAs
+    if (l <= 10) cost *= 1.25;  // tiny CTAs (<= 64 threads): measured slower than the count suggests
     if (forced == l) cost = -1.0;
     if (cost < best) { best = cost; best_l = l; }
   }
@@ -448,6 +463,15 @@ void plan_range(b200dd_caf *h) {
     if (h->nSeg < 1) h->nSeg = 1;
     h->L = (nCorr + h->nSeg - 1) / h->nSeg;
     h->nSeg = (nCorr + h->L - 1) / h->L;
+    // occupancy: aim for >= 24 resident warps per SM by splitting batches into parts
+    const int warps_per_cta = (M / 16 + 31) / 32;
+    const int ctas_wanted = (h->num_sms * 24 + warps_per_cta - 1) / warps_per_cta;
+    int parts = (ctas_wanted + (int)h->g.nDop - 1) / (int)h->g.nDop;
+    if (const char *e = getenv("B200DD_CAF_PARTS")) parts = atoi(e);
+    if (parts < 1) parts = 1;
+    if (parts > h->nSeg) parts = h->nSeg;
+    h->segPerPart = (h->nSeg + parts - 1) / parts;
+    h->nParts = (h->nSeg + h->segPerPart - 1) / h->segPerPart;
   }
 }
 
@@ -482,7 +506,7 @@ int caf_setup_device(b200dd_caf *h) {
   if (rc != B200DD_OK) { cudaFree(d_bw); return rc; }
   B2_CUDA(cudaStreamSynchronize(h->stream));
   cudaFree(d_bw);
-  B2_CUDA(cudaMalloc(&h->d_R, sizeof(float2) * (size_t)g.nDop * g.nDel));
+  B2_CUDA(cudaMalloc(&h->d_R, sizeof(float2) * (size_t)h->nParts * g.nDop * g.nDel));
   B2_CUDA(cudaMalloc(&h->d_map, sizeof(float2) * (size_t)g.nDop * g.nDel));
   return B200DD_OK;
 }
@@ -500,12 +524,15 @@ int caf_run_device(b200dd_caf *h, const float2 *d_x, const float2 *d_y, float2 *
   ra.lagMin = g.delayMin;
   ra.nSeg = h->nSeg;
   ra.L = h->L;
+  ra.segPerPart = h->segPerPart;
+  ra.nDop = (int)g.nDop;
   if (ev) B2_CUDA(cudaEventRecord(ev[0], st));
-  int rc = dispatch_range(h->log2m, ra, (int)g.nDop, st);
+  int rc = dispatch_range(h->log2m, ra, (int)g.nDop, h->nParts, st);
   if (rc != B200DD_OK) return rc;
   if (ev) B2_CUDA(cudaEventRecord(ev[1], st));
   DopplerArgs da;
   da.R = h->d_R;
+  da.nParts = h->nParts;
   da.out = d_map;
   da.chirp = h->d_chirp;
   da.bhat = h->d_bhat;
@@ -548,6 +575,13 @@ int b200dd_caf_create(const b200dd_caf_params *params, b200dd_caf **out) {
   // the reference only reads defined memory for -nDel <= delayMin <= 1 (SURVEY.md s8 footnote c);
   // we compute lag delayMin + j directly and accept any window that fits the FFT plan.
   if (g.nDop > 8192) return fail(geom_fail("b200dd_caf_create: more than 8192 Doppler bins unsupported"));
+  {
+    int d0 = params->device;
+    if (d0 < 0) cudaGetDevice(&d0);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d0) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+    cudaGetLastError();
+  }
   plan_range(h);
   if (h->log2m == 0) return fail(geom_fail("b200dd_caf_create: nDelayBins too large for the range FFT (max ~7168)"));
   int l2 = 8;
@@ -601,6 +635,7 @@ int b200dd_caf_get_geometry(const b200dd_caf *h, b200dd_caf_geometry *out) {
   out->range_fft_len = 1u << h->log2m;
   out->range_segments = (uint32_t)h->nSeg;
   out->range_hop = (uint32_t)h->L;
+  out->range_parts = (uint32_t)h->nParts;
   out->doppler_fft_len = 1u << h->log2m2;
   return B200DD_OK;
 }
@@ -682,8 +717,16 @@ int b200dd_caf_profile_device(b200dd_caf *h, const void *d_x, const void *d_y, u
 int b200dd_caf_debug_range_matrix(b200dd_caf *h, float *out) {
   if (!h || !out) return arg_fail("b200dd_caf_debug_range_matrix: null argument");
   DeviceGuard guard(h->device);
-  B2_CUDA(cudaStreamSynchronize(h->stream));
-  B2_CUDA(cudaMemcpy(out, h->d_R, sizeof(float2) * (size_t)h->g.nDop * h->g.nDel, cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaDeviceSynchronize());
+  const size_t cells = (size_t)h->g.nDop * h->g.nDel;
+  std::vector<float2> tmp(cells * h->nParts);
+  B2_CUDA(cudaMemcpy(tmp.data(), h->d_R, sizeof(float2) * tmp.size(), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < cells; i++) {
+    float2 acc = tmp[i];
+    for (int p = 1; p < h->nParts; p++) { acc.x += tmp[p * cells + i].x; acc.y += tmp[p * cells + i].y; }
+    out[2 * i] = acc.x;
+    out[2 * i + 1] = acc.y;
+  }
   return B200DD_OK;
 }
 

@@ -179,19 +179,34 @@ B2_HD void fft_butterfly(int b, int log2S, const cpx<T> *__restrict__ tw, LD ld,
   cpx<T> v[R];
 #pragma unroll
   for (int k = 0; k < R; k++) v[k] = ld(base + (k << log2S));
-  // twiddle index step: lo * (M / ncur), ncur = R * S
-  const int tstep = lo << (LOG2M - log2S - ilog2<R>());
+  // Twiddles w^q, q = 1..R-1, with w = exp(-2 pi i lo / ncur) = tw[lo * (M / ncur)]: ONE table load,
+  // the powers by a depth-<=4 product tree in registers (squarings where possible).  This replaces
+  // R-1 dependent-latency table loads per butterfly (the dominant stall in the first profile,
+  // profiles/r01_first_ncu.md) by ~3.5 flops per twiddle.
+  cpx<T> w[R];
+  if (log2S > 0) {
+    const int tstep = lo << (LOG2M - log2S - ilog2<R>());
+    w[1] = tw[tstep];
+    if constexpr (R > 2) {
+#pragma unroll
+      for (int q = 2; q < R; q++) {
+        // q = a + b with a = largest power of two <= q/2 ... choose a = q/2, b = q - q/2 (depth log2 q)
+        const int a = q >> 1, b = q - a;
+        w[q] = (a == b) ? mk<T>(w[a].x * w[a].x - w[a].y * w[a].y, (w[a].x + w[a].x) * w[a].y) : cmul(w[a], w[b]);
+      }
+    }
+  }
   if constexpr (DIR > 0) {
     if (log2S > 0) {
 #pragma unroll
-      for (int q = 1; q < R; q++) v[q] = cmulc(v[q], tw[q * tstep]);
+      for (int q = 1; q < R; q++) v[q] = cmulc(v[q], w[q]);
     }
   }
   dft_reg<T, R, DIR>(v);
   if constexpr (DIR < 0) {
     if (log2S > 0) {
 #pragma unroll
-      for (int q = 1; q < R; q++) v[brev<R>(q)] = cmul(v[brev<R>(q)], tw[q * tstep]);
+      for (int q = 1; q < R; q++) v[brev<R>(q)] = cmul(v[brev<R>(q)], w[q]);
     }
   }
 #pragma unroll

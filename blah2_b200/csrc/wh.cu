@@ -12,10 +12,12 @@
 //                                in shared memory, one inverse FFT per CTA and per correlation,
 //                                per-CTA partial sums reduced in a fixed order by K4.
 //   K4  wh_solve_kernel          W4: Hermitian Toeplitz system A w = b (the reference builds A
-//                                with arma::toeplitz and solves by Cholesky, :85-122).  Single CTA
-//                                Levinson recursion in FP64; "not positive definite" (a reflection
-//                                coefficient with |.| >= 1, equivalently a non-positive Cholesky
-//                                pivot) raises the failure flag = the reference's `return false`.
+//                                with arma::toeplitz and solves by Cholesky + two triangular solves,
+//                                :85-122).  Single CTA, FP64: Cholesky factor by the generalized Schur
+//                                algorithm (O(n^2), elementwise steps), forward substitution fused,
+//                                then back substitution.  "Not positive definite" (|rho| >= 1, i.e. a
+//                                non-positive Cholesky pivot) raises the failure flag = the reference's
+//                                `return false`.
 //   K5  wh_apply_kernel<LOG2M>   W5: y'[i] = ys[i] - sum_{k<nBins, k<=i} w[k] xs[i-k]  (:125-160, a
 //                                LINEAR convolution with zero history) by overlap-save with the
 //                                spectrum of w computed once per CPI.
@@ -40,7 +42,6 @@ using namespace b2;
 
 namespace {
 
-constexpr int kSolveThreads = 512;
 constexpr int kMaxBins = 2048;
 
 __device__ __forceinline__ uint32_t xs_index(uint32_t i, int32_t delayMin, uint32_t N) {
@@ -177,116 +178,194 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, 1) wh_corr_kernel(CorrArgs a)
 }
 
 // ---------------------------------------------------------------------------------
-// K4: Levinson recursion for the Hermitian Toeplitz system A w = b,
-//     A(i,j) = a[j-i] (j >= i), conj(a[i-j]) (i > j)   (WienerHopf.cpp:85-97).
-// With t_k = conj(a[k]):  f = forward vector (T_m f = e_1), g = J conj(f) backward vector.
-//     eps_f = sum_{i<m} t_{m-i} f[i],  eps_x = sum_{i<m} t_{m-i} x[i]
-//     f' = ([f;0] - eps_f [0;g]) / (1 - |eps_f|^2),  x' = [x;0] + (b[m] - eps_x) J conj(f')
-// 1 - |eps_f|^2 <= 0  <=>  A not positive definite  <=>  the reference's chol() fails.
+// K4: Hermitian positive-definite Toeplitz solve A w = b,
+//     A(i,j) = a[j-i] (j >= i), conj(a[i-j]) (i > j)   (WienerHopf.cpp:85-97),
+// done the way the reference does it -- Cholesky factor, then two triangular solves
+// (arma::chol + solve(trimatl) + solve(trimatu), WienerHopf.cpp:111-117) -- but with the
+// factor produced by the generalized SCHUR algorithm, which exploits the Toeplitz
+// displacement structure: O(n^2) work, every step purely elementwise (no reductions).
+//
+//   T - Z T Z^H = alpha alpha^H - beta beta^H,  alpha_i = t_i / sqrt(t_0), beta_0 = 0, beta_i = alpha_i
+//   (t_i = A(i,0) = conj(a[i])).  Step k -> k+1:
+//       column k of L            L(i,k) = alpha_i                      (i >= k)
+//       forward substitution     z_k = r_k / L(k,k);  r_i -= L(i,k) z_k      (fused)
+//       shift                    at_i = alpha_{i-1}
+//       hyperbolic rotation      rho = beta_{k+1} / alpha_k,  c = 1/sqrt(1 - |rho|^2)
+//                                alpha_i <- c (at_i - conj(rho) beta_i),  beta_i <- c (beta_i - rho at_i)
+//   |rho| >= 1  <=>  A is not positive definite  <=>  the reference's chol() fails -> status 1.
+//   Second sweep: L^H w = z by column-oriented back substitution (rows of L read back from L2).
+// The Schur algorithm is backward stable for positive-definite Toeplitz matrices (Bojanczyk,
+// Brent, de Hoog, Sweet 1995), like the Cholesky factorisation it reproduces.
+//
+// Latency design: one CTA, one element per thread (two above 1024 taps), ONE __syncthreads per
+// step.  The per-step critical path is  LDS(pivot) -> rsqrt -> 2 FMAs -> STS; the L(k,k) pivots are
+// tracked as a scalar recurrence in every thread (alpha_{k+1,k+1} = alpha_{k,k} sqrt(1-|rho|^2)), so
+// no division and no reduction sits on the chain.  The next rows of L for the back substitution
+// are prefetched four steps ahead.
 // ---------------------------------------------------------------------------------
 struct SolveArgs {
   const double2 *partial;  // [nPartial][2][nBins]
   int nPartial, nBins;
   double2 *a_out, *b_out, *w_out;
+  double2 *L;   // [nBins][nBins] row-major scratch (lower triangle used)
   int *status;  // 0 ok, 1 failed
 };
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-__global__ void __launch_bounds__(kSolveThreads, 1) wh_solve_kernel(SolveArgs s) {
+template <int EPT> __global__ void __launch_bounds__(1024, 1) wh_solve_kernel(SolveArgs s) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = s.nBins;
-  double2 *tk = reinterpret_cast<double2 *>(smem_raw);  // t_k = conj(a[k])
-  double2 *fb0 = tk + n;
-  double2 *fb1 = fb0 + n;
-  double2 *xv = fb1 + n;
-  double2 *bv = xv + n;
-  __shared__ double red[2][kSolveThreads / 32][4];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = kSolveThreads / 32;
+  double2 *alb0 = reinterpret_cast<double2 *>(smem_raw);
+  double2 *alb1 = alb0 + n;
+  double2 *pub_r = alb1 + n;   // r_k published by thread k   (reused for w_k in the second sweep)
+  double2 *pub_b = pub_r + n;  // beta_{k+1} published by thread k+1
+  double2 *zv = pub_b + n;     // z = L^-1 b
+  double *invd = reinterpret_cast<double *>(zv + n);  // 1 / L(k,k)
+  __shared__ double s_t0;
+  const int tid = threadIdx.x, NTS = blockDim.x;
 
-  // fixed-order reduction of the per-CTA partial correlations
-  for (int k = tid; k < n; k += kSolveThreads) {
-    double2 sa = make_double2(0.0, 0.0), sb = make_double2(0.0, 0.0);
-    for (int p = 0; p < s.nPartial; p++) {
-      const double2 va = s.partial[((size_t)p * 2) * n + k];
-      const double2 vb = s.partial[((size_t)p * 2 + 1) * n + k];
-      sa.x += va.x; sa.y += va.y;
-      sb.x += vb.x; sb.y += vb.y;
-    }
-    s.a_out[k] = sa;
-    s.b_out[k] = sb;
-    tk[k] = make_double2(sa.x, -sa.y);
-    bv[k] = sb;
-    fb0[k] = make_double2(0.0, 0.0);
-    fb1[k] = make_double2(0.0, 0.0);
-    xv[k] = make_double2(0.0, 0.0);
-  }
-  __syncthreads();
-  const double a0 = tk[0].x;
-  bool ok = (a0 > 0.0) && isfinite(a0);
-  if (ok && tid == 0) {
-    fb0[0] = make_double2(1.0 / a0, 0.0);
-    xv[0] = make_double2(bv[0].x / a0, bv[0].y / a0);
-  }
-  __syncthreads();
-  double2 *fc = fb0, *fn = fb1;
-  for (int m = 1; m < n && ok; m++) {
-    // [A] partial dot products over own elements
-    double pfx = 0.0, pfy = 0.0, pxx = 0.0, pxy = 0.0;
-    for (int i = tid; i < m; i += kSolveThreads) {
-      const double2 t = tk[m - i];
-      const double2 f = fc[i];
-      const double2 xx = xv[i];
-      pfx += t.x * f.x - t.y * f.y;
-      pfy += t.x * f.y + t.y * f.x;
-      pxx += t.x * xx.x - t.y * xx.y;
-      pxy += t.x * xx.y + t.y * xx.x;
-    }
-    pfx = warp_sum(pfx); pfy = warp_sum(pfy); pxx = warp_sum(pxx); pxy = warp_sum(pxy);
-    if (lane == 0) {
-      red[m & 1][warp][0] = pfx; red[m & 1][warp][1] = pfy;
-      red[m & 1][warp][2] = pxx; red[m & 1][warp][3] = pxy;
-    }
-    __syncthreads();  // [B]
-    double efx = 0.0, efy = 0.0, exx = 0.0, exy = 0.0;
+  double2 al[EPT], be[EPT], rr[EPT];
+  // fixed-order reduction of the per-CTA partial correlations (deterministic)
 #pragma unroll
-    for (int w = 0; w < NW; w++) {
-      efx += red[m & 1][w][0]; efy += red[m & 1][w][1];
-      exx += red[m & 1][w][2]; exy += red[m & 1][w][3];
+  for (int e = 0; e < EPT; e++) {
+    const int i = tid + e * NTS;
+    al[e] = be[e] = rr[e] = make_double2(0.0, 0.0);
+    if (i < n) {
+      double2 sa = make_double2(0.0, 0.0), sb = make_double2(0.0, 0.0);
+      for (int p = 0; p < s.nPartial; p++) {
+        const double2 va = s.partial[((size_t)p * 2) * n + i];
+        const double2 vb = s.partial[((size_t)p * 2 + 1) * n + i];
+        sa.x += va.x; sa.y += va.y;
+        sb.x += vb.x; sb.y += vb.y;
+      }
+      s.a_out[i] = sa;
+      s.b_out[i] = sb;
+      al[e] = make_double2(sa.x, -sa.y);  // t_i = conj(a[i])
+      rr[e] = sb;
+      if (i == 0) s_t0 = sa.x;
     }
-    const double d = 1.0 - (efx * efx + efy * efy);
-    if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }  // uniform: every thread sees the same sums
-    const double al = 1.0 / d;
-    const double2 bm = bv[m];
-    const double cx = bm.x - exx, cy = bm.y - exy;
-    // [D] update own elements i <= m
-    for (int i = tid; i <= m; i += kSolveThreads) {
-      const double2 fi = (i < m) ? fc[i] : make_double2(0.0, 0.0);
-      const double2 fmi = (i >= 1) ? fc[m - i] : make_double2(0.0, 0.0);
-      // f'[i]   = al (f[i]   - eps_f conj(f[m-i]))
-      // f'[m-i] = al (f[m-i] - eps_f conj(f[i]))
-      double2 fni, fnm;
-      fni.x = al * (fi.x - (efx * fmi.x + efy * fmi.y));
-      fni.y = al * (fi.y - (efy * fmi.x - efx * fmi.y));
-      fnm.x = al * (fmi.x - (efx * fi.x + efy * fi.y));
-      fnm.y = al * (fmi.y - (efy * fi.x - efx * fi.y));
-      fn[i] = fni;
-      // x'[i] = x[i] + c conj(f'[m-i])
-      double2 xi = (i < m) ? xv[i] : make_double2(0.0, 0.0);
-      xi.x += cx * fnm.x + cy * fnm.y;
-      xi.y += cy * fnm.x - cx * fnm.y;
-      xv[i] = xi;
-    }
-    double2 *tmp = fc; fc = fn; fn = tmp;
-    // no barrier: the next [A] reads only elements this thread wrote itself
   }
   __syncthreads();
-  for (int k = tid; k < n; k += kSolveThreads) s.w_out[k] = ok ? xv[k] : make_double2(0.0, 0.0);
+  const double t0 = s_t0;
+  bool ok = (t0 > 0.0) && isfinite(t0);
+  double pivot = ok ? sqrt(t0) : 1.0;
+  double inv_pivot = 1.0 / pivot;
+#pragma unroll
+  for (int e = 0; e < EPT; e++) {
+    const int i = tid + e * NTS;
+    if (i < n) {
+      al[e].x *= inv_pivot; al[e].y *= inv_pivot;
+      be[e] = i ? al[e] : make_double2(0.0, 0.0);
+      alb0[i] = al[e];
+      s.L[(size_t)i * n] = al[e];
+      if (i == 0) { pub_r[0] = rr[e]; invd[0] = inv_pivot; }
+      if (i == 1) pub_b[0] = be[e];
+    }
+  }
+  __syncthreads();
+  double2 *ac = alb0, *an = alb1;
+  if (ok) {
+    for (int k = 0; k < n - 1; k++) {
+      const double2 pr = pub_r[k], pb = pub_b[k];
+      const double2 z = make_double2(pr.x * inv_pivot, pr.y * inv_pivot);
+      const double2 rho = make_double2(pb.x * inv_pivot, pb.y * inv_pivot);
+      const double d = 1.0 - (rho.x * rho.x + rho.y * rho.y);
+      if (!(d > 0.0)) { ok = false; break; }  // uniform: every thread reads the same published pivot
+      const double c = rsqrt(d);
+#pragma unroll
+      for (int e = 0; e < EPT; e++) {
+        const int i = tid + e * NTS;
+        if (i > k && i < n) {
+          const double2 at = ac[i - 1];
+          // forward substitution with column k:  r_i -= L(i,k) z_k
+          rr[e].x -= al[e].x * z.x - al[e].y * z.y;
+          rr[e].y -= al[e].x * z.y + al[e].y * z.x;
+          // alpha' = c (at - conj(rho) beta),  beta' = c (beta - rho at)
+          double2 na, nb;
+          na.x = c * (at.x - (rho.x * be[e].x + rho.y * be[e].y));
+          na.y = c * (at.y - (rho.x * be[e].y - rho.y * be[e].x));
+          nb.x = c * (be[e].x - (rho.x * at.x - rho.y * at.y));
+          nb.y = c * (be[e].y - (rho.x * at.y + rho.y * at.x));
+          al[e] = na;
+          be[e] = nb;
+          an[i] = na;
+          s.L[(size_t)i * n + (k + 1)] = na;
+          if (i == k + 1) pub_r[k + 1] = rr[e];
+          if (i == k + 2) pub_b[k + 1] = nb;
+        }
+      }
+      if (tid == 0) { zv[k] = z; invd[k + 1] = inv_pivot * c; }
+      pivot = pivot * d * c;  // L(k+1,k+1) = L(k,k) sqrt(1 - |rho|^2)
+      inv_pivot *= c;
+      __syncthreads();
+      double2 *t = ac; ac = an; an = t;
+    }
+  }
+  if (ok && tid == 0) {
+    const double2 pr = pub_r[n - 1];
+    zv[n - 1] = make_double2(pr.x * inv_pivot, pr.y * inv_pivot);
+  }
+  __syncthreads();
+  if (ok) {
+    // second sweep: L^H w = z, column oriented; pub_r[k] <- w_k
+    double2 zz[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; e++) {
+      const int i = tid + e * NTS;
+      zz[e] = i < n ? zv[i] : make_double2(0.0, 0.0);
+    }
+    constexpr int PF = 4;
+    double2 lc[PF][EPT], ln[PF][EPT];
+    auto load_rows = [&](int ktop, double2 (&dst)[PF][EPT]) {
+#pragma unroll
+      for (int q = 0; q < PF; q++) {
+        const int row = ktop - q;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+          const int i = tid + e * NTS;
+          dst[q][e] = (row >= 0 && i < row) ? __ldcg(s.L + (size_t)row * n + i) : make_double2(0.0, 0.0);
+        }
+      }
+    };
+    __threadfence_block();
+    load_rows(n - 1, lc);
+    for (int ktop = n - 1; ktop >= 0; ktop -= PF) {
+      load_rows(ktop - PF, ln);
+#pragma unroll
+      for (int q = 0; q < PF; q++) {
+        const int k = ktop - q;
+        if (k >= 0) {
+#pragma unroll
+          for (int e = 0; e < EPT; e++) {
+            const int i = tid + e * NTS;
+            if (i == k) pub_r[k] = make_double2(zz[e].x * invd[k], zz[e].y * invd[k]);
+          }
+        }
+        __syncthreads();
+        if (k >= 0) {
+          const double2 w = pub_r[k];
+#pragma unroll
+          for (int e = 0; e < EPT; e++) {
+            const int i = tid + e * NTS;
+            if (i < k) {  // zz_i -= conj(L(k,i)) w_k
+              const double2 l = lc[q][e];
+              zz[e].x -= l.x * w.x + l.y * w.y;
+              zz[e].y -= l.x * w.y - l.y * w.x;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < PF; q++)
+#pragma unroll
+        for (int e = 0; e < EPT; e++) lc[q][e] = ln[q][e];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int e = 0; e < EPT; e++) {
+    const int i = tid + e * NTS;
+    if (i < n) s.w_out[i] = ok ? pub_r[i] : make_double2(0.0, 0.0);
+  }
   if (tid == 0) *s.status = ok ? 0 : 1;
 }
 
@@ -384,7 +463,7 @@ struct b200dd_wh {
   int log2m = 12;
   int L = 0, nSeg = 0, segPerCta = 1, gridCorr = 1;  // correlation stage
   int Lout = 0, gridApply = 1;                       // filter stage
-  double2 *d_tw = nullptr, *d_partial = nullptr, *d_a = nullptr, *d_b = nullptr, *d_w = nullptr, *d_what = nullptr;
+  double2 *d_tw = nullptr, *d_partial = nullptr, *d_a = nullptr, *d_b = nullptr, *d_w = nullptr, *d_what = nullptr, *d_L = nullptr;
   int *d_status = nullptr;
   double2 *d_xd = nullptr, *d_yd = nullptr;  // host path staging (complex128)
   int num_sms = 148;
@@ -399,13 +478,14 @@ template <int LOG2M> size_t fft_smem() { return (size_t)Plan<LOG2M>::MP * sizeof
 template <int LOG2M, class TIN> int wh_launch_all(b200dd_wh *h, const void *x, const void *y, void *y_out, cudaStream_t st,
                                                   cudaEvent_t *ev) {
   using P = Plan<LOG2M>;
-  const size_t solve_smem = (size_t)5 * h->nBins * sizeof(double2);
+  const size_t solve_smem = (size_t)h->nBins * (5 * sizeof(double2) + sizeof(double));
   bool &done = sizeof(typename std::remove_pointer<decltype(TIN::x) *>::type) == 4 ? h->attr_f32 : h->attr_f64;
   if (!done) {
     B2_CUDA(cudaFuncSetAttribute(wh_corr_kernel<LOG2M, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_smem<LOG2M>()));
     B2_CUDA(cudaFuncSetAttribute(wh_apply_kernel<LOG2M, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M>()));
     B2_CUDA(cudaFuncSetAttribute(wh_wspec_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M>()));
-    B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+    B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+    B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
     done = true;
   }
   CorrArgs ca;
@@ -417,8 +497,13 @@ template <int LOG2M, class TIN> int wh_launch_all(b200dd_wh *h, const void *x, c
   if (ev) B2_CUDA(cudaEventRecord(ev[1], st));
   SolveArgs sa;
   sa.partial = h->d_partial; sa.nPartial = h->gridCorr; sa.nBins = h->nBins;
-  sa.a_out = h->d_a; sa.b_out = h->d_b; sa.w_out = h->d_w; sa.status = h->d_status;
-  wh_solve_kernel<<<1, kSolveThreads, solve_smem, st>>>(sa);
+  sa.a_out = h->d_a; sa.b_out = h->d_b; sa.w_out = h->d_w; sa.status = h->d_status; sa.L = h->d_L;
+  if (h->nBins <= 1024) {
+    const int threads = ((h->nBins + 31) / 32) * 32;
+    wh_solve_kernel<1><<<1, threads, solve_smem, st>>>(sa);
+  } else {
+    wh_solve_kernel<2><<<1, 1024, solve_smem, st>>>(sa);
+  }
   B2_LAUNCH_CHECK();
   if (ev) B2_CUDA(cudaEventRecord(ev[2], st));
   wh_wspec_kernel<LOG2M><<<1, P::NT, fft_smem<LOG2M>(), st>>>(h->d_w, h->nBins, h->d_what, h->d_tw);
@@ -514,6 +599,7 @@ int b200dd_wh_create(int32_t delay_min, int32_t delay_max, uint32_t n_samples, i
     B2_CUDA(cudaMalloc(&h->d_b, sizeof(double2) * h->nBins));
     B2_CUDA(cudaMalloc(&h->d_w, sizeof(double2) * h->nBins));
     B2_CUDA(cudaMalloc(&h->d_what, sizeof(double2) * M));
+    B2_CUDA(cudaMalloc(&h->d_L, sizeof(double2) * (size_t)h->nBins * h->nBins));
     B2_CUDA(cudaMalloc(&h->d_status, sizeof(int)));
     B2_CUDA(cudaMemset(h->d_status, 0, sizeof(int)));
     return B200DD_OK;
@@ -535,6 +621,7 @@ void b200dd_wh_destroy(b200dd_wh *h) {
     free_dev(h->d_b);
     free_dev(h->d_w);
     free_dev(h->d_what);
+    free_dev(h->d_L);
     free_dev(h->d_status);
     free_dev(h->d_xd);
     free_dev(h->d_yd);

@@ -105,6 +105,21 @@ def test_every_range_fft_length_gives_the_same_map(log2m, relerr, monkeypatch):
     assert e[0] < TOL and e[1] < TOL, f"log2m={log2m} map {e}"
 
 
+@pytest.mark.parametrize("parts", [1, 2, 3, 100])
+def test_batch_split_into_parts_gives_the_same_map(parts, relerr, monkeypatch):
+    monkeypatch.setenv("B200DD_CAF_LOG2M", "9")
+    monkeypatch.setenv("B200DD_CAF_PARTS", str(parts))
+    geom = (-5, 60, -200, 200, 100000, 100000, True)
+    x, y = random_iq(geom[5], seed=6)
+    amb, m = _run(geom, x, y)
+    assert 1 <= amb.geometry.range_parts <= amb.geometry.range_segments
+    ref, _, _ = O.ambiguity_process(x, y, O.ambiguity_geometry(*geom))
+    e = relerr(m.data, ref)
+    assert e[0] < TOL and e[1] < TOL, f"parts={parts} map {e}"
+    Rref = O.range_matrix(np.asarray(x, np.complex128), np.asarray(y, np.complex128), O.ambiguity_geometry(*geom))
+    assert relerr(amb.debug_range_matrix(), Rref)[0] < TOL
+
+
 def test_linearity_and_determinism_full_size():
     """Size-independent properties at BASELINE config-3 size (oracle too slow to run in
     seconds): CAF(x, a*y1 + b*y2) = a CAF(x,y1) + b CAF(x,y2), and bitwise repeatability."""

@@ -43,8 +43,9 @@ def test_filter_matches_oracle_fp64_host_path(case, relerr):
     y_ref = O.wienerhopf_apply(xs, sc.y, w_ref)
     e = relerr(y, y_ref)
     assert e[0] < 1e-9 and e[1] < 1e-9, f"filtered surveillance {e}"
-    # it must actually cancel clutter
-    assert np.linalg.norm(y) < 0.1 * np.linalg.norm(sc.y)
+    # it must actually cancel clutter (when the tap window covers the direct path at lag 0)
+    if dm <= 0:
+        assert np.linalg.norm(y) < 0.1 * np.linalg.norm(sc.y)
 
 
 def test_cholesky_failure_leaves_y_untouched():

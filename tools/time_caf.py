@@ -11,9 +11,11 @@ CFGS = {
 }
 PEAK = 6584.8e9
 
-def run(name, log2m=None, iters=20, nbuf=8):
+def run(name, log2m=None, parts=None, iters=20, nbuf=8):
     if log2m: os.environ["B200DD_CAF_LOG2M"] = str(log2m)
     else: os.environ.pop("B200DD_CAF_LOG2M", None)
+    if parts: os.environ["B200DD_CAF_PARTS"] = str(parts)
+    else: os.environ.pop("B200DD_CAF_PARTS", None)
     geom = CFGS[name]
     amb = Ambiguity(*geom)
     g = amb.geometry
@@ -36,12 +38,14 @@ def run(name, log2m=None, iters=20, nbuf=8):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     byts = 16 * g.n_used + 8 * g.n_doppler_bins * g.n_delay_bins
-    print(json.dumps(dict(cfg=name, log2m=g.range_fft_len, nseg=g.range_segments, hop=g.range_hop, m2=g.doppler_fft_len,
+    print(json.dumps(dict(cfg=name, log2m=g.range_fft_len, nseg=g.range_segments, parts=g.range_parts, hop=g.range_hop, m2=g.doppler_fft_len,
                           ms=round(ms, 4), maps_per_s=round(1e3 / ms, 1), msamples_per_s=round(n / ms / 1e3, 1),
                           gbs=round(byts / ms / 1e6, 1), frac=round(byts / (ms * 1e-3) / PEAK, 4))), flush=True)
     amb.close()
 
 if __name__ == "__main__":
     for name in sys.argv[1:] or ["cfg1", "cfg3"]:
-        for l in (None, 10, 11, 12, 13):
-            run(name, l)
+        run(name)
+        for l in (10, 11, 12, 13):
+            for p in (1, 2, 4, 8):
+                run(name, l, p)
