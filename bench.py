@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=2, help="CPIs in flight per GPU (independent pipelines on their own streams)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -186,7 +187,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    pipe = Pipeline(**GEOM, clutter=CLUTTER, detection=DET, device=local_rank)
+    NPIPE = max(1, args.streams)
+    pipes = [Pipeline(**GEOM, clutter=CLUTTER, detection=DET, device=local_rank) for _ in range(NPIPE)]
+    pipe = pipes[0]
     g = pipe.geometry
     cells = g.n_doppler_bins * g.n_delay_bins
 
@@ -200,9 +203,11 @@ def main():
     hx = [torch.from_numpy(np.roll(sc.x, 977 * b)).pin_memory() for b in range(2)]
     hy = [torch.from_numpy(np.roll(sc.y, 977 * b)).pin_memory() for b in range(2)]
     hmap = torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex128).pin_memory()
-    dmap = torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda")
+    dmaps = [torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda") for _ in range(NPIPE)]
+    dmap = dmaps[0]
     gathered = [torch.empty_like(dmap) for _ in range(world)] if (world > 1 and rank == 0) else None
-    stream = torch.cuda.Stream()
+    streams = [torch.cuda.Stream() for _ in range(NPIPE)]
+    stream = streams[0]
     st = stream.cuda_stream
 
     def barrier():
@@ -211,21 +216,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput ----
-    with torch.cuda.stream(stream):
-        for i in range(args.warmup):
-            pipe.submit_device(xs[i % NB], ys[i % NB], dmap, st)
-        last = pipe.fetch(st)
+    def submit(i):
+        p = i % NPIPE
+        with torch.cuda.stream(streams[p]):
+            pipes[p].submit_device(xs[i % NB], ys[i % NB], dmaps[p], streams[p].cuda_stream)
+
+    # ---- device-resident throughput: a stream of independent CPIs, NPIPE in flight ----
+    for i in range(args.warmup):
+        submit(i)
+    for p in range(NPIPE):
+        last = pipes[p].fetch(streams[p].cuda_stream)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for s_ in streams[1:]:
+        s_.wait_event(e0)
+    for i in range(args.steps):
+        submit(i)
+    for p in reversed(range(NPIPE)):  # synchronises each stream; detections + metrics of the final CPIs on the host
+        last = pipes[p].fetch(streams[p].cuda_stream)
     with torch.cuda.stream(stream):
-        e0.record(stream)
-        for i in range(args.steps):
-            pipe.submit_device(xs[i % NB], ys[i % NB], dmap, st)
-        last = pipe.fetch(st)  # synchronises; detections + metrics of the final CPI on the host
         if world > 1:  # the final map gather (NCCL over NVLink), ordered after the kernels on `stream`
             dist.gather(dmap, gathered, dst=0)
         e1.record(stream)
@@ -237,13 +250,21 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the host API (pinned complex128 in, complex128 map out) ----
-    for i in range(2):
-        pipe.process(hx[i % 2], hy[i % 2], map_out=hmap)
+    # Two pipelines alternate: submit_host(i) enqueues H2D + kernels + D2H, fetch(i-1) collects the
+    # previous CPI's map/detections, so PCIe transfers of one CPI overlap the kernels of the other.
+    hmaps = [torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex128).pin_memory() for _ in range(NPIPE)]
+    for i in range(2 * NPIPE):
+        pipes[i % NPIPE].process(hx[i % 2], hy[i % 2], map_out=hmaps[i % NPIPE])
     barrier()
-    e2e_steps = max(5, min(args.steps, 30))
+    e2e_steps = max(6, min(args.steps, 30))
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        r_e2e = pipe.process(hx[i % 2], hy[i % 2], map_out=hmap)
+        p = i % NPIPE
+        if i >= NPIPE:
+            r_e2e = pipes[p].fetch()          # result of CPI i - NPIPE is now in host memory
+        pipes[p].submit_host(hx[i % 2], hy[i % 2], map_out=hmaps[p])
+    for i in range(e2e_steps, e2e_steps + NPIPE):
+        r_e2e = pipes[i % NPIPE].fetch()
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
     if world > 1:
@@ -284,13 +305,14 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (CAF) / f64 (WienerHopf, detection)",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "cpis_per_step_per_gpu": 1, "parallelism": f"independent CPIs x{world}",
-                   "l2": f"{NB} distinct CPI input sets rotated ({NB * 32} MB > L2)",
+                   "l2": f"{NB} distinct CPI input sets rotated ({NB * 32} MB > L2)", "cpis_in_flight": NPIPE,
                    "range_fft": f"M={g.range_fft_len} x{g.range_segments} segments, hop {g.range_hop}",
                    "doppler_fft": f"Bluestein M2={g.doppler_fft_len}"},
         "e2e": {"value": round(e2e_value, 2), "unit": "Msamples/s", "h2d_bytes_per_step": 2 * 16 * N,
                 "d2h_bytes_per_step": 16 * cells + 3 * 8 * int(r_e2e["detections"].get_nDetections()) + 32,
                 "ms_per_step": round(e2e_s / e2e_steps * 1e3, 4), "steps": e2e_steps,
-                "api": "Pipeline.process(pinned complex128 x, y) -> complex128 map + detections"},
+                "api": "Pipeline.submit_host(pinned complex128 x, y) / fetch() -> complex128 map + detections, "
+                       f"{NPIPE} CPIs in flight"},
         "gpu_launches": KERNELS_PER_STEP * args.steps,
         "clocks": clocks,
         "roofline": {"kernel": "caf_range_kernel", "bound": "hbm", "achieved": round(ach_range, 1), "peak": peak,

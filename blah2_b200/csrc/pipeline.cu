@@ -179,13 +179,11 @@ int b200dd_pipeline_fetch(b200dd_pipeline *h, b200dd_cpi_result *result, double 
   return rc;
 }
 
-int b200dd_pipeline_process_host(b200dd_pipeline *h, const double *x, const double *y, uint32_t n, double *map_out,
-                                 b200dd_cpi_result *result, double *o_delay, double *o_doppler, double *o_snr,
-                                 uint32_t cap) {
-  if (!h || !x || !y || !result) return arg_fail("b200dd_pipeline_process_host: null argument");
+int b200dd_pipeline_submit_host(b200dd_pipeline *h, const double *x, const double *y, uint32_t n, double *map_out) {
+  if (!h || !x || !y) return arg_fail("b200dd_pipeline_submit_host: null argument");
   const uint32_t N = h->p.caf.n_samples;
   const uint32_t need = h->wh ? N : h->g.n_used;
-  if (h->wh ? (n != N) : (n < need)) return arg_fail("b200dd_pipeline_process_host: wrong number of samples");
+  if (h->wh ? (n != N) : (n < need)) return arg_fail("b200dd_pipeline_submit_host: wrong number of samples");
   DeviceGuard guard(h->device);
   cudaStream_t st = h->stream;
   if (!h->d_xd) {
@@ -221,7 +219,16 @@ int b200dd_pipeline_process_host(b200dd_pipeline *h, const double *x, const doub
     B2_LAUNCH_CHECK();
     B2_CUDA(cudaMemcpyAsync(map_out, h->d_mapd, sizeof(double2) * cells, cudaMemcpyDeviceToHost, st));
   }
-  return b200dd_pipeline_fetch(h, result, o_delay, o_doppler, o_snr, cap, st);
+  return B200DD_OK;
+}
+
+int b200dd_pipeline_process_host(b200dd_pipeline *h, const double *x, const double *y, uint32_t n, double *map_out,
+                                 b200dd_cpi_result *result, double *o_delay, double *o_doppler, double *o_snr,
+                                 uint32_t cap) {
+  if (!result) return arg_fail("b200dd_pipeline_process_host: null argument");
+  int rc = b200dd_pipeline_submit_host(h, x, y, n, map_out);
+  if (rc != B200DD_OK) return rc;
+  return b200dd_pipeline_fetch(h, result, o_delay, o_doppler, o_snr, cap, h->stream);
 }
 
 }  // extern "C"

@@ -393,6 +393,14 @@ class Pipeline:
                                                           capi.ptr(self._os), self.cap), allow=(capi.ERR_CAPACITY,))
         return self._result(res, map_out)
 
+    def submit_host(self, x, y, map_out=None):
+        """Asynchronous host path: enqueue H2D + kernels + D2H(map) and return; pair with fetch().
+        x, y, map_out must stay alive (pinned for real overlap) until fetch() returns."""
+        n = x.numel() if hasattr(x, "numel") else x.shape[0]
+        self._pending_map = map_out
+        capi.check(self._lib.b200dd_pipeline_submit_host(self._h, capi.ptr(x), capi.ptr(y), int(n),
+                                                         capi.ptr(map_out) if map_out is not None else None))
+
     def submit_device(self, d_x, d_y, d_map=None, stream=None):
         n = d_x.numel() if hasattr(d_x, "numel") else self.n_samples
         capi.check(self._lib.b200dd_pipeline_submit_device(self._h, capi.ptr(d_x), capi.ptr(d_y), int(n),

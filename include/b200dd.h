@@ -272,6 +272,13 @@ B200DD_API int b200dd_pipeline_process_host(b200dd_pipeline *h, const double *x,
                                             double *map_out, b200dd_cpi_result *result, double *o_delay,
                                             double *o_doppler, double *o_snr, uint32_t cap);
 
+/* Asynchronous form of the host entry: enqueues H2D, all kernels and the D2H of the map on the
+ * pipeline's own stream and returns; x, y and map_out must stay valid (pinned memory for true
+ * overlap) until b200dd_pipeline_fetch returns.  Two pipelines used alternately overlap the PCIe
+ * transfers of one CPI with the kernels of the other. */
+B200DD_API int b200dd_pipeline_submit_host(b200dd_pipeline *h, const double *x, const double *y, uint32_t n,
+                                           double *map_out);
+
 /* DEVICE buffers (float2), asynchronous on `stream` (NULL = the pipeline's stream).  d_map
  * (nullable) receives the float2 map.  Results stay on the device until b200dd_pipeline_fetch. */
 B200DD_API int b200dd_pipeline_submit_device(b200dd_pipeline *h, const void *d_x, const void *d_y, uint32_t n,
