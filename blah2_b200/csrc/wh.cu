@@ -44,13 +44,34 @@ namespace {
 
 constexpr int kMaxBins = 2048;
 
-__device__ __forceinline__ uint32_t xs_index(uint32_t i, int32_t delayMin, uint32_t N) {
-  if (delayMin <= 0) {
-    uint32_t t = i + (uint32_t)(-delayMin);
-    return t >= N ? t % N : t;
+// xs[i] = x[map(i)] reproduces the reference's (((i - delayMin) % N) + N) % N evaluated in uint32
+// arithmetic (WienerHopf.cpp:67) EXACTLY, with no division and no branch on the load path (the first
+// profile showed the pass-0 loads serialised behind per-element branches, profiles/r01_summary.md):
+//   delayMin <= 0 : (i + |delayMin|) mod N                        -> add1 = |delayMin| mod N, thr = 0
+//   delayMin  > 0 : i >= delayMin: i - delayMin                   -> add1 = (N - delayMin mod N) mod N
+//                   i <  delayMin: (2^32 - delayMin + i) mod N    -> add2 = (2^32 - delayMin) mod N
+// (the uint32 subtraction wraps modulo 2^32 in the reference; that quirk is kept).
+struct XsMap {
+  uint32_t N, thr, add1, add2;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+    const uint32_t t = i + (i >= thr ? add1 : add2);
+    return t >= N ? t - N : t;
   }
-  uint32_t t = i - (uint32_t)delayMin;  // wraps modulo 2^32 like the reference
-  return ((t % N) + N) % N;
+};
+
+inline XsMap make_xs_map(uint32_t N, int32_t delayMin) {
+  XsMap m;
+  m.N = N;
+  if (delayMin <= 0) {
+    m.thr = 0;
+    m.add1 = (uint32_t)((-(int64_t)delayMin) % (int64_t)N);
+    m.add2 = 0;
+  } else {
+    m.thr = (uint32_t)delayMin;
+    m.add1 = (uint32_t)(((int64_t)N - ((int64_t)delayMin % (int64_t)N)) % (int64_t)N);
+    m.add2 = (uint32_t)(((1ll << 32) - (int64_t)delayMin) % (int64_t)N);
+  }
+  return m;
 }
 
 template <class TIN> __device__ __forceinline__ double2 ld_iq(const TIN *p, uint32_t i) {
@@ -64,7 +85,7 @@ struct CorrArgs {
   double2 *partial;   // [grid][2][nBins]
   const double2 *tw;  // exp(-2 pi i j / M)
   uint32_t N;
-  int32_t delayMin;
+  XsMap xs;
   int nBins, L, nSegTotal, segPerCta;
 };
 
@@ -122,22 +143,28 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, 1) wh_corr_kernel(CorrArgs a)
   }
   const int s0 = blockIdx.x * a.segPerCta;
   const int s1 = min(s0 + a.segPerCta, a.nSegTotal);
+  const XsMap xs = a.xs;
   for (int s = s0; s < s1; s++) {
     const uint32_t n0 = (uint32_t)s * (uint32_t)a.L;
     const int len = (int)min((uint32_t)a.L, a.N - n0);
     const int wlen = len + a.nBins - 1;
-    auto ldxp = [&](int m) { return m < len ? ld_iq(x, xs_index(n0 + (uint32_t)m, a.delayMin, a.N)) : zero; };
+    // branch-free loaders: every load is unconditional on a valid index (so the 16 loads of a
+    // butterfly are issued back to back) and masked afterwards
+    auto ldxp = [&](int m) {
+      const double2 v = ld_iq(x, xs(n0 + (uint32_t)min(m, len - 1)));
+      return m < len ? v : zero;
+    };
     auto ldxw = [&](int m) {
-      if (m >= wlen) return zero;
       uint32_t i = n0 + (uint32_t)m;
-      if (i >= a.N) i -= a.N;  // circular correlation over N (WienerHopf.cpp:76-108)
-      return ld_iq(x, xs_index(i, a.delayMin, a.N));
+      i = i >= a.N ? i - a.N : i;  // circular correlation over N (WienerHopf.cpp:76-108)
+      const double2 v = ld_iq(x, xs(i));
+      return m < wlen ? v : zero;
     };
     auto ldyw = [&](int m) {
-      if (m >= wlen) return zero;
       uint32_t i = n0 + (uint32_t)m;
-      if (i >= a.N) i -= a.N;
-      return ld_iq(y, i);
+      i = i >= a.N ? i - a.N : i;
+      const double2 v = ld_iq(y, i);
+      return m < wlen ? v : zero;
     };
     double2 vxp[16], v[16];
     fwd_fft_regs<LOG2M>(A, a.tw, tid, ldxp, vxp);
@@ -180,36 +207,45 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, 1) wh_corr_kernel(CorrArgs a)
 // ---------------------------------------------------------------------------------
 // K4: Hermitian positive-definite Toeplitz solve A w = b,
 //     A(i,j) = a[j-i] (j >= i), conj(a[i-j]) (i > j)   (WienerHopf.cpp:85-97),
-// done the way the reference does it -- Cholesky factor, then two triangular solves
-// (arma::chol + solve(trimatl) + solve(trimatu), WienerHopf.cpp:111-117) -- but with the
-// factor produced by the generalized SCHUR algorithm, which exploits the Toeplitz
-// displacement structure: O(n^2) work, every step purely elementwise (no reductions).
+// done the way the reference does it -- triangular factor, then two triangular solves
+// (arma::chol + solve(trimatl) + solve(trimatu), WienerHopf.cpp:111-117) -- with the factor
+// produced by the generalized SCHUR algorithm, which exploits the Toeplitz displacement
+// structure: O(n^2) work, every step purely elementwise (no reductions).
 //
-//   T - Z T Z^H = alpha alpha^H - beta beta^H,  alpha_i = t_i / sqrt(t_0), beta_0 = 0, beta_i = alpha_i
-//   (t_i = A(i,0) = conj(a[i])).  Step k -> k+1:
-//       column k of L            L(i,k) = alpha_i                      (i >= k)
-//       forward substitution     z_k = r_k / L(k,k);  r_i -= L(i,k) z_k      (fused)
-//       shift                    at_i = alpha_{i-1}
-//       hyperbolic rotation      rho = beta_{k+1} / alpha_k,  c = 1/sqrt(1 - |rho|^2)
-//                                alpha_i <- c (at_i - conj(rho) beta_i),  beta_i <- c (beta_i - rho at_i)
+// Normalised form (what Cholesky computes; t_i = A(i,0) = conj(a[i])):
+//   T - Z T Z^H = A A^H - B B^H,  A_i = t_i / sqrt(t_0), B_0 = 0, B_i = A_i.   Step k -> k+1:
+//       column k of L        L(i,k) = A_i                                   (i >= k)
+//       shift                At_i = A_{i-1}
+//       rotation             rho = B_{k+1} / A_k,  c = 1/sqrt(1 - |rho|^2)
+//                            A_i <- c (At_i - conj(rho) B_i),   B_i <- c (B_i - rho At_i)
 //   |rho| >= 1  <=>  A is not positive definite  <=>  the reference's chol() fails -> status 1.
-//   Second sweep: L^H w = z by column-oriented back substitution (rows of L read back from L2).
-// The Schur algorithm is backward stable for positive-definite Toeplitz matrices (Bojanczyk,
-// Brent, de Hoog, Sweet 1995), like the Cholesky factorisation it reproduces.
 //
-// Latency design: one CTA, one element per thread (two above 1024 taps), ONE __syncthreads per
-// step.  The per-step critical path is  LDS(pivot) -> rsqrt -> 2 FMAs -> STS; the L(k,k) pivots are
-// tracked as a scalar recurrence in every thread (alpha_{k+1,k+1} = alpha_{k,k} sqrt(1-|rho|^2)), so
-// no division and no reduction sits on the chain.  The next rows of L for the back substitution
-// are prefetched four steps ahead.
+// What the kernel runs is the FRACTION-FREE, SQUARE-ROOT-FREE version of the same recursion
+// (an LDL^H factorisation): with a_i = gamma_k A_i, b_i = gamma_k B_i, pivot p = a_k (real),
+//       a_i <- s (p at_i - conj(b_{k+1}) b_i),   b_i <- s (p b_i - b_{k+1} at_i),
+//       p   <- s (p^2 - |b_{k+1}|^2),            G = gamma^2 <- G s p_new,
+// s = an exact power of two that keeps p near 1.  No division, sqrt or rsqrt sits on the
+// step-to-step dependency chain (LDS pivot -> 3 FP64 ops -> STS -> barrier); p > 0 <=> |rho| < 1.
+// Forward substitution is fused and scale free:  r_i -= a_i (r_k / p);  the scaled solution
+// u_k = z_k gamma_k = r_k G / p feeds the back substitution  w_k = u_k / p_k,
+// u_j -= conj(a_k^{(j)}) w_k  (rows of the factor are read back from L2, prefetched).
+// The Schur algorithm is backward stable for positive-definite Toeplitz matrices (Bojanczyk,
+// Brent, de Hoog, Sweet 1995), like the Cholesky factorisation it reproduces; prototype and
+// accuracy check against LAPACK: tools/schur_prototype.py.
 // ---------------------------------------------------------------------------------
 struct SolveArgs {
   const double2 *partial;  // [nPartial][2][nBins]
   int nPartial, nBins;
   double2 *a_out, *b_out, *w_out;
-  double2 *L;   // [nBins][nBins] row-major scratch (lower triangle used)
+  double2 *L;   // [nBins][nBins] row-major scratch (lower triangle used): scaled factor a_i^{(k)}
   int *status;  // 0 ok, 1 failed
 };
+
+// 2^(1-e) where p*p = m 2^e, m in [0.5, 1): exact power of two, integer ops only
+__device__ __forceinline__ double pow2_scale(double p) {
+  const int ex = (__double2hiint(p * p) >> 20) & 0x7ff;
+  return __hiloint2double((2046 - ex) << 20, 0);
+}
 
 template <int EPT> __global__ void __launch_bounds__(1024, 1) wh_solve_kernel(SolveArgs s) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -217,9 +253,9 @@ template <int EPT> __global__ void __launch_bounds__(1024, 1) wh_solve_kernel(So
   double2 *alb0 = reinterpret_cast<double2 *>(smem_raw);
   double2 *alb1 = alb0 + n;
   double2 *pub_r = alb1 + n;   // r_k published by thread k   (reused for w_k in the second sweep)
-  double2 *pub_b = pub_r + n;  // beta_{k+1} published by thread k+1
-  double2 *zv = pub_b + n;     // z = L^-1 b
-  double *invd = reinterpret_cast<double *>(zv + n);  // 1 / L(k,k)
+  double2 *pub_b = pub_r + n;  // b_{k+1} published by thread k+1
+  double2 *uv = pub_b + n;     // u = scaled L^-1 b
+  double *ipv = reinterpret_cast<double *>(uv + n);  // 1 / p_k
   __shared__ double s_t0;
   const int tid = threadIdx.x, NTS = blockDim.x;
 
@@ -247,71 +283,73 @@ template <int EPT> __global__ void __launch_bounds__(1024, 1) wh_solve_kernel(So
   __syncthreads();
   const double t0 = s_t0;
   bool ok = (t0 > 0.0) && isfinite(t0);
-  double pivot = ok ? sqrt(t0) : 1.0;
-  double inv_pivot = 1.0 / pivot;
+  const double inv_t0 = ok ? 1.0 / t0 : 1.0;
 #pragma unroll
   for (int e = 0; e < EPT; e++) {
     const int i = tid + e * NTS;
     if (i < n) {
-      al[e].x *= inv_pivot; al[e].y *= inv_pivot;
+      al[e].x *= inv_t0; al[e].y *= inv_t0;  // a_i^(0) = t_i / t_0  (p_0 = 1, G_0 = 1 / t_0)
       be[e] = i ? al[e] : make_double2(0.0, 0.0);
       alb0[i] = al[e];
       s.L[(size_t)i * n] = al[e];
-      if (i == 0) { pub_r[0] = rr[e]; invd[0] = inv_pivot; }
+      if (i == 0) pub_r[0] = rr[e];
       if (i == 1) pub_b[0] = be[e];
     }
   }
   __syncthreads();
+  double p = 1.0, inv_p = 1.0, G = inv_t0, sc = 1.0;
   double2 *ac = alb0, *an = alb1;
   if (ok) {
     for (int k = 0; k < n - 1; k++) {
-      const double2 pr = pub_r[k], pb = pub_b[k];
-      const double2 z = make_double2(pr.x * inv_pivot, pr.y * inv_pivot);
-      const double2 rho = make_double2(pb.x * inv_pivot, pb.y * inv_pivot);
-      const double d = 1.0 - (rho.x * rho.x + rho.y * rho.y);
-      if (!(d > 0.0)) { ok = false; break; }  // uniform: every thread reads the same published pivot
-      const double c = rsqrt(d);
+      const double2 b = pub_b[k], rk = pub_r[k];
+      const double ps = p * sc;
+      const double2 bs = make_double2(b.x * sc, b.y * sc);
+      const double pn = ps * p - (bs.x * b.x + bs.y * b.y);  // p_{k+1} = s (p^2 - |b|^2)
+      if (!(pn > 0.0)) { ok = false; break; }  // uniform: every thread reads the same published pivot
+      const double2 q = make_double2(rk.x * inv_p, rk.y * inv_p);  // r_k / p_k
 #pragma unroll
       for (int e = 0; e < EPT; e++) {
         const int i = tid + e * NTS;
         if (i > k && i < n) {
           const double2 at = ac[i - 1];
-          // forward substitution with column k:  r_i -= L(i,k) z_k
-          rr[e].x -= al[e].x * z.x - al[e].y * z.y;
-          rr[e].y -= al[e].x * z.y + al[e].y * z.x;
-          // alpha' = c (at - conj(rho) beta),  beta' = c (beta - rho at)
           double2 na, nb;
-          na.x = c * (at.x - (rho.x * be[e].x + rho.y * be[e].y));
-          na.y = c * (at.y - (rho.x * be[e].y - rho.y * be[e].x));
-          nb.x = c * (be[e].x - (rho.x * at.x - rho.y * at.y));
-          nb.y = c * (be[e].y - (rho.x * at.y + rho.y * at.x));
+          na.x = ps * at.x - (bs.x * be[e].x + bs.y * be[e].y);   // s (p at - conj(b) be)
+          na.y = ps * at.y - (bs.x * be[e].y - bs.y * be[e].x);
+          nb.x = ps * be[e].x - (bs.x * at.x - bs.y * at.y);      // s (p be - b at)
+          nb.y = ps * be[e].y - (bs.x * at.y + bs.y * at.x);
+          an[i] = na;
+          if (i == k + 2) pub_b[k + 1] = nb;
+          // forward substitution with column k:  r_i -= a_i (r_k / p_k)
+          rr[e].x -= al[e].x * q.x - al[e].y * q.y;
+          rr[e].y -= al[e].x * q.y + al[e].y * q.x;
+          if (i == k + 1) pub_r[k + 1] = rr[e];
           al[e] = na;
           be[e] = nb;
-          an[i] = na;
           s.L[(size_t)i * n + (k + 1)] = na;
-          if (i == k + 1) pub_r[k + 1] = rr[e];
-          if (i == k + 2) pub_b[k + 1] = nb;
         }
       }
-      if (tid == 0) { zv[k] = z; invd[k + 1] = inv_pivot * c; }
-      pivot = pivot * d * c;  // L(k+1,k+1) = L(k,k) sqrt(1 - |rho|^2)
-      inv_pivot *= c;
+      if (tid == 0) { uv[k] = make_double2(q.x * G, q.y * G); ipv[k] = inv_p; }
+      G = G * sc * pn;
+      p = pn;
+      inv_p = 1.0 / pn;
+      sc = pow2_scale(pn);
       __syncthreads();
       double2 *t = ac; ac = an; an = t;
     }
   }
   if (ok && tid == 0) {
-    const double2 pr = pub_r[n - 1];
-    zv[n - 1] = make_double2(pr.x * inv_pivot, pr.y * inv_pivot);
+    const double2 rk = pub_r[n - 1];
+    uv[n - 1] = make_double2(rk.x * inv_p * G, rk.y * inv_p * G);
+    ipv[n - 1] = inv_p;
   }
   __syncthreads();
   if (ok) {
-    // second sweep: L^H w = z, column oriented; pub_r[k] <- w_k
+    // second sweep: back substitution in scaled units; pub_r[k] <- w_k
     double2 zz[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; e++) {
       const int i = tid + e * NTS;
-      zz[e] = i < n ? zv[i] : make_double2(0.0, 0.0);
+      zz[e] = i < n ? uv[i] : make_double2(0.0, 0.0);
     }
     constexpr int PF = 4;
     double2 lc[PF][EPT], ln[PF][EPT];
@@ -326,7 +364,6 @@ template <int EPT> __global__ void __launch_bounds__(1024, 1) wh_solve_kernel(So
         }
       }
     };
-    __threadfence_block();
     load_rows(n - 1, lc);
     for (int ktop = n - 1; ktop >= 0; ktop -= PF) {
       load_rows(ktop - PF, ln);
@@ -337,7 +374,7 @@ template <int EPT> __global__ void __launch_bounds__(1024, 1) wh_solve_kernel(So
 #pragma unroll
           for (int e = 0; e < EPT; e++) {
             const int i = tid + e * NTS;
-            if (i == k) pub_r[k] = make_double2(zz[e].x * invd[k], zz[e].y * invd[k]);
+            if (i == k) pub_r[k] = make_double2(zz[e].x * ipv[k], zz[e].y * ipv[k]);
           }
         }
         __syncthreads();
@@ -346,7 +383,7 @@ template <int EPT> __global__ void __launch_bounds__(1024, 1) wh_solve_kernel(So
 #pragma unroll
           for (int e = 0; e < EPT; e++) {
             const int i = tid + e * NTS;
-            if (i < k) {  // zz_i -= conj(L(k,i)) w_k
+            if (i < k) {  // u_i -= conj(a_k^(i)) w_k
               const double2 l = lc[q][e];
               zz[e].x -= l.x * w.x + l.y * w.y;
               zz[e].y -= l.x * w.y - l.y * w.x;
@@ -393,7 +430,7 @@ struct ApplyArgs {
   const double2 *tw;
   const int *status;
   uint32_t N;
-  int32_t delayMin;
+  XsMap xs;
   int nBins, Lout;
 };
 
@@ -421,10 +458,14 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, 1) wh_apply_kernel(ApplyArgs 
   }
   const int hist = a.nBins - 1;
   const double2 zero = make_double2(0.0, 0.0);
-  // window element m <-> shifted-reference index i0 - hist + m (zero history before sample 0)
+  // window element m <-> shifted-reference index i0 - hist + m (zero history before sample 0);
+  // branch-free: load from a clamped valid index, mask afterwards
+  const XsMap xs = a.xs;
   auto ldw = [&](int m) {
     const int64_t i = (int64_t)i0 - hist + m;
-    return (i >= 0 && i < (int64_t)a.N && m < hist + nOut) ? ld_iq(x, xs_index((uint32_t)i, a.delayMin, a.N)) : zero;
+    const int64_t ic = i < 0 ? 0 : (i >= (int64_t)a.N ? (int64_t)a.N - 1 : i);
+    const double2 v = ld_iq(x, xs((uint32_t)ic));
+    return (i >= 0 && i < (int64_t)a.N && m < hist + nOut) ? v : zero;
   };
   double2 v[16];
   fwd_fft_regs<LOG2M>(A, a.tw, tid, ldw, v);
@@ -489,7 +530,7 @@ template <int LOG2M, class TIN> int wh_launch_all(b200dd_wh *h, const void *x, c
     done = true;
   }
   CorrArgs ca;
-  ca.x = x; ca.y = y; ca.partial = h->d_partial; ca.tw = h->d_tw; ca.N = h->N; ca.delayMin = h->delayMin;
+  ca.x = x; ca.y = y; ca.partial = h->d_partial; ca.tw = h->d_tw; ca.N = h->N; ca.xs = make_xs_map(h->N, h->delayMin);
   ca.nBins = h->nBins; ca.L = h->L; ca.nSegTotal = h->nSeg; ca.segPerCta = h->segPerCta;
   if (ev) B2_CUDA(cudaEventRecord(ev[0], st));
   wh_corr_kernel<LOG2M, TIN><<<h->gridCorr, P::NT, corr_smem<LOG2M>(), st>>>(ca);
@@ -510,7 +551,7 @@ template <int LOG2M, class TIN> int wh_launch_all(b200dd_wh *h, const void *x, c
   B2_LAUNCH_CHECK();
   ApplyArgs aa;
   aa.x = x; aa.y = y; aa.y_out = y_out; aa.what = h->d_what; aa.tw = h->d_tw; aa.status = h->d_status;
-  aa.N = h->N; aa.delayMin = h->delayMin; aa.nBins = h->nBins; aa.Lout = h->Lout;
+  aa.N = h->N; aa.xs = ca.xs; aa.nBins = h->nBins; aa.Lout = h->Lout;
   wh_apply_kernel<LOG2M, TIN><<<h->gridApply, P::NT, fft_smem<LOG2M>(), st>>>(aa);
   B2_LAUNCH_CHECK();
   if (ev) B2_CUDA(cudaEventRecord(ev[3], st));
@@ -537,6 +578,7 @@ void wh_plan(b200dd_wh *h) {
     const int M = 1 << l;
     const int L = M - h->nBins + 1;
     if (L < M / 8) continue;
+    if ((uint32_t)M > h->N) continue;  // a window never wraps around the signal more than once
     double cost = (double)M * l / (double)L;
     if (forced == l) cost = -1.0;
     if (cost < best) { best = cost; best_l = l; }
@@ -587,7 +629,7 @@ int b200dd_wh_create(int32_t delay_min, int32_t delay_max, uint32_t n_samples, i
   if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaGetDeviceProperties", __FILE__, __LINE__));
   h->num_sms = prop.multiProcessorCount;
   wh_plan(h);
-  if (!h->log2m) return fail(geom_fail("b200dd_wh_create: too many taps for the FFT plan"));
+  if (!h->log2m) return fail(geom_fail("b200dd_wh_create: no FFT plan (needs nSamples >= 512 and nBins <= 2048)"));
   auto body = [&]() -> int {
     B2_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     const int M = 1 << h->log2m;

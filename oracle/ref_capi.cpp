@@ -33,6 +33,18 @@
 
 #define REF_API extern "C" __attribute__((visibility("default")))
 
+// Exceptions must not cross the C boundary into ctypes: report and turn into an error value.
+static thread_local char g_err[512] = "";
+#define REF_TRY try {
+#define REF_CATCH(retval)                                             \
+  }                                                                   \
+  catch (const std::exception &e) {                                   \
+    snprintf(g_err, sizeof(g_err), "%s", e.what());                   \
+    fprintf(stderr, "refpath: exception: %s\n", e.what());            \
+    return retval;                                                    \
+  }
+REF_API const char *refpath_last_error() { return g_err; }
+
 namespace {
 
 using Complex = std::complex<double>;
@@ -99,6 +111,7 @@ REF_API int refpath_ambiguity_geometry(int32_t delayMin, int32_t delayMax, int32
                                        uint32_t fs, uint32_t n, int roundHamming, uint32_t *nDelayBins,
                                        uint32_t *nDopplerBins, uint32_t *nCorr, uint32_t *nfft, double *cpi,
                                        double *dopplerMiddle) {
+  REF_TRY
   Ambiguity a(delayMin, delayMax, dopplerMin, dopplerMax, fs, n, roundHamming != 0);
   *nDelayBins = a.get_n_delay_bins();
   *nDopplerBins = a.get_n_doppler_bins();
@@ -107,6 +120,7 @@ REF_API int refpath_ambiguity_geometry(int32_t delayMin, int32_t delayMax, int32
   *cpi = a.get_cpi();
   *dopplerMiddle = a.get_doppler_middle();
   return 0;
+  REF_CATCH(-1000)
 }
 
 // x, y: nIn interleaved complex128 each.  map_o: [nDop][nDel] interleaved complex128.
@@ -116,6 +130,7 @@ REF_API int refpath_ambiguity_process(int32_t delayMin, int32_t delayMax, int32_
                                       uint32_t fs, uint32_t n, int roundHamming, const double *x, const double *y,
                                       uint32_t nIn, double *map_o, int32_t *delay_o, double *doppler_o,
                                       double *metrics, uint32_t *leftover) {
+  REF_TRY
   Ambiguity a(delayMin, delayMax, dopplerMin, dopplerMax, fs, n, roundHamming != 0);
   IqData xd(nIn), yd(nIn);
   fill_iq(xd, x, nIn);
@@ -130,12 +145,14 @@ REF_API int refpath_ambiguity_process(int32_t delayMin, int32_t delayMax, int32_
   leftover[0] = xd.get_length();
   leftover[1] = yd.get_length();
   return 0;
+  REF_CATCH(-1000)
 }
 
 // Returns 1 when the filter succeeded (y_io overwritten with the filtered surveillance
 // channel), 0 when WienerHopf::process returned false (y_io untouched).
 REF_API int refpath_wienerhopf_process(int32_t delayMin, int32_t delayMax, uint32_t nSamples, const double *x,
                                        double *y_io) {
+  REF_TRY
   WienerHopf wh(delayMin, delayMax, nSamples);
   IqData xd(nSamples), yd(nSamples);
   fill_iq(xd, x, nSamples);
@@ -148,6 +165,7 @@ REF_API int refpath_wienerhopf_process(int32_t delayMin, int32_t delayMax, uint3
     y_io[2 * i + 1] = data[i].imag();
   }
   return 1;
+  REF_CATCH(-1000)
 }
 
 REF_API void refpath_set_metrics(const double *m, uint32_t nDop, uint32_t nDel, double *metrics) {
@@ -162,32 +180,38 @@ REF_API void refpath_set_metrics(const double *m, uint32_t nDop, uint32_t nDel, 
 REF_API uint32_t refpath_cfar(double pfa, int nGuard, int nTrain, int minDelay, double minDoppler, const double *m,
                               uint32_t nDop, uint32_t nDel, const int32_t *delay, const double *doppler,
                               double noisePower, double *o_delay, double *o_doppler, double *o_snr, uint32_t cap) {
+  REF_TRY
   auto map = map_in(m, nDop, nDel, delay, doppler, noisePower);
   CfarDetector1D cfar(pfa, (int8_t)nGuard, (int8_t)nTrain, (int8_t)minDelay, minDoppler);
   auto det = cfar.process(map.get());
   return det_out(det.get(), o_delay, o_doppler, o_snr, cap);
+  REF_CATCH(0xFFFFFFFFu)
 }
 
 REF_API uint32_t refpath_centroid(uint32_t nDelay, uint32_t nDoppler, double resolutionDoppler, const double *delay,
                                   const double *doppler, const double *snr, uint32_t n, double *o_delay,
                                   double *o_doppler, double *o_snr, uint32_t cap) {
+  REF_TRY
   Detection in(std::vector<double>(delay, delay + n), std::vector<double>(doppler, doppler + n),
                std::vector<double>(snr, snr + n));
   Centroid cen((uint16_t)nDelay, (uint16_t)nDoppler, resolutionDoppler);
   auto det = cen.process(&in);
   return det_out(det.get(), o_delay, o_doppler, o_snr, cap);
+  REF_CATCH(0xFFFFFFFFu)
 }
 
 REF_API uint32_t refpath_interpolate(int doDelay, int doDoppler, const double *delay, const double *doppler,
                                      const double *snr, uint32_t n, const double *m, uint32_t nDop, uint32_t nDel,
                                      const int32_t *mdelay, const double *mdoppler, double noisePower,
                                      double *o_delay, double *o_doppler, double *o_snr, uint32_t cap) {
+  REF_TRY
   Detection in(std::vector<double>(delay, delay + n), std::vector<double>(doppler, doppler + n),
                std::vector<double>(snr, snr + n));
   auto map = map_in(m, nDop, nDel, mdelay, mdoppler, noisePower);
   Interpolate interp(doDelay != 0, doDoppler != 0);
   auto det = interp.process(&in, map.get());
   return det_out(det.get(), o_delay, o_doppler, o_snr, cap);
+  REF_CATCH(0xFFFFFFFFu)
 }
 
 // ---- whole chain with persistent objects (construction outside the timed region, as in
@@ -197,6 +221,7 @@ REF_API void *refpath_chain_create(int32_t delayMin, int32_t delayMax, int32_t d
                                    uint32_t fs, uint32_t n, int roundHamming, int clutterEnable,
                                    int32_t delayMinClutter, int32_t delayMaxClutter, double pfa, int nGuard,
                                    int nTrain, int minDelay, double minDoppler, uint32_t nCentroid) {
+  REF_TRY
   auto *c = new Chain;
   c->n = n;
   c->clutter = clutterEnable != 0;
@@ -207,6 +232,7 @@ REF_API void *refpath_chain_create(int32_t delayMin, int32_t delayMax, int32_t d
   c->cen = std::make_unique<Centroid>((uint16_t)nCentroid, (uint16_t)nCentroid, 1.0 / ((double)n / (double)fs));
   c->interp = std::make_unique<Interpolate>(true, true);
   return c;
+  REF_CATCH(nullptr)
 }
 
 REF_API void refpath_chain_destroy(void *h) { delete static_cast<Chain *>(h); }
@@ -215,6 +241,7 @@ REF_API void refpath_chain_destroy(void *h) { delete static_cast<Chain *>(h); }
 // Returns -1 if the clutter filter failed (CPI skipped, blah2.cpp:270-273), else #detections.
 REF_API int refpath_chain_run(void *h, const double *x, const double *y, double *map_o, double *metrics,
                               double *o_delay, double *o_doppler, double *o_snr, uint32_t cap, double *stage_ms) {
+  REF_TRY
   auto *c = static_cast<Chain *>(h);
   IqData xd(c->n), yd(c->n);
   fill_iq(xd, x, c->n);
@@ -242,4 +269,5 @@ REF_API int refpath_chain_run(void *h, const double *x, const double *y, double 
     metrics[1] = map->maxPower;
   }
   return (int)det_out(d3.get(), o_delay, o_doppler, o_snr, cap);
+  REF_CATCH(-1000)
 }

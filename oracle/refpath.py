@@ -41,7 +41,14 @@ def lib():
         _lib.refpath_cfar.restype = C.c_uint32
         _lib.refpath_centroid.restype = C.c_uint32
         _lib.refpath_interpolate.restype = C.c_uint32
+        _lib.refpath_last_error.restype = C.c_char_p
     return _lib
+
+
+def _check(rc, bad=(-1000,)):
+    if rc in bad:
+        raise RuntimeError("refpath: " + lib().refpath_last_error().decode("utf-8", "replace"))
+    return rc
 
 
 def _p(a):
@@ -59,10 +66,10 @@ def next_hamming(v: int) -> int:
 def ambiguity_geometry(delayMin, delayMax, dopplerMin, dopplerMax, fs, n, roundHamming=False) -> dict:
     nDel, nDop, nCorr, nfft = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
     cpi, mid = C.c_double(), C.c_double()
-    lib().refpath_ambiguity_geometry(C.c_int32(delayMin), C.c_int32(delayMax), C.c_int32(dopplerMin),
+    _check(lib().refpath_ambiguity_geometry(C.c_int32(delayMin), C.c_int32(delayMax), C.c_int32(dopplerMin),
                                      C.c_int32(dopplerMax), C.c_uint32(fs), C.c_uint32(n), C.c_int(int(roundHamming)),
                                      C.byref(nDel), C.byref(nDop), C.byref(nCorr), C.byref(nfft), C.byref(cpi),
-                                     C.byref(mid))
+                                     C.byref(mid)))
     return dict(nDelayBins=nDel.value, nDopplerBins=nDop.value, nCorr=nCorr.value, nfft=nfft.value, cpi=cpi.value,
                 dopplerMiddle=mid.value)
 
@@ -77,10 +84,10 @@ def ambiguity_process(x, y, delayMin, delayMax, dopplerMin, dopplerMax, fs, n, r
     doppler = np.empty(nDop, dtype=np.float64)
     metrics = np.empty(2, dtype=np.float64)
     left = np.empty(2, dtype=np.uint32)
-    lib().refpath_ambiguity_process(C.c_int32(delayMin), C.c_int32(delayMax), C.c_int32(dopplerMin),
+    _check(lib().refpath_ambiguity_process(C.c_int32(delayMin), C.c_int32(delayMax), C.c_int32(dopplerMin),
                                     C.c_int32(dopplerMax), C.c_uint32(fs), C.c_uint32(n), C.c_int(int(roundHamming)),
                                     _p(x), _p(y), C.c_uint32(x.shape[0]), _p(m), _p(delay), _p(doppler), _p(metrics),
-                                    _p(left))
+                                    _p(left)))
     g.update(map=m, delay=delay, doppler=doppler, noisePower=float(metrics[0]), maxPower=float(metrics[1]),
              leftover=(int(left[0]), int(left[1])))
     return g
@@ -88,8 +95,8 @@ def ambiguity_process(x, y, delayMin, delayMax, dopplerMin, dopplerMax, fs, n, r
 
 def wienerhopf_process(x, y, delayMin, delayMax):
     x, y = _c128(x), _c128(y).copy()
-    ok = lib().refpath_wienerhopf_process(C.c_int32(delayMin), C.c_int32(delayMax), C.c_uint32(x.shape[0]), _p(x),
-                                          _p(y))
+    ok = _check(lib().refpath_wienerhopf_process(C.c_int32(delayMin), C.c_int32(delayMax), C.c_uint32(x.shape[0]),
+                                                 _p(x), _p(y)))
     return bool(ok), y
 
 
@@ -113,6 +120,7 @@ def cfar_1d(m, delay, doppler, noisePower, pfa, nGuard, nTrain, minDelay, minDop
     n = lib().refpath_cfar(C.c_double(pfa), C.c_int(nGuard), C.c_int(nTrain), C.c_int(minDelay),
                            C.c_double(minDoppler), _p(m), C.c_uint32(m.shape[0]), C.c_uint32(m.shape[1]), _p(delay),
                            _p(doppler), C.c_double(noisePower), _p(od), _p(of), _p(os_), C.c_uint32(cap))
+    _check(n, (0xFFFFFFFF,))
     return od[:n].copy(), of[:n].copy(), os_[:n].copy()
 
 
@@ -124,6 +132,7 @@ def centroid(delay, doppler, snr, nDelay, nDoppler, resolutionDoppler):
     od, of, os_ = _det_bufs(cap)
     n = lib().refpath_centroid(C.c_uint32(nDelay), C.c_uint32(nDoppler), C.c_double(resolutionDoppler), _p(d), _p(f),
                                _p(s), C.c_uint32(d.shape[0]), _p(od), _p(of), _p(os_), C.c_uint32(cap))
+    _check(n, (0xFFFFFFFF,))
     return od[:n].copy(), of[:n].copy(), os_[:n].copy()
 
 
@@ -140,6 +149,7 @@ def interpolate(delay, doppler, snr, m, mdelay, mdoppler, noisePower, doDelay=Tr
                                   C.c_uint32(d.shape[0]), _p(m), C.c_uint32(m.shape[0]), C.c_uint32(m.shape[1]),
                                   _p(mdelay), _p(mdoppler), C.c_double(noisePower), _p(od), _p(of), _p(os_),
                                   C.c_uint32(cap))
+    _check(n, (0xFFFFFFFF,))
     return od[:n].copy(), of[:n].copy(), os_[:n].copy()
 
 
@@ -154,6 +164,8 @@ class Chain:
         self.h = lib().refpath_chain_create(delayMin, delayMax, dopplerMin, dopplerMax, fs, n, int(roundHamming),
                                             int(clutter is not None), cl[0], cl[1], pfa, nGuard, nTrain, minDelay,
                                             minDoppler, nCentroid)
+        if not self.h:
+            _check(-1000)
 
     def run(self, x, y, want_map=True):
         x, y = _c128(x), _c128(y)
@@ -166,6 +178,7 @@ class Chain:
         stage = np.zeros(3, dtype=np.float64)
         n = lib().refpath_chain_run(self.h, _p(x), _p(y), _p(m) if want_map else None, _p(metrics), _p(od), _p(of),
                                     _p(os_), C.c_uint32(cap), _p(stage))
+        _check(n)
         if n < 0:
             return dict(skipped=True, stage_ms=stage)
         return dict(skipped=False, map=m, noisePower=float(metrics[0]), maxPower=float(metrics[1]),
