@@ -463,10 +463,12 @@ void plan_range(b200dd_caf *h) {
     if (h->nSeg < 1) h->nSeg = 1;
     h->L = (nCorr + h->nSeg - 1) / h->nSeg;
     h->nSeg = (nCorr + h->L - 1) / h->L;
-    // occupancy: aim for >= 24 resident warps per SM by splitting batches into parts
-    const int warps_per_cta = (M / 16 + 31) / 32;
-    const int ctas_wanted = (h->num_sms * 24 + warps_per_cta - 1) / warps_per_cta;
+    // occupancy: with fewer batches than ~2 CTAs per SM, split batches into parts.  (Measured on
+    // BASELINE config 1, 257 batches: 1..3 parts are within 3 % of each other -- the kernel is
+    // FP32-issue bound there, profiles/r01_summary.md -- so splitting is reserved for small nDop.)
+    const int ctas_wanted = 2 * h->num_sms;
     int parts = (ctas_wanted + (int)h->g.nDop - 1) / (int)h->g.nDop;
+    if ((int)h->g.nDop >= h->num_sms) parts = 1;
     if (const char *e = getenv("B200DD_CAF_PARTS")) parts = atoi(e);
     if (parts < 1) parts = 1;
     if (parts > h->nSeg) parts = h->nSeg;

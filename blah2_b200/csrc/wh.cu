@@ -13,11 +13,11 @@
 //                                per-CTA partial sums reduced in a fixed order by K4.
 //   K4  wh_solve_kernel          W4: Hermitian Toeplitz system A w = b (the reference builds A
 //                                with arma::toeplitz and solves by Cholesky + two triangular solves,
-//                                :85-122).  Single CTA, FP64: Cholesky factor by the generalized Schur
-//                                algorithm (O(n^2), elementwise steps), forward substitution fused,
-//                                then back substitution.  "Not positive definite" (|rho| >= 1, i.e. a
-//                                non-positive Cholesky pivot) raises the failure flag = the reference's
-//                                `return false`.
+//                                :85-122).  Single CTA, FP64, one sweep of nBins elementwise steps:
+//                                generalized Schur recursion (Cholesky columns, reflection coefficients,
+//                                fused forward substitution) driving a Levinson accumulation of w.
+//                                "Not positive definite" (|rho| >= 1, i.e. a non-positive Cholesky
+//                                pivot) raises the failure flag = the reference's `return false`.
 //   K5  wh_apply_kernel<LOG2M>   W5: y'[i] = ys[i] - sum_{k<nBins, k<=i} w[k] xs[i-k]  (:125-160, a
 //                                LINEAR convolution with zero history) by overlap-save with the
 //                                spectrum of w computed once per CPI.
@@ -206,38 +206,39 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, 1) wh_corr_kernel(CorrArgs a)
 
 // ---------------------------------------------------------------------------------
 // K4: Hermitian positive-definite Toeplitz solve A w = b,
-//     A(i,j) = a[j-i] (j >= i), conj(a[i-j]) (i > j)   (WienerHopf.cpp:85-97),
-// done the way the reference does it -- triangular factor, then two triangular solves
-// (arma::chol + solve(trimatl) + solve(trimatu), WienerHopf.cpp:111-117) -- with the factor
-// produced by the generalized SCHUR algorithm, which exploits the Toeplitz displacement
-// structure: O(n^2) work, every step purely elementwise (no reductions).
+//     A(i,j) = a[j-i] (j >= i), conj(a[i-j]) (i > j)   (WienerHopf.cpp:85-97).
+// The reference factors A = R^H R (arma::chol) and does two triangular solves (:111-117).  We get
+// the same w, and the same "not positive definite" verdict, from ONE sweep of n elementwise steps:
 //
-// Normalised form (what Cholesky computes; t_i = A(i,0) = conj(a[i])):
-//   T - Z T Z^H = A A^H - B B^H,  A_i = t_i / sqrt(t_0), B_0 = 0, B_i = A_i.   Step k -> k+1:
-//       column k of L        L(i,k) = A_i                                   (i >= k)
-//       shift                At_i = A_{i-1}
-//       rotation             rho = B_{k+1} / A_k,  c = 1/sqrt(1 - |rho|^2)
-//                            A_i <- c (At_i - conj(rho) B_i),   B_i <- c (B_i - rho At_i)
-//   |rho| >= 1  <=>  A is not positive definite  <=>  the reference's chol() fails -> status 1.
+//  (1) the generalized SCHUR recursion on the displacement generator of the Toeplitz matrix
+//      (t_i = A(i,0) = conj(a[i]);  T - Z T Z^H = A A^H - B B^H, A_i = t_i/sqrt(t_0), B_0 = 0, B_i = A_i):
+//          column k of the Cholesky factor   L(i,k) = A_i                         (i >= k)
+//          forward substitution              r_i -= L(i,k) (r_k / L(k,k))         (fused)
+//          shift + hyperbolic rotation       rho_k = B_{k+1} / A_k,  A_i <- c (A_{i-1} - conj(rho) B_i),
+//                                            B_i <- c (B_i - rho A_{i-1}),  c = 1/sqrt(1 - |rho|^2)
+//      yields, WITHOUT any inner product, the reflection coefficients rho_k and the innovations
+//      r_k = b_k - (prediction of b_k from b_0..b_{k-1}).   |rho_k| >= 1  <=>  a Cholesky pivot is not
+//      positive  <=>  the reference's chol() fails -> status 1.
+//      It runs in FRACTION-FREE, SQUARE-ROOT-FREE form: a_i = gamma_k A_i, b_i = gamma_k B_i, pivot p = a_k,
+//          a_i <- s (p a_{i-1} - conj(b_{k+1}) b_i),  b_i <- s (p b_i - b_{k+1} a_{i-1}),  p <- s (p^2 - |b_{k+1}|^2)
+//      with s an exact power of two keeping p near 1; the forward substitution r_i -= a_i (r_k / p) is
+//      scale free.  No division, sqrt or rsqrt is on the step-to-step dependency chain.
+//  (2) a Levinson-type accumulation of the solution driven by those rho_k and r_k (classical Levinson
+//      needs two length-k inner products per step exactly for these two numbers):
+//          monic predictor  phi <- [phi; 0] - rho_k [0; J conj(phi)],   f = sigma phi solves T_k f = e_1,
+//          sigma <- sigma / (1 - |rho_k|^2),        x <- [x; 0] + r_k sigma J conj(phi).
 //
-// What the kernel runs is the FRACTION-FREE, SQUARE-ROOT-FREE version of the same recursion
-// (an LDL^H factorisation): with a_i = gamma_k A_i, b_i = gamma_k B_i, pivot p = a_k (real),
-//       a_i <- s (p at_i - conj(b_{k+1}) b_i),   b_i <- s (p b_i - b_{k+1} at_i),
-//       p   <- s (p^2 - |b_{k+1}|^2),            G = gamma^2 <- G s p_new,
-// s = an exact power of two that keeps p near 1.  No division, sqrt or rsqrt sits on the
-// step-to-step dependency chain (LDS pivot -> 3 FP64 ops -> STS -> barrier); p > 0 <=> |rho| < 1.
-// Forward substitution is fused and scale free:  r_i -= a_i (r_k / p);  the scaled solution
-// u_k = z_k gamma_k = r_k G / p feeds the back substitution  w_k = u_k / p_k,
-// u_j -= conj(a_k^{(j)}) w_k  (rows of the factor are read back from L2, prefetched).
-// The Schur algorithm is backward stable for positive-definite Toeplitz matrices (Bojanczyk,
-// Brent, de Hoog, Sweet 1995), like the Cholesky factorisation it reproduces; prototype and
-// accuracy check against LAPACK: tools/schur_prototype.py.
+// One CTA, one matrix row per thread (two above 1024 taps), ONE __syncthreads per step; thread i runs
+// part (2) while i <= k+1 and part (1) while i > k, so the CTA stays busy for all n steps.  No factor
+// is stored (an earlier two-sweep version spent most of its time scattering L to global memory:
+// profiles/r01_summary.md).  Prototype and accuracy check against LAPACK (1e-15 at 2048 taps):
+// tools/schur_prototype.py.  The Schur recursion is backward stable for positive-definite Toeplitz
+// matrices (Bojanczyk, Brent, de Hoog, Sweet 1995).
 // ---------------------------------------------------------------------------------
 struct SolveArgs {
   const double2 *partial;  // [nPartial][2][nBins]
   int nPartial, nBins;
   double2 *a_out, *b_out, *w_out;
-  double2 *L;   // [nBins][nBins] row-major scratch (lower triangle used): scaled factor a_i^{(k)}
   int *status;  // 0 ok, 1 failed
 };
 
@@ -250,21 +251,21 @@ __device__ __forceinline__ double pow2_scale(double p) {
 template <int EPT> __global__ void __launch_bounds__(1024, 1) wh_solve_kernel(SolveArgs s) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = s.nBins;
-  double2 *alb0 = reinterpret_cast<double2 *>(smem_raw);
+  double2 *alb0 = reinterpret_cast<double2 *>(smem_raw);  // generator a_i, ping-pong (neighbour shift)
   double2 *alb1 = alb0 + n;
-  double2 *pub_r = alb1 + n;   // r_k published by thread k   (reused for w_k in the second sweep)
+  double2 *phb0 = alb1 + n;    // predictor phi_i, ping-pong (mirrored access)
+  double2 *phb1 = phb0 + n;
+  double2 *pub_r = phb1 + n;   // r_k published by thread k
   double2 *pub_b = pub_r + n;  // b_{k+1} published by thread k+1
-  double2 *uv = pub_b + n;     // u = scaled L^-1 b
-  double *ipv = reinterpret_cast<double *>(uv + n);  // 1 / p_k
   __shared__ double s_t0;
   const int tid = threadIdx.x, NTS = blockDim.x;
 
-  double2 al[EPT], be[EPT], rr[EPT];
+  double2 al[EPT], be[EPT], rr[EPT], xx[EPT];
   // fixed-order reduction of the per-CTA partial correlations (deterministic)
 #pragma unroll
   for (int e = 0; e < EPT; e++) {
     const int i = tid + e * NTS;
-    al[e] = be[e] = rr[e] = make_double2(0.0, 0.0);
+    al[e] = be[e] = rr[e] = xx[e] = make_double2(0.0, 0.0);
     if (i < n) {
       double2 sa = make_double2(0.0, 0.0), sb = make_double2(0.0, 0.0);
       for (int p = 0; p < s.nPartial; p++) {
@@ -288,29 +289,33 @@ template <int EPT> __global__ void __launch_bounds__(1024, 1) wh_solve_kernel(So
   for (int e = 0; e < EPT; e++) {
     const int i = tid + e * NTS;
     if (i < n) {
-      al[e].x *= inv_t0; al[e].y *= inv_t0;  // a_i^(0) = t_i / t_0  (p_0 = 1, G_0 = 1 / t_0)
+      al[e].x *= inv_t0; al[e].y *= inv_t0;  // a_i^(0) = t_i / t_0  (p_0 = 1)
       be[e] = i ? al[e] : make_double2(0.0, 0.0);
       alb0[i] = al[e];
-      s.L[(size_t)i * n] = al[e];
+      phb0[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // phi^(1) = [1], sigma = 1 / t_0
+      phb1[i] = make_double2(0.0, 0.0);
       if (i == 0) pub_r[0] = rr[e];
       if (i == 1) pub_b[0] = be[e];
     }
   }
   __syncthreads();
-  double p = 1.0, inv_p = 1.0, G = inv_t0, sc = 1.0;
-  double2 *ac = alb0, *an = alb1;
+  double p = 1.0, inv_p = 1.0, sc = 1.0, sigma = inv_t0;
+  double2 *ac = alb0, *an = alb1, *pc = phb0, *pn_ = phb1;
   if (ok) {
     for (int k = 0; k < n - 1; k++) {
       const double2 b = pub_b[k], rk = pub_r[k];
+      const double2 rho = make_double2(b.x * inv_p, b.y * inv_p);
       const double ps = p * sc;
       const double2 bs = make_double2(b.x * sc, b.y * sc);
-      const double pn = ps * p - (bs.x * b.x + bs.y * b.y);  // p_{k+1} = s (p^2 - |b|^2)
-      if (!(pn > 0.0)) { ok = false; break; }  // uniform: every thread reads the same published pivot
-      const double2 q = make_double2(rk.x * inv_p, rk.y * inv_p);  // r_k / p_k
+      const double pnew = ps * p - (bs.x * b.x + bs.y * b.y);  // p_{k+1} = s (p^2 - |b|^2)
+      if (!(pnew > 0.0)) { ok = false; break; }  // uniform: every thread reads the same published pivot
+      const double2 q = make_double2(rk.x * inv_p, rk.y * inv_p);   // r_k / p_k
+      const double2 g = make_double2(rk.x * sigma, rk.y * sigma);   // r_k sigma
 #pragma unroll
       for (int e = 0; e < EPT; e++) {
         const int i = tid + e * NTS;
         if (i > k && i < n) {
+          // ---- (1) Schur: generator update and fused forward substitution
           const double2 at = ac[i - 1];
           double2 na, nb;
           na.x = ps * at.x - (bs.x * be[e].x + bs.y * be[e].y);   // s (p at - conj(b) be)
@@ -319,89 +324,56 @@ template <int EPT> __global__ void __launch_bounds__(1024, 1) wh_solve_kernel(So
           nb.y = ps * be[e].y - (bs.x * at.y + bs.y * at.x);
           an[i] = na;
           if (i == k + 2) pub_b[k + 1] = nb;
-          // forward substitution with column k:  r_i -= a_i (r_k / p_k)
-          rr[e].x -= al[e].x * q.x - al[e].y * q.y;
+          rr[e].x -= al[e].x * q.x - al[e].y * q.y;               // r_i -= a_i (r_k / p_k)
           rr[e].y -= al[e].x * q.y + al[e].y * q.x;
           if (i == k + 1) pub_r[k + 1] = rr[e];
           al[e] = na;
           be[e] = nb;
-          s.L[(size_t)i * n + (k + 1)] = na;
+        }
+        if (i <= k + 1 && i < n) {
+          // ---- (2) Levinson: x_i += (r_k sigma) conj(phi[k-i]) (i <= k);
+          //          phi'[i] = phi[i] (i <= k) - rho conj(phi[k+1-i]) (i >= 1)
+          const double2 ph_i = (i <= k) ? pc[i] : make_double2(0.0, 0.0);
+          const double2 ph_m = (i >= 1) ? pc[k + 1 - i] : make_double2(0.0, 0.0);
+          if (i <= k) {
+            const double2 ph_x = pc[k - i];
+            xx[e].x += g.x * ph_x.x + g.y * ph_x.y;
+            xx[e].y += g.y * ph_x.x - g.x * ph_x.y;
+          }
+          double2 np_;
+          np_.x = ph_i.x - (rho.x * ph_m.x + rho.y * ph_m.y);
+          np_.y = ph_i.y - (rho.y * ph_m.x - rho.x * ph_m.y);
+          pn_[i] = np_;
         }
       }
-      if (tid == 0) { uv[k] = make_double2(q.x * G, q.y * G); ipv[k] = inv_p; }
-      G = G * sc * pn;
-      p = pn;
-      inv_p = 1.0 / pn;
-      sc = pow2_scale(pn);
+      const double inv_pn = 1.0 / pnew;
+      sigma = sigma * sc * p * p * inv_pn;  // sigma / (1 - |rho|^2)
+      p = pnew;
+      inv_p = inv_pn;
+      sc = pow2_scale(pnew);
       __syncthreads();
       double2 *t = ac; ac = an; an = t;
+      t = pc; pc = pn_; pn_ = t;
     }
   }
-  if (ok && tid == 0) {
-    const double2 rk = pub_r[n - 1];
-    uv[n - 1] = make_double2(rk.x * inv_p * G, rk.y * inv_p * G);
-    ipv[n - 1] = inv_p;
-  }
-  __syncthreads();
   if (ok) {
-    // second sweep: back substitution in scaled units; pub_r[k] <- w_k
-    double2 zz[EPT];
+    // last innovation: x_i += (r_{n-1} sigma) conj(phi[n-1-i])
+    const double2 rk = pub_r[n - 1];
+    const double2 g = make_double2(rk.x * sigma, rk.y * sigma);
 #pragma unroll
     for (int e = 0; e < EPT; e++) {
       const int i = tid + e * NTS;
-      zz[e] = i < n ? uv[i] : make_double2(0.0, 0.0);
-    }
-    constexpr int PF = 4;
-    double2 lc[PF][EPT], ln[PF][EPT];
-    auto load_rows = [&](int ktop, double2 (&dst)[PF][EPT]) {
-#pragma unroll
-      for (int q = 0; q < PF; q++) {
-        const int row = ktop - q;
-#pragma unroll
-        for (int e = 0; e < EPT; e++) {
-          const int i = tid + e * NTS;
-          dst[q][e] = (row >= 0 && i < row) ? __ldcg(s.L + (size_t)row * n + i) : make_double2(0.0, 0.0);
-        }
+      if (i < n) {
+        const double2 ph_x = pc[n - 1 - i];
+        xx[e].x += g.x * ph_x.x + g.y * ph_x.y;
+        xx[e].y += g.y * ph_x.x - g.x * ph_x.y;
       }
-    };
-    load_rows(n - 1, lc);
-    for (int ktop = n - 1; ktop >= 0; ktop -= PF) {
-      load_rows(ktop - PF, ln);
-#pragma unroll
-      for (int q = 0; q < PF; q++) {
-        const int k = ktop - q;
-        if (k >= 0) {
-#pragma unroll
-          for (int e = 0; e < EPT; e++) {
-            const int i = tid + e * NTS;
-            if (i == k) pub_r[k] = make_double2(zz[e].x * ipv[k], zz[e].y * ipv[k]);
-          }
-        }
-        __syncthreads();
-        if (k >= 0) {
-          const double2 w = pub_r[k];
-#pragma unroll
-          for (int e = 0; e < EPT; e++) {
-            const int i = tid + e * NTS;
-            if (i < k) {  // u_i -= conj(a_k^(i)) w_k
-              const double2 l = lc[q][e];
-              zz[e].x -= l.x * w.x + l.y * w.y;
-              zz[e].y -= l.x * w.y - l.y * w.x;
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < PF; q++)
-#pragma unroll
-        for (int e = 0; e < EPT; e++) lc[q][e] = ln[q][e];
     }
-    __syncthreads();
   }
 #pragma unroll
   for (int e = 0; e < EPT; e++) {
     const int i = tid + e * NTS;
-    if (i < n) s.w_out[i] = ok ? pub_r[i] : make_double2(0.0, 0.0);
+    if (i < n) s.w_out[i] = ok ? xx[e] : make_double2(0.0, 0.0);
   }
   if (tid == 0) *s.status = ok ? 0 : 1;
 }
@@ -504,7 +476,7 @@ struct b200dd_wh {
   int log2m = 12;
   int L = 0, nSeg = 0, segPerCta = 1, gridCorr = 1;  // correlation stage
   int Lout = 0, gridApply = 1;                       // filter stage
-  double2 *d_tw = nullptr, *d_partial = nullptr, *d_a = nullptr, *d_b = nullptr, *d_w = nullptr, *d_what = nullptr, *d_L = nullptr;
+  double2 *d_tw = nullptr, *d_partial = nullptr, *d_a = nullptr, *d_b = nullptr, *d_w = nullptr, *d_what = nullptr;
   int *d_status = nullptr;
   double2 *d_xd = nullptr, *d_yd = nullptr;  // host path staging (complex128)
   int num_sms = 148;
@@ -519,7 +491,7 @@ template <int LOG2M> size_t fft_smem() { return (size_t)Plan<LOG2M>::MP * sizeof
 template <int LOG2M, class TIN> int wh_launch_all(b200dd_wh *h, const void *x, const void *y, void *y_out, cudaStream_t st,
                                                   cudaEvent_t *ev) {
   using P = Plan<LOG2M>;
-  const size_t solve_smem = (size_t)h->nBins * (5 * sizeof(double2) + sizeof(double));
+  const size_t solve_smem = (size_t)h->nBins * 6 * sizeof(double2);
   bool &done = sizeof(typename std::remove_pointer<decltype(TIN::x) *>::type) == 4 ? h->attr_f32 : h->attr_f64;
   if (!done) {
     B2_CUDA(cudaFuncSetAttribute(wh_corr_kernel<LOG2M, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_smem<LOG2M>()));
@@ -538,7 +510,7 @@ template <int LOG2M, class TIN> int wh_launch_all(b200dd_wh *h, const void *x, c
   if (ev) B2_CUDA(cudaEventRecord(ev[1], st));
   SolveArgs sa;
   sa.partial = h->d_partial; sa.nPartial = h->gridCorr; sa.nBins = h->nBins;
-  sa.a_out = h->d_a; sa.b_out = h->d_b; sa.w_out = h->d_w; sa.status = h->d_status; sa.L = h->d_L;
+  sa.a_out = h->d_a; sa.b_out = h->d_b; sa.w_out = h->d_w; sa.status = h->d_status;
   if (h->nBins <= 1024) {
     const int threads = ((h->nBins + 31) / 32) * 32;
     wh_solve_kernel<1><<<1, threads, solve_smem, st>>>(sa);
@@ -641,7 +613,6 @@ int b200dd_wh_create(int32_t delay_min, int32_t delay_max, uint32_t n_samples, i
     B2_CUDA(cudaMalloc(&h->d_b, sizeof(double2) * h->nBins));
     B2_CUDA(cudaMalloc(&h->d_w, sizeof(double2) * h->nBins));
     B2_CUDA(cudaMalloc(&h->d_what, sizeof(double2) * M));
-    B2_CUDA(cudaMalloc(&h->d_L, sizeof(double2) * (size_t)h->nBins * h->nBins));
     B2_CUDA(cudaMalloc(&h->d_status, sizeof(int)));
     B2_CUDA(cudaMemset(h->d_status, 0, sizeof(int)));
     return B200DD_OK;
@@ -663,7 +634,6 @@ void b200dd_wh_destroy(b200dd_wh *h) {
     free_dev(h->d_b);
     free_dev(h->d_w);
     free_dev(h->d_what);
-    free_dev(h->d_L);
     free_dev(h->d_status);
     free_dev(h->d_xd);
     free_dev(h->d_yd);
