@@ -179,6 +179,7 @@ def main():
 
     from blah2_b200.process import Ambiguity, Pipeline, WienerHopf
     from blah2_b200.scene import make_scene
+    from blah2_b200.shard import gather_maps
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
@@ -205,7 +206,7 @@ def main():
     hmap = torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex128).pin_memory()
     dmaps = [torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda") for _ in range(NPIPE)]
     dmap = dmaps[0]
-    gathered = [torch.empty_like(dmap) for _ in range(world)] if (world > 1 and rank == 0) else None
+    gathered = None
     streams = [torch.cuda.Stream() for _ in range(NPIPE)]
     stream = streams[0]
     st = stream.cuda_stream
@@ -240,7 +241,7 @@ def main():
         last = pipes[p].fetch(streams[p].cuda_stream)
     with torch.cuda.stream(stream):
         if world > 1:  # the final map gather (NCCL over NVLink), ordered after the kernels on `stream`
-            dist.gather(dmap, gathered, dst=0)
+            gathered = gather_maps(dmap.unsqueeze(0), world, rank, world)
         e1.record(stream)
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")

@@ -78,6 +78,12 @@ template <int R> B2_HD constexpr int ilog2() {
   return l;
 }
 
+B2_HD constexpr int ilog2_rt(int r) {
+  int l = 0;
+  for (; r > 1; r >>= 1) l++;
+  return l;
+}
+
 // cos(2 pi k / 32) for k = 0..8 and by symmetry for any k
 template <class T> B2_HD constexpr T cos32_q(int k) {
   return k == 0 ? T(1.0)
@@ -179,36 +185,38 @@ B2_HD void fft_butterfly(int b, int log2S, const cpx<T> *__restrict__ tw, LD ld,
   cpx<T> v[R];
 #pragma unroll
   for (int k = 0; k < R; k++) v[k] = ld(base + (k << log2S));
-  // Twiddles w^q, q = 1..R-1, with w = exp(-2 pi i lo / ncur) = tw[lo * (M / ncur)]: ONE table load,
-  // the powers by a depth-<=4 product tree in registers (squarings where possible).  This replaces
-  // R-1 dependent-latency table loads per butterfly (the dominant stall in the first profile,
-  // profiles/r01_first_ncu.md) by ~3.5 flops per twiddle.
-  cpx<T> w[R];
+  // Twiddles w^q, q = 1..R-1, with w = exp(-2 pi i lo / ncur) = tw[lo * (M / ncur)]: ONE table load; the
+  // powers are formed on the fly, w^q = w^(q - lowbit) * w^(lowbit), and consumed immediately, so only the
+  // powers of two and one running product are live (keeps the FP64 kernels under 128 registers).  This
+  // replaced R-1 dependent-latency table loads per butterfly, the dominant stall in the first profile
+  // (profiles/r01_summary.md), by ~3.5 flops per twiddle; depth <= 4 products, error ~4 ulp.
+  if constexpr (DIR < 0) dft_reg<T, R, DIR>(v);
   if (log2S > 0) {
     const int tstep = lo << (LOG2M - log2S - ilog2<R>());
-    w[1] = tw[tstep];
-    if constexpr (R > 2) {
+    cpx<T> wp[ilog2<R>() > 0 ? ilog2<R>() : 1];  // w^1, w^2, w^4, ...
+    wp[0] = tw[tstep];
 #pragma unroll
-      for (int q = 2; q < R; q++) {
-        // q = a + b with a = largest power of two <= q/2 ... choose a = q/2, b = q - q/2 (depth log2 q)
-        const int a = q >> 1, b = q - a;
-        w[q] = (a == b) ? mk<T>(w[a].x * w[a].x - w[a].y * w[a].y, (w[a].x + w[a].x) * w[a].y) : cmul(w[a], w[b]);
-      }
+    for (int j = 1; j < ilog2<R>(); j++)
+      wp[j] = mk<T>(wp[j - 1].x * wp[j - 1].x - wp[j - 1].y * wp[j - 1].y, (wp[j - 1].x + wp[j - 1].x) * wp[j - 1].y);
+    cpx<T> run = wp[0];  // w^(q with its lowest set bit cleared), valid when that is non-zero
+    cpx<T> hold = wp[0];
+#pragma unroll
+    for (int q = 1; q < R; q++) {
+      const int low = q & -q, rest = q - low;
+      int lj = 0;
+      for (int t = low; t > 1; t >>= 1) lj++;
+      cpx<T> wq;
+      if (rest == 0) wq = wp[lj];
+      else wq = cmul((rest & (rest - 1)) == 0 ? wp[ilog2_rt(rest)] : ((rest == (q - 1) && low == 1) ? run : hold), wp[lj]);
+      // bookkeeping of the two running products: `run` = w^(q) for use by q+1 (odd), `hold` = w^(q) kept
+      // for q with the same upper bits (e.g. w^12 for 13, 14; w^6 for 7; w^10 for 11; w^14 for 15)
+      run = wq;
+      if ((q & 1) == 0) hold = wq;
+      if constexpr (DIR > 0) v[q] = cmulc(v[q], wq);
+      else v[brev<R>(q)] = cmul(v[brev<R>(q)], wq);
     }
   }
-  if constexpr (DIR > 0) {
-    if (log2S > 0) {
-#pragma unroll
-      for (int q = 1; q < R; q++) v[q] = cmulc(v[q], w[q]);
-    }
-  }
-  dft_reg<T, R, DIR>(v);
-  if constexpr (DIR < 0) {
-    if (log2S > 0) {
-#pragma unroll
-      for (int q = 1; q < R; q++) v[brev<R>(q)] = cmul(v[brev<R>(q)], w[q]);
-    }
-  }
+  if constexpr (DIR > 0) dft_reg<T, R, DIR>(v);
 #pragma unroll
   for (int q = 0; q < R; q++) st(base + (q << log2S), v[brev<R>(q)]);
 }

@@ -79,6 +79,9 @@ template <class TIN> __device__ __forceinline__ double2 ld_iq(const TIN *p, uint
   return make_double2((double)v.x, (double)v.y);
 }
 
+// resident CTAs per SM the register allocator leaves room for (<= 128 registers per thread)
+template <int LOG2M> constexpr int wh_min_ctas() { return 512 / Plan<LOG2M>::NT > 8 ? 8 : 512 / Plan<LOG2M>::NT; }
+
 struct CorrArgs {
   const void *x;
   const void *y;
@@ -414,7 +417,7 @@ template <> __device__ __forceinline__ void st_iq<double2>(double2 *p, uint32_t 
 
 // one CTA per block of Lout outputs: window of M = Lout + nBins - 1 shifted-reference samples
 template <int LOG2M, class TIN>
-__global__ void __launch_bounds__(Plan<LOG2M>::NT, 1) wh_apply_kernel(ApplyArgs a) {
+__global__ void __launch_bounds__(Plan<LOG2M>::NT, wh_min_ctas<LOG2M>()) wh_apply_kernel(ApplyArgs a) {
   using P = Plan<LOG2M>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *A = reinterpret_cast<double2 *>(smem_raw);
