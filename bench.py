@@ -272,6 +272,32 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
 
+    # ---- the same, fed with the reference's replay layout (int16 I1 Q1 I2 Q2, 8 B per instant) ----
+    def to_i16(b):
+        x_, y_ = np.roll(sc.x, 977 * b), np.roll(sc.y, 977 * b)
+        iq = np.empty((N, 4), dtype="<i2")
+        iq[:, 0], iq[:, 1], iq[:, 2], iq[:, 3] = x_.real, x_.imag, y_.real, y_.imag
+        return torch.from_numpy(iq).pin_memory()
+
+    hq = [to_i16(b) for b in range(2)]
+    for i in range(NPIPE):
+        pipes[i].submit_host_rspduo(hq[i % 2], map_out=hmaps[i])
+        pipes[i].fetch()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        p = i % NPIPE
+        if i >= NPIPE:
+            r_i16 = pipes[p].fetch()
+        pipes[p].submit_host_rspduo(hq[i % 2], map_out=hmaps[p])
+    for i in range(e2e_steps, e2e_steps + NPIPE):
+        r_i16 = pipes[i % NPIPE].fetch()
+    torch.cuda.synchronize()
+    i16_s = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(i16_s, op=dist.ReduceOp.MAX)
+    i16_s = float(i16_s.item())
+
     # ---- per-kernel durations for the roofline (CUDA events around each kernel) ----
     amb = Ambiguity(GEOM["delayMin"], GEOM["delayMax"], GEOM["dopplerMin"], GEOM["dopplerMax"], FS, N, True,
                     device=local_rank)
@@ -314,6 +340,10 @@ def main():
                 "ms_per_step": round(e2e_s / e2e_steps * 1e3, 4), "steps": e2e_steps,
                 "api": "Pipeline.submit_host(pinned complex128 x, y) / fetch() -> complex128 map + detections, "
                        f"{NPIPE} CPIs in flight"},
+        "e2e_rspduo_int16": {"value": round(world * e2e_steps * N / i16_s / 1e6, 2), "unit": "Msamples/s",
+                             "h2d_bytes_per_step": 8 * N, "ms_per_step": round(i16_s / e2e_steps * 1e3, 4),
+                             "api": "Pipeline.submit_host_rspduo(pinned int16 I1 Q1 I2 Q2) / fetch()",
+                             "n_detections": int(r_i16["detections"].get_nDetections())},
         "gpu_launches": KERNELS_PER_STEP * args.steps,
         "clocks": clocks,
         "roofline": {"kernel": "caf_range_kernel", "bound": "hbm", "achieved": round(ach_range, 1), "peak": peak,

@@ -112,6 +112,7 @@ SIGNATURES = [
     ("b200dd_pipeline_process_host", C.c_int, [_VP, _VP, _VP, C.c_uint32, _VP, C.POINTER(CpiResult), _VP, _VP, _VP,
                                                C.c_uint32]),
     ("b200dd_pipeline_submit_host", C.c_int, [_VP, _VP, _VP, C.c_uint32, _VP]),
+    ("b200dd_pipeline_submit_host_rspduo", C.c_int, [_VP, _VP, C.c_uint32, _VP]),
     ("b200dd_pipeline_submit_device", C.c_int, [_VP, _VP, _VP, C.c_uint32, _VP, _VP]),
     ("b200dd_pipeline_fetch", C.c_int, [_VP, C.POINTER(CpiResult), _VP, _VP, _VP, C.c_uint32, _VP]),
     ("b200dd_pipeline_stream", _VP, [_VP]),

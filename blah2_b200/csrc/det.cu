@@ -555,8 +555,8 @@ int b200dd_det_create(const b200dd_det_params *params, uint32_t max_doppler_bins
     B2_CUDA(cudaMalloc(&h->d_keep, h->cap));
     B2_CUDA(cudaMalloc(&h->d_part, sizeof(double) * 2 * h->nPart));
     B2_CUDA(cudaMalloc(&h->d_metrics, sizeof(double) * 2));
-    B2_CUDA(cudaFuncSetAttribute(cfar_flag_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * h->maxDel)));
-    B2_CUDA(cudaFuncSetAttribute(cfar_flag_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * h->maxDel)));
+    B2_CUDA(cudaFuncSetAttribute(cfar_flag_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 16384)));  // per function, not per handle: always the supported maximum
+    B2_CUDA(cudaFuncSetAttribute(cfar_flag_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 16384)));
     return B200DD_OK;
   };
   int rc = body();

@@ -25,6 +25,18 @@ __global__ void pl_widen_kernel(const float2 *__restrict__ in, double2 *__restri
   }
 }
 
+// RSPduo replay / capture layout: little-endian int16 I1 Q1 I2 Q2 per time instant
+// (reference src/capture/rspduo/RspDuo.cpp:155-174, test reader TestAmbiguity.cpp:39-69).
+// channel 1 = reference x, channel 2 = surveillance y.  One 8-byte load per instant.
+__global__ void pl_ingest_rspduo_kernel(const short4 *__restrict__ in, float2 *__restrict__ x, float2 *__restrict__ y,
+                                        uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const short4 v = in[i];
+    x[i] = make_float2((float)v.x, (float)v.y);
+    y[i] = make_float2((float)v.z, (float)v.w);
+  }
+}
+
 inline int grid_for(uint32_t n) {
   int b = (int)((n + 255u) / 256u);
   return b > 148 * 8 ? 148 * 8 : (b < 1 ? 1 : b);
@@ -47,6 +59,7 @@ struct b200dd_pipeline {
   float2 *d_xf = nullptr, *d_yf2 = nullptr;
   double2 *d_mapd = nullptr;
   float2 *d_map = nullptr;
+  short4 *d_iq16 = nullptr;  // int16 ingest staging
   bool last_had_filter = false;
 };
 
@@ -107,6 +120,7 @@ void b200dd_pipeline_destroy(b200dd_pipeline *h) {
     free_dev(h->d_yf2);
     free_dev(h->d_mapd);
     free_dev(h->d_map);
+    free_dev(h->d_iq16);
     if (h->stream) cudaStreamDestroy(h->stream);
   }
   delete h;
@@ -189,9 +203,11 @@ int b200dd_pipeline_submit_host(b200dd_pipeline *h, const double *x, const doubl
   if (!h->d_xd) {
     B2_CUDA(cudaMalloc(&h->d_xd, sizeof(double2) * N));
     B2_CUDA(cudaMalloc(&h->d_yd, sizeof(double2) * N));
-    B2_CUDA(cudaMalloc(&h->d_xf, sizeof(float2) * N));
-    B2_CUDA(cudaMalloc(&h->d_yf2, sizeof(float2) * N));
-    B2_CUDA(cudaMalloc(&h->d_mapd, sizeof(double2) * (size_t)h->g.n_doppler_bins * h->g.n_delay_bins));
+    if (!h->d_xf) {
+      B2_CUDA(cudaMalloc(&h->d_xf, sizeof(float2) * N));
+      B2_CUDA(cudaMalloc(&h->d_yf2, sizeof(float2) * N));
+    }
+    if (!h->d_mapd) B2_CUDA(cudaMalloc(&h->d_mapd, sizeof(double2) * (size_t)h->g.n_doppler_bins * h->g.n_delay_bins));
   }
   B2_CUDA(cudaMemcpyAsync(h->d_xd, x, sizeof(double2) * need, cudaMemcpyHostToDevice, st));
   B2_CUDA(cudaMemcpyAsync(h->d_yd, y, sizeof(double2) * need, cudaMemcpyHostToDevice, st));
@@ -213,6 +229,37 @@ int b200dd_pipeline_submit_host(b200dd_pipeline *h, const double *x, const doubl
                                        h->g.n_delay_bins, h->delay.data(), h->doppler.data(), st);
     if (rc != B200DD_OK) return rc;
   }
+  if (map_out) {
+    const uint32_t cells = h->g.n_doppler_bins * h->g.n_delay_bins;
+    pl_widen_kernel<<<grid_for(cells), 256, 0, st>>>(h->d_map, h->d_mapd, cells);
+    B2_LAUNCH_CHECK();
+    B2_CUDA(cudaMemcpyAsync(map_out, h->d_mapd, sizeof(double2) * cells, cudaMemcpyDeviceToHost, st));
+  }
+  return B200DD_OK;
+}
+
+int b200dd_pipeline_submit_host_rspduo(b200dd_pipeline *h, const int16_t *iq, uint32_t n, double *map_out) {
+  if (!h || !iq) return arg_fail("b200dd_pipeline_submit_host_rspduo: null argument");
+  const uint32_t N = h->p.caf.n_samples;
+  const uint32_t need = h->wh ? N : h->g.n_used;
+  if (h->wh ? (n != N) : (n < need)) return arg_fail("b200dd_pipeline_submit_host_rspduo: wrong number of samples");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = h->stream;
+  if (!h->d_iq16) {
+    B2_CUDA(cudaMalloc(&h->d_iq16, sizeof(short4) * N));
+    if (!h->d_xf) {
+      B2_CUDA(cudaMalloc(&h->d_xf, sizeof(float2) * N));
+      B2_CUDA(cudaMalloc(&h->d_yf2, sizeof(float2) * N));
+    }
+  }
+  if (map_out && !h->d_mapd) B2_CUDA(cudaMalloc(&h->d_mapd, sizeof(double2) * (size_t)h->g.n_doppler_bins * h->g.n_delay_bins));
+  B2_CUDA(cudaMemcpyAsync(h->d_iq16, iq, sizeof(short4) * need, cudaMemcpyHostToDevice, st));
+  pl_ingest_rspduo_kernel<<<grid_for(need), 256, 0, st>>>(h->d_iq16, h->d_xf, h->d_yf2, need);
+  B2_LAUNCH_CHECK();
+  // int16 samples are exact in float32, so the float2 device path gives the same result as the
+  // complex128 host path
+  int rc = b200dd_pipeline_submit_device(h, h->d_xf, h->d_yf2, need, h->d_map, st);
+  if (rc != B200DD_OK) return rc;
   if (map_out) {
     const uint32_t cells = h->g.n_doppler_bins * h->g.n_delay_bins;
     pl_widen_kernel<<<grid_for(cells), 256, 0, st>>>(h->d_map, h->d_mapd, cells);

@@ -476,14 +476,14 @@ struct b200dd_wh {
   int nBins = 0;
   int device = 0;
   cudaStream_t stream = nullptr;
-  int log2m = 12;
+  int log2m_c = 12, log2m_a = 12;  // FFT lengths of the correlation / filter stages
   int L = 0, nSeg = 0, segPerCta = 1, gridCorr = 1;  // correlation stage
   int Lout = 0, gridApply = 1;                       // filter stage
-  double2 *d_tw = nullptr, *d_partial = nullptr, *d_a = nullptr, *d_b = nullptr, *d_w = nullptr, *d_what = nullptr;
+  double2 *d_tw_c = nullptr, *d_tw_a = nullptr, *d_partial = nullptr, *d_a = nullptr, *d_b = nullptr, *d_w = nullptr, *d_what = nullptr;
   int *d_status = nullptr;
   double2 *d_xd = nullptr, *d_yd = nullptr;  // host path staging (complex128)
   int num_sms = 148;
-  bool attr_f32 = false, attr_f64 = false;
+  bool attr_corr_f32 = false, attr_corr_f64 = false, attr_apply_f32 = false, attr_apply_f64 = false, attr_solve = false;
 };
 
 namespace {
@@ -491,26 +491,50 @@ namespace {
 template <int LOG2M> size_t corr_smem() { return (size_t)(Plan<LOG2M>::MP + 2 * Plan<LOG2M>::M) * sizeof(double2); }
 template <int LOG2M> size_t fft_smem() { return (size_t)Plan<LOG2M>::MP * sizeof(double2); }
 
-template <int LOG2M, class TIN> int wh_launch_all(b200dd_wh *h, const void *x, const void *y, void *y_out, cudaStream_t st,
-                                                  cudaEvent_t *ev) {
+template <class TIN> constexpr bool is_f32() { return sizeof(TIN) == sizeof(float2); }
+
+// correlation stage with its own FFT length (smaller M -> two CTAs per SM fit beside the accumulators)
+template <int LOG2M, class TIN> int wh_launch_corr(b200dd_wh *h, const void *x, const void *y, cudaStream_t st) {
   using P = Plan<LOG2M>;
-  const size_t solve_smem = (size_t)h->nBins * 6 * sizeof(double2);
-  bool &done = sizeof(typename std::remove_pointer<decltype(TIN::x) *>::type) == 4 ? h->attr_f32 : h->attr_f64;
+  bool &done = is_f32<TIN>() ? h->attr_corr_f32 : h->attr_corr_f64;
   if (!done) {
     B2_CUDA(cudaFuncSetAttribute(wh_corr_kernel<LOG2M, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_smem<LOG2M>()));
-    B2_CUDA(cudaFuncSetAttribute(wh_apply_kernel<LOG2M, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M>()));
-    B2_CUDA(cudaFuncSetAttribute(wh_wspec_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M>()));
-    B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
-    B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
     done = true;
   }
   CorrArgs ca;
-  ca.x = x; ca.y = y; ca.partial = h->d_partial; ca.tw = h->d_tw; ca.N = h->N; ca.xs = make_xs_map(h->N, h->delayMin);
+  ca.x = x; ca.y = y; ca.partial = h->d_partial; ca.tw = h->d_tw_c; ca.N = h->N; ca.xs = make_xs_map(h->N, h->delayMin);
   ca.nBins = h->nBins; ca.L = h->L; ca.nSegTotal = h->nSeg; ca.segPerCta = h->segPerCta;
-  if (ev) B2_CUDA(cudaEventRecord(ev[0], st));
   wh_corr_kernel<LOG2M, TIN><<<h->gridCorr, P::NT, corr_smem<LOG2M>(), st>>>(ca);
   B2_LAUNCH_CHECK();
-  if (ev) B2_CUDA(cudaEventRecord(ev[1], st));
+  return B200DD_OK;
+}
+
+template <int LOG2M, class TIN> int wh_launch_apply(b200dd_wh *h, const void *x, const void *y, void *y_out, cudaStream_t st) {
+  using P = Plan<LOG2M>;
+  bool &done = is_f32<TIN>() ? h->attr_apply_f32 : h->attr_apply_f64;
+  if (!done) {
+    B2_CUDA(cudaFuncSetAttribute(wh_apply_kernel<LOG2M, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M>()));
+    B2_CUDA(cudaFuncSetAttribute(wh_wspec_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M>()));
+    done = true;
+  }
+  wh_wspec_kernel<LOG2M><<<1, P::NT, fft_smem<LOG2M>(), st>>>(h->d_w, h->nBins, h->d_what, h->d_tw_a);
+  B2_LAUNCH_CHECK();
+  ApplyArgs aa;
+  aa.x = x; aa.y = y; aa.y_out = y_out; aa.what = h->d_what; aa.tw = h->d_tw_a; aa.status = h->d_status;
+  aa.N = h->N; aa.xs = make_xs_map(h->N, h->delayMin); aa.nBins = h->nBins; aa.Lout = h->Lout;
+  wh_apply_kernel<LOG2M, TIN><<<h->gridApply, P::NT, fft_smem<LOG2M>(), st>>>(aa);
+  B2_LAUNCH_CHECK();
+  return B200DD_OK;
+}
+
+int wh_launch_solve(b200dd_wh *h, cudaStream_t st) {
+  const size_t solve_smem = (size_t)h->nBins * 6 * sizeof(double2);
+  const size_t solve_smem_max = (size_t)kMaxBins * 6 * sizeof(double2);  // attribute is per function, not per handle
+  if (!h->attr_solve) {
+    B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
+    B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
+    h->attr_solve = true;
+  }
   SolveArgs sa;
   sa.partial = h->d_partial; sa.nPartial = h->gridCorr; sa.nBins = h->nBins;
   sa.a_out = h->d_a; sa.b_out = h->d_b; sa.w_out = h->d_w; sa.status = h->d_status;
@@ -521,32 +545,41 @@ template <int LOG2M, class TIN> int wh_launch_all(b200dd_wh *h, const void *x, c
     wh_solve_kernel<2><<<1, 1024, solve_smem, st>>>(sa);
   }
   B2_LAUNCH_CHECK();
-  if (ev) B2_CUDA(cudaEventRecord(ev[2], st));
-  wh_wspec_kernel<LOG2M><<<1, P::NT, fft_smem<LOG2M>(), st>>>(h->d_w, h->nBins, h->d_what, h->d_tw);
-  B2_LAUNCH_CHECK();
-  ApplyArgs aa;
-  aa.x = x; aa.y = y; aa.y_out = y_out; aa.what = h->d_what; aa.tw = h->d_tw; aa.status = h->d_status;
-  aa.N = h->N; aa.xs = ca.xs; aa.nBins = h->nBins; aa.Lout = h->Lout;
-  wh_apply_kernel<LOG2M, TIN><<<h->gridApply, P::NT, fft_smem<LOG2M>(), st>>>(aa);
-  B2_LAUNCH_CHECK();
-  if (ev) B2_CUDA(cudaEventRecord(ev[3], st));
   return B200DD_OK;
 }
 
 template <class TIN> int wh_dispatch(b200dd_wh *h, const void *x, const void *y, void *y_out, cudaStream_t st,
                                      cudaEvent_t *ev = nullptr) {
-  switch (h->log2m) {
-    case 9: return wh_launch_all<9, TIN>(h, x, y, y_out, st, ev);
-    case 10: return wh_launch_all<10, TIN>(h, x, y, y_out, st, ev);
-    case 11: return wh_launch_all<11, TIN>(h, x, y, y_out, st, ev);
-    case 12: return wh_launch_all<12, TIN>(h, x, y, y_out, st, ev);
+  int rc = B200DD_ERR_GEOMETRY;
+  if (ev) B2_CUDA(cudaEventRecord(ev[0], st));
+  switch (h->log2m_c) {
+    case 9: rc = wh_launch_corr<9, TIN>(h, x, y, st); break;
+    case 10: rc = wh_launch_corr<10, TIN>(h, x, y, st); break;
+    case 11: rc = wh_launch_corr<11, TIN>(h, x, y, st); break;
+    case 12: rc = wh_launch_corr<12, TIN>(h, x, y, st); break;
   }
-  return geom_fail("WienerHopf FFT length out of range");
+  if (rc != B200DD_OK) return rc == B200DD_ERR_GEOMETRY ? geom_fail("WienerHopf FFT length out of range") : rc;
+  if (ev) B2_CUDA(cudaEventRecord(ev[1], st));
+  rc = wh_launch_solve(h, st);
+  if (rc != B200DD_OK) return rc;
+  if (ev) B2_CUDA(cudaEventRecord(ev[2], st));
+  rc = B200DD_ERR_GEOMETRY;
+  switch (h->log2m_a) {
+    case 9: rc = wh_launch_apply<9, TIN>(h, x, y, y_out, st); break;
+    case 10: rc = wh_launch_apply<10, TIN>(h, x, y, y_out, st); break;
+    case 11: rc = wh_launch_apply<11, TIN>(h, x, y, y_out, st); break;
+    case 12: rc = wh_launch_apply<12, TIN>(h, x, y, y_out, st); break;
+  }
+  if (rc != B200DD_OK) return rc == B200DD_ERR_GEOMETRY ? geom_fail("WienerHopf FFT length out of range") : rc;
+  if (ev) B2_CUDA(cudaEventRecord(ev[3], st));
+  return B200DD_OK;
 }
 
-void wh_plan(b200dd_wh *h) {
+// FFT length minimising FFT work per new sample, M log2 M / (M - nBins + 1), among lengths that fit
+int wh_pick_log2m(const b200dd_wh *h, const char *env1, const char *env2) {
   int forced = 0;
-  if (const char *e = getenv("B200DD_WH_LOG2M")) forced = atoi(e);
+  if (const char *e = getenv(env1)) forced = atoi(e);
+  if (const char *e = getenv(env2)) forced = atoi(e);
   double best = 1e300;
   int best_l = 0;
   for (int l = 9; l <= 12; l++) {
@@ -558,12 +591,17 @@ void wh_plan(b200dd_wh *h) {
     if (forced == l) cost = -1.0;
     if (cost < best) { best = cost; best_l = l; }
   }
-  h->log2m = best_l;
-  if (!best_l) return;
-  const int M = 1 << best_l;
+  return best_l;
+}
+
+void wh_plan(b200dd_wh *h) {
+  h->log2m_c = wh_pick_log2m(h, "B200DD_WH_LOG2M", "B200DD_WH_CORR_LOG2M");
+  h->log2m_a = wh_pick_log2m(h, "B200DD_WH_LOG2M", "B200DD_WH_APPLY_LOG2M");
+  if (!h->log2m_c || !h->log2m_a) return;
+  const int M = 1 << h->log2m_c;
   h->L = M - h->nBins + 1;
   h->nSeg = (int)(((uint64_t)h->N + h->L - 1) / h->L);
-  // CTAs resident at once: shared memory allows 1 (M=4096) or 2+ (smaller) per SM
+  // CTAs resident at once: shared memory allows 1 (M=4096) or 2 (smaller) per SM
   const size_t smem = (size_t)(M + M / 16 + 2 * M) * sizeof(double2);
   int per_sm = (int)((227 * 1024) / smem);
   if (per_sm < 1) per_sm = 1;
@@ -572,8 +610,9 @@ void wh_plan(b200dd_wh *h) {
   h->segPerCta = (h->nSeg + slots - 1) / slots;
   if (h->segPerCta < 1) h->segPerCta = 1;
   h->gridCorr = (h->nSeg + h->segPerCta - 1) / h->segPerCta;
-  h->Lout = h->L;
-  h->gridApply = h->nSeg;
+  const int Ma = 1 << h->log2m_a;
+  h->Lout = Ma - h->nBins + 1;
+  h->gridApply = (int)(((uint64_t)h->N + h->Lout - 1) / h->Lout);
 }
 
 }  // namespace
@@ -604,13 +643,15 @@ int b200dd_wh_create(int32_t delay_min, int32_t delay_max, uint32_t n_samples, i
   if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaGetDeviceProperties", __FILE__, __LINE__));
   h->num_sms = prop.multiProcessorCount;
   wh_plan(h);
-  if (!h->log2m) return fail(geom_fail("b200dd_wh_create: no FFT plan (needs nSamples >= 512 and nBins <= 2048)"));
+  if (!h->log2m_c || !h->log2m_a) return fail(geom_fail("b200dd_wh_create: no FFT plan (needs nSamples >= 512 and nBins <= 2048)"));
   auto body = [&]() -> int {
     B2_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    const int M = 1 << h->log2m;
-    auto tw = twiddle_table_f64(M);
-    B2_CUDA(cudaMalloc(&h->d_tw, sizeof(double2) * M));
-    B2_CUDA(cudaMemcpy(h->d_tw, tw.data(), sizeof(double2) * M, cudaMemcpyHostToDevice));
+    const int Mc = 1 << h->log2m_c, M = 1 << h->log2m_a;
+    auto twc = twiddle_table_f64(Mc), twa = twiddle_table_f64(M);
+    B2_CUDA(cudaMalloc(&h->d_tw_c, sizeof(double2) * Mc));
+    B2_CUDA(cudaMemcpy(h->d_tw_c, twc.data(), sizeof(double2) * Mc, cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMalloc(&h->d_tw_a, sizeof(double2) * M));
+    B2_CUDA(cudaMemcpy(h->d_tw_a, twa.data(), sizeof(double2) * M, cudaMemcpyHostToDevice));
     B2_CUDA(cudaMalloc(&h->d_partial, sizeof(double2) * (size_t)h->gridCorr * 2 * h->nBins));
     B2_CUDA(cudaMalloc(&h->d_a, sizeof(double2) * h->nBins));
     B2_CUDA(cudaMalloc(&h->d_b, sizeof(double2) * h->nBins));
@@ -631,7 +672,8 @@ void b200dd_wh_destroy(b200dd_wh *h) {
   {
     DeviceGuard guard(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    free_dev(h->d_tw);
+    free_dev(h->d_tw_c);
+    free_dev(h->d_tw_a);
     free_dev(h->d_partial);
     free_dev(h->d_a);
     free_dev(h->d_b);

@@ -401,6 +401,14 @@ class Pipeline:
         capi.check(self._lib.b200dd_pipeline_submit_host(self._h, capi.ptr(x), capi.ptr(y), int(n),
                                                          capi.ptr(map_out) if map_out is not None else None))
 
+    def submit_host_rspduo(self, iq, map_out=None):
+        """Asynchronous host path fed with the reference's replay layout: int16 [n, 4] = I1 Q1 I2 Q2
+        (blah2_b200/scene.py write_rspduo).  Pair with fetch()."""
+        n = (iq.numel() if hasattr(iq, "numel") else iq.size) // 4
+        self._pending_map = map_out
+        capi.check(self._lib.b200dd_pipeline_submit_host_rspduo(self._h, capi.ptr(iq), int(n),
+                                                                capi.ptr(map_out) if map_out is not None else None))
+
     def submit_device(self, d_x, d_y, d_map=None, stream=None):
         n = d_x.numel() if hasattr(d_x, "numel") else self.n_samples
         capi.check(self._lib.b200dd_pipeline_submit_device(self._h, capi.ptr(d_x), capi.ptr(d_y), int(n),

@@ -279,6 +279,12 @@ B200DD_API int b200dd_pipeline_process_host(b200dd_pipeline *h, const double *x,
 B200DD_API int b200dd_pipeline_submit_host(b200dd_pipeline *h, const double *x, const double *y, uint32_t n,
                                            double *map_out);
 
+/* Same, fed with the reference's replay / capture layout: n time instants of little-endian int16
+ * I1 Q1 I2 Q2 (src/capture/rspduo/RspDuo.cpp:155-174; channel 1 = reference, channel 2 = surveillance).
+ * 8 bytes per instant cross PCIe instead of 32; the de-interleave runs on the device.  int16 is exact
+ * in float32, so results equal the complex128 entry point's. */
+B200DD_API int b200dd_pipeline_submit_host_rspduo(b200dd_pipeline *h, const int16_t *iq, uint32_t n, double *map_out);
+
 /* DEVICE buffers (float2), asynchronous on `stream` (NULL = the pipeline's stream).  d_map
  * (nullable) receives the float2 map.  Results stay on the device until b200dd_pipeline_fetch. */
 B200DD_API int b200dd_pipeline_submit_device(b200dd_pipeline *h, const void *d_x, const void *d_y, uint32_t n,

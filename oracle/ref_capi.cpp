@@ -27,6 +27,7 @@
 #include <complex>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -235,7 +236,23 @@ REF_API void *refpath_chain_create(int32_t delayMin, int32_t delayMax, int32_t d
   REF_CATCH(nullptr)
 }
 
-REF_API void refpath_chain_destroy(void *h) { delete static_cast<Chain *>(h); }
+REF_API void refpath_chain_destroy(void *h) {
+  auto *c = static_cast<Chain *>(h);
+  if (!c) return;
+  const bool dbg = getenv("REFPATH_DEBUG") != nullptr;
+  if (dbg) fprintf(stderr, "chain_destroy: interp\n");
+  c->interp.reset();
+  if (dbg) fprintf(stderr, "chain_destroy: centroid\n");
+  c->cen.reset();
+  if (dbg) fprintf(stderr, "chain_destroy: cfar\n");
+  c->cfar.reset();
+  if (dbg) fprintf(stderr, "chain_destroy: wh\n");
+  c->wh.reset();
+  if (dbg) fprintf(stderr, "chain_destroy: amb\n");
+  c->amb.reset();
+  if (dbg) fprintf(stderr, "chain_destroy: done\n");
+  delete c;
+}
 
 // stage_ms[0] = clutter_filter, [1] = ambiguity_processing (incl. set_metrics), [2] = detector.
 // Returns -1 if the clutter filter failed (CPI skipped, blah2.cpp:270-273), else #detections.

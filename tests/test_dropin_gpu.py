@@ -70,16 +70,19 @@ def test_wienerhopf_class_matches_reference_class(D, relerr):
 def test_whole_loop_body_with_dropin_classes(D, relerr):
     """src/blah2.cpp:268-287 through the class API: filter -> ambiguity -> set_metrics (the reference's
     own Map code) -> CFAR -> Centroid -> Interpolate."""
+    # geometry inside the reference's own valid domain: its Doppler work buffer has nfft entries but the
+    # Doppler FFT nDopplerBins points (Ambiguity.cpp:72,79-80), so nDopplerBins <= nfft is required or the
+    # reference overflows its heap (found the hard way; the CUDA path has no such limit)
     fs, n = 2000000, 200000
-    args = dict(delayMin=-10, delayMax=120, dopplerMin=-5000, dopplerMax=5000, fs=fs, n=n, roundHamming=True,
+    args = dict(delayMin=-10, delayMax=120, dopplerMin=-1000, dopplerMax=1000, fs=fs, n=n, roundHamming=True,
                 clutter=(-10, 60), pfa=1e-5, nGuard=2, nTrain=6, minDelay=5, minDoppler=15.0, nCentroid=6)
-    sc = make_scene(n, fs, seed=5, targets=[Target(37, 3000.0, -30.0), Target(92, -2000.0, -35.0)])
+    sc = make_scene(n, fs, seed=5, targets=[Target(37, 600.0, -30.0), Target(92, -400.0, -35.0)])
     d = D.Chain(**args).run(sc.x, sc.y)
     if R.available():
         r = R.Chain(**args).run(sc.x, sc.y)
         ref_map, ref_det, noise = r["map"], r["detections"], r["noisePower"]
     else:
-        g = O.ambiguity_geometry(-10, 120, -5000, 5000, fs, n, True)
+        g = O.ambiguity_geometry(-10, 120, -1000, 1000, fs, n, True)
         o = O.chain(sc.x, sc.y, g, clutter=(-10, 60), det=dict(pfa=1e-5, nGuard=2, nTrain=6, minDelay=5,
                                                                   minDoppler=15.0, nCentroid=6))
         ref_map, ref_det, noise = o["map"], o["detections"], o["noisePower"]
