@@ -108,6 +108,7 @@ struct RangeArgs {
   const float2 *tw;  // exp(-2 pi i j / M)
   int nCorr, nDel, lagMin, nSeg, L;
   int segPerPart, nDop;
+  int batch0;  // first batch of this launch (sharded single-CPI mode); x, y point at batch 0 of the CPI
 };
 
 // resident CTAs per SM the register allocator must leave room for (<= 128 regs/thread)
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, range_min_ctas<LOG2M>()) caf_
   float2 *A = reinterpret_cast<float2 *>(smem_raw);
   float2 *B = A + P::MP;
   const int tid = threadIdx.x;
-  const int batch = blockIdx.x;
+  const int batch = a.batch0 + blockIdx.x;
   const float2 *__restrict__ xb = a.x + (size_t)batch * a.nCorr;
   const float2 *__restrict__ yb = a.y + (size_t)batch * a.nCorr;
   const float2 zero = make_float2(0.f, 0.f);
@@ -203,6 +204,7 @@ struct DopplerArgs {
   const float2 *bhat;   // FFT_M2 of the wrapped conj chirp, digit-reversed position order
   const float2 *tw;     // exp(-2 pi i j / M2)
   int nDop, nDel;
+  int col0, nCols, ldOut;  // column tile [col0, col0 + nCols) of the map; out has row stride ldOut, tile-relative columns
 };
 
 // Column j: D[m] = sum_i R[i][j] exp(-2 pi i m i / nDop)  (Ambiguity.cpp:160) via
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT) caf_doppler_kernel(DopplerArg
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *A = reinterpret_cast<float2 *>(smem_raw);
   const int tid = threadIdx.x;
-  const int col = blockIdx.x;
+  const int col = a.col0 + blockIdx.x;
   const float2 zero = make_float2(0.f, 0.f);
   const size_t plane = (size_t)a.nDop * a.nDel;
   auto ld0 = [&](int i) {
@@ -252,13 +254,23 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT) caf_doppler_kernel(DopplerArg
       float2 d = cmul(val, __ldg(a.chirp + m));
       int k = m - shift;
       if (k < 0) k += a.nDop;
-      a.out[(size_t)k * a.nDel + col] = make_float2(d.x * scale, d.y * scale);
+      a.out[(size_t)k * a.ldOut + blockIdx.x] = make_float2(d.x * scale, d.y * scale);
     }
   };
   constexpr int S0 = 1 << P::log2S(0);
 #pragma unroll 1
   for (int b = tid; b < P::M / P::R0; b += P::NT) {
     if ((b & (S0 - 1)) < a.nDop) fft_butterfly<float, P::R0, +1, LOG2M>(b, P::log2S(0), a.tw, ldA, stO);
+  }
+}
+
+// rows [row0, row0 + nRows) of the range matrix = fixed-order sum of the parts (sharded single-CPI mode)
+__global__ void caf_sum_parts_kernel(const float2 *__restrict__ parts, int nParts, size_t plane, size_t first, size_t count,
+                                     float2 *__restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    float2 acc = parts[first + i];
+    for (int q = 1; q < nParts; q++) acc = cadd(acc, parts[q * plane + first + i]);
+    out[i] = acc;
   }
 }
 
@@ -349,7 +361,7 @@ template <int LOG2M> int launch_doppler(const DopplerArgs &a, cudaStream_t st) {
     B2_CUDA(cudaFuncSetAttribute(caf_doppler_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done[dev & 63] = true;
   }
-  caf_doppler_kernel<LOG2M><<<a.nDel, P::NT, smem, st>>>(a);
+  caf_doppler_kernel<LOG2M><<<a.nCols, P::NT, smem, st>>>(a);
   B2_LAUNCH_CHECK();
   return B200DD_OK;
 }
@@ -528,6 +540,7 @@ int caf_run_device(b200dd_caf *h, const float2 *d_x, const float2 *d_y, float2 *
   ra.L = h->L;
   ra.segPerPart = h->segPerPart;
   ra.nDop = (int)g.nDop;
+  ra.batch0 = 0;
   if (ev) B2_CUDA(cudaEventRecord(ev[0], st));
   int rc = dispatch_range(h->log2m, ra, (int)g.nDop, h->nParts, st);
   if (rc != B200DD_OK) return rc;
@@ -541,6 +554,9 @@ int caf_run_device(b200dd_caf *h, const float2 *d_x, const float2 *d_y, float2 *
   da.tw = h->d_tw2;
   da.nDop = (int)g.nDop;
   da.nDel = (int)g.nDel;
+  da.col0 = 0;
+  da.nCols = (int)g.nDel;
+  da.ldOut = (int)g.nDel;
   rc = dispatch_doppler(h->log2m2, da, st);
   if (rc != B200DD_OK) return rc;
   if (ev) B2_CUDA(cudaEventRecord(ev[2], st));
@@ -714,6 +730,44 @@ int b200dd_caf_profile_device(b200dd_caf *h, const void *d_x, const void *d_y, u
   }
   for (int i = 0; i < 3; i++) cudaEventDestroy(ev[i]);
   return rc;
+}
+
+int b200dd_caf_range_device(b200dd_caf *h, const void *d_x, const void *d_y, uint32_t batch0, uint32_t n_batches,
+                            void *d_R, void *stream) {
+  if (!h || !d_x || !d_y || !d_R) return arg_fail("b200dd_caf_range_device: null argument");
+  const HostGeom &g = h->g;
+  if (n_batches == 0 || (uint64_t)batch0 + n_batches > g.nDop) return arg_fail("b200dd_caf_range_device: batch range outside the CPI");
+  if (g.dopplerMiddle != 0.0) return geom_fail("b200dd_caf_range_device: symmetric Doppler windows only");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  RangeArgs ra;
+  // the kernel indexes batches absolutely; the caller hands over the slice that STARTS at batch0
+  ra.x = (const float2 *)d_x - (size_t)batch0 * g.nCorr;
+  ra.y = (const float2 *)d_y - (size_t)batch0 * g.nCorr;
+  ra.R = h->d_R;
+  ra.tw = h->d_tw1;
+  ra.nCorr = (int)g.nCorr; ra.nDel = (int)g.nDel; ra.lagMin = g.delayMin; ra.nSeg = h->nSeg; ra.L = h->L;
+  ra.segPerPart = h->segPerPart; ra.nDop = (int)g.nDop; ra.batch0 = (int)batch0;
+  int rc = dispatch_range(h->log2m, ra, (int)n_batches, h->nParts, st);
+  if (rc != B200DD_OK) return rc;
+  const size_t plane = (size_t)g.nDop * g.nDel, first = (size_t)batch0 * g.nDel, count = (size_t)n_batches * g.nDel;
+  caf_sum_parts_kernel<<<grid_for((uint32_t)count), 256, 0, st>>>(h->d_R, h->nParts, plane, first, count, (float2 *)d_R);
+  B2_LAUNCH_CHECK();
+  return B200DD_OK;
+}
+
+int b200dd_caf_doppler_device(b200dd_caf *h, const void *d_R, uint32_t col0, uint32_t n_cols, void *d_map_tile,
+                              void *stream) {
+  if (!h || !d_R || !d_map_tile) return arg_fail("b200dd_caf_doppler_device: null argument");
+  const HostGeom &g = h->g;
+  if (n_cols == 0 || (uint64_t)col0 + n_cols > g.nDel) return arg_fail("b200dd_caf_doppler_device: column range outside the map");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  DopplerArgs da;
+  da.R = (const float2 *)d_R; da.nParts = 1; da.out = (float2 *)d_map_tile; da.chirp = h->d_chirp; da.bhat = h->d_bhat;
+  da.tw = h->d_tw2; da.nDop = (int)g.nDop; da.nDel = (int)g.nDel; da.col0 = (int)col0; da.nCols = (int)n_cols;
+  da.ldOut = (int)n_cols;
+  return dispatch_doppler(h->log2m2, da, st);
 }
 
 int b200dd_caf_debug_range_matrix(b200dd_caf *h, float *out) {

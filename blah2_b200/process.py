@@ -115,6 +115,16 @@ class Ambiguity:
         capi.check(self._lib.b200dd_caf_process_device(self._h, capi.ptr(d_x), capi.ptr(d_y), int(n),
                                                        capi.ptr(d_map), capi.ptr(stream) if stream else None))
 
+    def range_device(self, d_x, d_y, batch0, n_batches, d_R, stream=None):
+        """Range stage on batches [batch0, batch0+n_batches): d_x, d_y hold exactly those batches."""
+        capi.check(self._lib.b200dd_caf_range_device(self._h, capi.ptr(d_x), capi.ptr(d_y), int(batch0), int(n_batches),
+                                                     capi.ptr(d_R), capi.ptr(stream) if stream else None))
+
+    def doppler_device(self, d_R, col0, n_cols, d_map_tile, stream=None):
+        """Doppler stage on delay columns [col0, col0+n_cols) of the complete range matrix d_R."""
+        capi.check(self._lib.b200dd_caf_doppler_device(self._h, capi.ptr(d_R), int(col0), int(n_cols),
+                                                       capi.ptr(d_map_tile), capi.ptr(stream) if stream else None))
+
     def profile_device(self, d_x, d_y, d_map=None, stream=None):
         """(ms_range, ms_doppler): CUDA-event durations of the two CAF kernels for one CPI."""
         a, b = C.c_float(), C.c_float()

@@ -121,6 +121,19 @@ B200DD_API int b200dd_caf_process_host(b200dd_caf *h, const double *x, const dou
 B200DD_API int b200dd_caf_process_device(b200dd_caf *h, const void *d_x, const void *d_y, uint32_t n, void *d_map,
                               void *stream);
 
+/* The two stages separately, for ONE large CPI sharded over several GPUs (BASELINE config 5):
+ * range stage on a contiguous block of batches (the rank's 1/world slice of the IQ), then -- after the
+ * caller has all-gathered the range matrix -- the Doppler stage on a tile of delay columns.
+ *   d_x, d_y : float2 samples of batches [batch0, batch0 + n_batches), i.e. n_batches * n_corr samples
+ *   d_R      : out, float2 [n_batches][n_delay_bins]  (rows batch0.. of the range matrix)
+ *   d_R (doppler) : in, the COMPLETE range matrix float2 [n_doppler_bins][n_delay_bins]
+ *   d_map_tile    : out, float2 [n_doppler_bins][n_cols] = map[:, col0 : col0 + n_cols]
+ * Symmetric Doppler windows only (the pre-rotation phase would need the global sample index). */
+B200DD_API int b200dd_caf_range_device(b200dd_caf *h, const void *d_x, const void *d_y, uint32_t batch0,
+                                       uint32_t n_batches, void *d_R, void *stream);
+B200DD_API int b200dd_caf_doppler_device(b200dd_caf *h, const void *d_R, uint32_t col0, uint32_t n_cols,
+                                         void *d_map_tile, void *stream);
+
 /* Profiling aid: same as b200dd_caf_process_device but brackets the range-correlation kernel and the
  * Doppler kernel with CUDA events on the launching stream and returns their durations (ms).
  * Synchronises the stream.  Used by bench.py for the roofline figures. */

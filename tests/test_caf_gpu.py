@@ -147,3 +147,37 @@ def test_too_few_samples_is_an_error():
     amb = Ambiguity(-3, 20, -50, 50, 10000, 4000)
     with pytest.raises(capi.B200ddError):
         amb.process(np.zeros(100, complex), np.zeros(100, complex))
+
+
+def test_stagewise_entry_points_emulating_two_ranks(relerr):
+    """b200dd_caf_range_device / b200dd_caf_doppler_device (single CPI split over GPUs, BASELINE config 5):
+    two 'ranks' emulated on one device must reproduce the one-shot map bit for bit."""
+    import torch
+    from blah2_b200.shard import block_range, caf_single_cpi_sharded
+    geom = (-5, 60, -200, 200, 100000, 100000, True)
+    x, y = random_iq(geom[5], seed=12)
+    amb = Ambiguity(*geom)
+    g = amb.geometry
+    dx = torch.from_numpy(x.astype(np.complex64)).cuda()
+    dy = torch.from_numpy(y.astype(np.complex64)).cuda()
+    full = torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        amb.process_device(dx, dy, full, s.cuda_stream)
+        one = caf_single_cpi_sharded(amb, dx[: g.n_used], dy[: g.n_used], 0, 1, s)
+        R = torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda")
+        for r in range(2):
+            b0, nb = block_range(g.n_doppler_bins, r, 2)
+            lo, hi = b0 * g.n_corr, (b0 + nb) * g.n_corr
+            amb.range_device(dx[lo:hi], dy[lo:hi], b0, nb, R[b0:b0 + nb], s.cuda_stream)
+        tiles = []
+        for r in range(2):
+            c0, nc = block_range(g.n_delay_bins, r, 2)
+            t = torch.empty((g.n_doppler_bins, nc), dtype=torch.complex64, device="cuda")
+            amb.doppler_device(R, c0, nc, t, s.cuda_stream)
+            tiles.append(t)
+    s.synchronize()
+    assert torch.equal(one, full)
+    assert torch.equal(torch.cat(tiles, dim=1), full)
+    ref, _, _ = O.ambiguity_process(x, y, O.ambiguity_geometry(*geom))
+    assert relerr(full.cpu().numpy().astype(np.complex128), ref)[0] < TOL
