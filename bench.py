@@ -46,6 +46,19 @@ WORKLOAD = ("cfg2: WienerHopf(410 taps)+Ambiguity(300 delay x 257 Doppler)+set_m
 KERNELS_PER_STEP = 4 + 2 + 2 + 3 + 2 + 2  # wh(corr,solve,wspec,apply) caf(range,doppler) metrics(2) cfar(3) centroid(2) interp(2)
 
 
+def ncu_traffic(kernel="caf_range_kernel"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
+    extract (profiles/r01z_kernels.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r01z_kernels.json")
+    try:
+        for k in json.load(open(p))["kernels"]:
+            if kernel in k["name"]:
+                return int(k["dram_bytes_read"] + k["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -71,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -162,7 +175,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=2, help="CPIs in flight per GPU (independent pipelines on their own streams)")
+    ap.add_argument("--streams", type=int, default=3, help="CPIs in flight per GPU (independent pipelines on their own streams)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -252,7 +265,6 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the host API (pinned complex128 in, complex128 map out) ----
     # Two pipelines alternate: submit_host(i) enqueues H2D + kernels + D2H, fetch(i-1) collects the
@@ -301,6 +313,8 @@ def main():
     if world > 1:
         dist.all_reduce(i16_s, op=dist.ReduceOp.MAX)
     i16_s = float(i16_s.item())
+
+    clocks = sampler.stop() if rank == 0 else None  # sampled over the device-resident AND the end-to-end timed regions
 
     # ---- per-kernel durations for the roofline (CUDA events around each kernel) ----
     amb = Ambiguity(GEOM["delayMin"], GEOM["delayMax"], GEOM["dopplerMin"], GEOM["dopplerMax"], FS, N, True,
@@ -351,7 +365,7 @@ def main():
         "gpu_launches": KERNELS_PER_STEP * args.steps,
         "clocks": clocks,
         "roofline": {"kernel": "caf_range_kernel", "bound": "hbm", "achieved": round(ach_range, 1), "peak": peak,
-                     "unit": "GB/s", "frac": round(ach_range / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": round(ach_range / peak, 4), "traffic": ncu_traffic(), "peak_source": peak_src,
                      "algorithmic_bytes": bytes_range, "kernel_ms": round(kms["range"], 5),
                      "caf_total": {"ms": round(kms["range"] + kms["doppler"], 5),
                                    "frac": round(bytes_caf / ((kms["range"] + kms["doppler"]) * 1e-3) / 1e9 / peak, 4)},

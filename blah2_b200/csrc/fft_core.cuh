@@ -176,13 +176,14 @@ template <int LOG2M> struct Plan {
 // tw[j] = exp(-2 pi i j / M), j < M.  log2S = log2 of this pass's stride.
 // ld(idx) returns element idx (natural index in [0, M)); st(idx, v) stores it.
 // ---------------------------------------------------------------------------------
-template <class T, int R, int DIR, int LOG2M, class LD, class ST>
-B2_HD void fft_butterfly(int b, int log2S, const cpx<T> *__restrict__ tw, LD ld, ST st) {
+// Core: loads, twiddles and the register DFT; output q (natural) is left in v[brev<R>(q)] and belongs at
+// index base + (q << log2S).  Returns base.
+template <class T, int R, int DIR, int LOG2M, class LD>
+B2_HD int fft_butterfly_core(int b, int log2S, const cpx<T> *__restrict__ tw, LD ld, cpx<T> (&v)[R]) {
   const int S = 1 << log2S;
   const int lo = b & (S - 1);
   const int hi = b >> log2S;
   const int base = hi * (R << log2S) + lo;
-  cpx<T> v[R];
 #pragma unroll
   for (int k = 0; k < R; k++) v[k] = ld(base + (k << log2S));
   // Twiddles w^q, q = 1..R-1, with w = exp(-2 pi i lo / ncur) = tw[lo * (M / ncur)]: ONE table load; the
@@ -217,6 +218,13 @@ B2_HD void fft_butterfly(int b, int log2S, const cpx<T> *__restrict__ tw, LD ld,
     }
   }
   if constexpr (DIR > 0) dft_reg<T, R, DIR>(v);
+  return base;
+}
+
+template <class T, int R, int DIR, int LOG2M, class LD, class ST>
+B2_HD void fft_butterfly(int b, int log2S, const cpx<T> *__restrict__ tw, LD ld, ST st) {
+  cpx<T> v[R];
+  const int base = fft_butterfly_core<T, R, DIR, LOG2M>(b, log2S, tw, ld, v);
 #pragma unroll
   for (int q = 0; q < R; q++) st(base + (q << log2S), v[brev<R>(q)]);
 }

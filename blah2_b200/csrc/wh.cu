@@ -448,14 +448,40 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, wh_min_ctas<LOG2M>()) wh_appl
   for (int r = 0; r < 16; r++) v[r] = cmul(v[r], a.what[16 * tid + brev<16>(r)]);
   __syncthreads();
   const double scale = 1.0 / (double)P::M;
-  // conv[m] valid for m >= hist; output i = i0 + m - hist
-  inv_fft_from_regs<LOG2M>(A, a.tw, tid, v, P::M, [&](int m, double2 val) {
-    const int o = m - hist;
-    if (o >= 0 && o < nOut) {
-      const double2 yy = ld_iq(y, i0 + o);
-      st_iq<TIN>(yo, i0 + o, make_double2(yy.x - val.x * scale, yy.y - val.y * scale));
+  // conv[m] valid for m >= hist; output i = i0 + m - hist.  The final inverse pass is written out here so
+  // that the epilogue can issue all surveillance-channel loads of a butterfly back to back before the
+  // first store (y_out may alias y, so the compiler would otherwise keep load -> store order and
+  // serialise 16 global-load latencies per thread: profiles/r01_summary.md).
+  inv_first_from_regs<double, LOG2M>(A, tid, v);
+  __syncthreads();
+#pragma unroll 1
+  for (int p = P::NP - 2; p >= 1; p--) {
+    smem_pass<double, LOG2M, +1>(A, a.tw, p, tid);
+    __syncthreads();
+  }
+  auto ldA = [&](int i) { return A[pad(i)]; };
+  constexpr int R0 = P::R0;
+  constexpr int L2S0 = P::log2S(0);
+#pragma unroll 1
+  for (int b = tid; b < P::M / R0; b += P::NT) {
+    double2 c[R0];
+    const int base = fft_butterfly_core<double, R0, +1, LOG2M>(b, L2S0, a.tw, ldA, c);
+    TIN yy[R0];
+#pragma unroll
+    for (int q = 0; q < R0; q++) {
+      const int o = base + (q << L2S0) - hist;
+      const int oc = o < 0 ? 0 : (o >= nOut ? nOut - 1 : o);
+      yy[q] = y[i0 + oc];  // unconditional, clamped: batched loads
     }
-  });
+#pragma unroll
+    for (int q = 0; q < R0; q++) {
+      const int o = base + (q << L2S0) - hist;
+      if (o >= 0 && o < nOut) {
+        const double2 cv = c[brev<R0>(q)];
+        st_iq<TIN>(yo, i0 + o, make_double2((double)yy[q].x - cv.x * scale, (double)yy[q].y - cv.y * scale));
+      }
+    }
+  }
 }
 
 std::vector<double2> twiddle_table_f64(int M) {
