@@ -80,7 +80,9 @@ template <class TIN> __device__ __forceinline__ double2 ld_iq(const TIN *p, uint
 }
 
 // resident CTAs per SM the register allocator leaves room for (<= 128 registers per thread)
-template <int LOG2M> constexpr int wh_min_ctas() { return 512 / Plan<LOG2M>::NT > 8 ? 8 : 512 / Plan<LOG2M>::NT; }
+template <int LOG2M, int LR> constexpr int wh_min_ctas() {
+  return 512 / Plan<LOG2M, LR>::NT > 8 ? 8 : (512 / Plan<LOG2M, LR>::NT < 1 ? 1 : 512 / Plan<LOG2M, LR>::NT);
+}
 
 struct CorrArgs {
   const void *x;
@@ -93,34 +95,34 @@ struct CorrArgs {
 };
 
 // forward FFT of M points from a loader, result in registers (position order of fft_core.cuh)
-template <int LOG2M, class LD>
-__device__ __forceinline__ void fwd_fft_regs(double2 *A, const double2 *tw, int tid, LD ld, double2 (&v)[16]) {
-  using P = Plan<LOG2M>;
-  auto stA = [&](int i, double2 val) { A[pad(i)] = val; };
+template <int LOG2M, int LR, class LD>
+__device__ __forceinline__ void fwd_fft_regs(double2 *A, const double2 *tw, int tid, LD ld, double2 (&v)[1 << LR]) {
+  using P = Plan<LOG2M, LR>;
+  auto stA = [&](int i, double2 val) { A[padr<LR>(i)] = val; };
 #pragma unroll 1
   for (int b = tid; b < P::M / P::R0; b += P::NT) fft_butterfly<double, P::R0, -1, LOG2M>(b, P::log2S(0), tw, ld, stA);
   __syncthreads();
 #pragma unroll 1
   for (int p = 1; p < P::NP - 1; p++) {
-    smem_pass<double, LOG2M, -1>(A, tw, p, tid);
+    smem_pass<double, LOG2M, -1, LR>(A, tw, p, tid);
     __syncthreads();
   }
-  fwd_last_to_regs<double, LOG2M>(A, tid, v);
+  fwd_last_to_regs<double, LOG2M, LR>(A, tid, v);
 }
 
 // inverse FFT from registers; the final pass hands natural-order outputs to st(m, value)
-template <int LOG2M, class ST>
-__device__ __forceinline__ void inv_fft_from_regs(double2 *A, const double2 *tw, int tid, const double2 (&z)[16], int keep,
-                                                  ST st) {
-  using P = Plan<LOG2M>;
-  inv_first_from_regs<double, LOG2M>(A, tid, z);
+template <int LOG2M, int LR, class ST>
+__device__ __forceinline__ void inv_fft_from_regs(double2 *A, const double2 *tw, int tid, const double2 (&z)[1 << LR],
+                                                  int keep, ST st) {
+  using P = Plan<LOG2M, LR>;
+  inv_first_from_regs<double, LOG2M, LR>(A, tid, z);
   __syncthreads();
 #pragma unroll 1
   for (int p = P::NP - 2; p >= 1; p--) {
-    smem_pass<double, LOG2M, +1>(A, tw, p, tid);
+    smem_pass<double, LOG2M, +1, LR>(A, tw, p, tid);
     __syncthreads();
   }
-  auto ldA = [&](int i) { return A[pad(i)]; };
+  auto ldA = [&](int i) { return A[padr<LR>(i)]; };
   constexpr int S0 = 1 << P::log2S(0);
 #pragma unroll 1
   for (int b = tid; b < P::M / P::R0; b += P::NT) {
@@ -128,9 +130,10 @@ __device__ __forceinline__ void inv_fft_from_regs(double2 *A, const double2 *tw,
   }
 }
 
-template <int LOG2M, class TIN>
-__global__ void __launch_bounds__(Plan<LOG2M>::NT, 1) wh_corr_kernel(CorrArgs a) {
-  using P = Plan<LOG2M>;
+template <int LOG2M, int LR, class TIN>
+__global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, 1) wh_corr_kernel(CorrArgs a) {
+  using P = Plan<LOG2M, LR>;
+  constexpr int R = P::R;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *A = reinterpret_cast<double2 *>(smem_raw);
   double2 *Za = A + P::MP;
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, 1) wh_corr_kernel(CorrArgs a)
   const TIN *__restrict__ y = reinterpret_cast<const TIN *>(a.y);
   const double2 zero = make_double2(0.0, 0.0);
 #pragma unroll
-  for (int r = 0; r < 16; r++) {
+  for (int r = 0; r < R; r++) {
     Za[r * P::NT + tid] = zero;
     Zb[r * P::NT + tid] = zero;
   }
@@ -169,20 +172,20 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, 1) wh_corr_kernel(CorrArgs a)
       const double2 v = ld_iq(y, i);
       return m < wlen ? v : zero;
     };
-    double2 vxp[16], v[16];
-    fwd_fft_regs<LOG2M>(A, a.tw, tid, ldxp, vxp);
+    double2 vxp[R], v[R];
+    fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldxp, vxp);
     __syncthreads();
-    fwd_fft_regs<LOG2M>(A, a.tw, tid, ldxw, v);
+    fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldxw, v);
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
+    for (int r = 0; r < R; r++) {
       double2 acc = Za[r * P::NT + tid];
       cfmac(acc, v[r], vxp[r]);
       Za[r * P::NT + tid] = acc;
     }
     __syncthreads();
-    fwd_fft_regs<LOG2M>(A, a.tw, tid, ldyw, v);
+    fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldyw, v);
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
+    for (int r = 0; r < R; r++) {
       double2 acc = Zb[r * P::NT + tid];
       cfmac(acc, v[r], vxp[r]);
       Zb[r * P::NT + tid] = acc;
@@ -192,17 +195,17 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, 1) wh_corr_kernel(CorrArgs a)
   const double scale = 1.0 / (double)P::M;
   double2 *pa = a.partial + (size_t)blockIdx.x * 2 * a.nBins;
   double2 *pb = pa + a.nBins;
-  double2 z[16];
+  double2 z[R];
 #pragma unroll
-  for (int r = 0; r < 16; r++) z[r] = Za[r * P::NT + tid];
+  for (int r = 0; r < R; r++) z[r] = Za[r * P::NT + tid];
   // IFFT gives ra[k] = sum xs[n+k] conj(xs[n]);  a[k] = conj(ra[k])  (WienerHopf.cpp:82-84)
-  inv_fft_from_regs<LOG2M>(A, a.tw, tid, z, a.nBins, [&](int m, double2 val) {
+  inv_fft_from_regs<LOG2M, LR>(A, a.tw, tid, z, a.nBins, [&](int m, double2 val) {
     if (m < a.nBins) pa[m] = make_double2(val.x * scale, -val.y * scale);
   });
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < 16; r++) z[r] = Zb[r * P::NT + tid];
-  inv_fft_from_regs<LOG2M>(A, a.tw, tid, z, a.nBins, [&](int m, double2 val) {
+  for (int r = 0; r < R; r++) z[r] = Zb[r * P::NT + tid];
+  inv_fft_from_regs<LOG2M, LR>(A, a.tw, tid, z, a.nBins, [&](int m, double2 val) {
     if (m < a.nBins) pb[m] = make_double2(val.x * scale, val.y * scale);
   });
 }
@@ -384,17 +387,18 @@ template <int EPT> __global__ void __launch_bounds__(1024, 1) wh_solve_kernel(So
 // ---------------------------------------------------------------------------------
 // spectrum of the zero-padded weights (position order), once per CPI
 // ---------------------------------------------------------------------------------
-template <int LOG2M>
-__global__ void __launch_bounds__(Plan<LOG2M>::NT, 1) wh_wspec_kernel(const double2 *w, int nBins, double2 *what,
+template <int LOG2M, int LR>
+__global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, 1) wh_wspec_kernel(const double2 *w, int nBins, double2 *what,
                                                                         const double2 *tw) {
-  using P = Plan<LOG2M>;
+  using P = Plan<LOG2M, LR>;
+  constexpr int R = P::R;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *A = reinterpret_cast<double2 *>(smem_raw);
   const int tid = threadIdx.x;
-  double2 v[16];
-  fwd_fft_regs<LOG2M>(A, tw, tid, [&](int i) { return i < nBins ? w[i] : make_double2(0.0, 0.0); }, v);
+  double2 v[R];
+  fwd_fft_regs<LOG2M, LR>(A, tw, tid, [&](int i) { return i < nBins ? w[i] : make_double2(0.0, 0.0); }, v);
 #pragma unroll
-  for (int r = 0; r < 16; r++) what[16 * tid + brev<16>(r)] = v[r];
+  for (int r = 0; r < R; r++) what[R * tid + brev<R>(r)] = v[r];
 }
 
 struct ApplyArgs {
@@ -416,9 +420,10 @@ template <> __device__ __forceinline__ void st_iq<float2>(float2 *p, uint32_t i,
 template <> __device__ __forceinline__ void st_iq<double2>(double2 *p, uint32_t i, double2 v) { p[i] = v; }
 
 // one CTA per block of Lout outputs: window of M = Lout + nBins - 1 shifted-reference samples
-template <int LOG2M, class TIN>
-__global__ void __launch_bounds__(Plan<LOG2M>::NT, wh_min_ctas<LOG2M>()) wh_apply_kernel(ApplyArgs a) {
-  using P = Plan<LOG2M>;
+template <int LOG2M, int LR, class TIN>
+__global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, wh_min_ctas<LOG2M, LR>()) wh_apply_kernel(ApplyArgs a) {
+  using P = Plan<LOG2M, LR>;
+  constexpr int R = P::R;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *A = reinterpret_cast<double2 *>(smem_raw);
   const int tid = threadIdx.x;
@@ -442,24 +447,24 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, wh_min_ctas<LOG2M>()) wh_appl
     const double2 v = ld_iq(x, xs((uint32_t)ic));
     return (i >= 0 && i < (int64_t)a.N && m < hist + nOut) ? v : zero;
   };
-  double2 v[16];
-  fwd_fft_regs<LOG2M>(A, a.tw, tid, ldw, v);
+  double2 v[R];
+  fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldw, v);
 #pragma unroll
-  for (int r = 0; r < 16; r++) v[r] = cmul(v[r], a.what[16 * tid + brev<16>(r)]);
+  for (int r = 0; r < R; r++) v[r] = cmul(v[r], a.what[R * tid + brev<R>(r)]);
   __syncthreads();
   const double scale = 1.0 / (double)P::M;
   // conv[m] valid for m >= hist; output i = i0 + m - hist.  The final inverse pass is written out here so
   // that the epilogue can issue all surveillance-channel loads of a butterfly back to back before the
   // first store (y_out may alias y, so the compiler would otherwise keep load -> store order and
   // serialise 16 global-load latencies per thread: profiles/r01_summary.md).
-  inv_first_from_regs<double, LOG2M>(A, tid, v);
+  inv_first_from_regs<double, LOG2M, LR>(A, tid, v);
   __syncthreads();
 #pragma unroll 1
   for (int p = P::NP - 2; p >= 1; p--) {
-    smem_pass<double, LOG2M, +1>(A, a.tw, p, tid);
+    smem_pass<double, LOG2M, +1, LR>(A, a.tw, p, tid);
     __syncthreads();
   }
-  auto ldA = [&](int i) { return A[pad(i)]; };
+  auto ldA = [&](int i) { return A[padr<LR>(i)]; };
   constexpr int R0 = P::R0;
   constexpr int L2S0 = P::log2S(0);
 #pragma unroll 1
@@ -503,6 +508,7 @@ struct b200dd_wh {
   int device = 0;
   cudaStream_t stream = nullptr;
   int log2m_c = 12, log2m_a = 12;  // FFT lengths of the correlation / filter stages
+  int lr = 4;                      // log2 of the base radix of the FP64 FFTs (B200DD_WH_RADIX = 8 | 16)
   int L = 0, nSeg = 0, segPerCta = 1, gridCorr = 1;  // correlation stage
   int Lout = 0, gridApply = 1;                       // filter stage
   double2 *d_tw_c = nullptr, *d_tw_a = nullptr, *d_partial = nullptr, *d_a = nullptr, *d_b = nullptr, *d_w = nullptr, *d_what = nullptr;
@@ -514,41 +520,41 @@ struct b200dd_wh {
 
 namespace {
 
-template <int LOG2M> size_t corr_smem() { return (size_t)(Plan<LOG2M>::MP + 2 * Plan<LOG2M>::M) * sizeof(double2); }
-template <int LOG2M> size_t fft_smem() { return (size_t)Plan<LOG2M>::MP * sizeof(double2); }
+template <int LOG2M, int LR> size_t corr_smem() { return (size_t)(Plan<LOG2M, LR>::MP + 2 * Plan<LOG2M, LR>::M) * sizeof(double2); }
+template <int LOG2M, int LR> size_t fft_smem() { return (size_t)Plan<LOG2M, LR>::MP * sizeof(double2); }
 
 template <class TIN> constexpr bool is_f32() { return sizeof(TIN) == sizeof(float2); }
 
 // correlation stage with its own FFT length (smaller M -> two CTAs per SM fit beside the accumulators)
-template <int LOG2M, class TIN> int wh_launch_corr(b200dd_wh *h, const void *x, const void *y, cudaStream_t st) {
-  using P = Plan<LOG2M>;
+template <int LOG2M, int LR, class TIN> int wh_launch_corr(b200dd_wh *h, const void *x, const void *y, cudaStream_t st) {
+  using P = Plan<LOG2M, LR>;
   bool &done = is_f32<TIN>() ? h->attr_corr_f32 : h->attr_corr_f64;
   if (!done) {
-    B2_CUDA(cudaFuncSetAttribute(wh_corr_kernel<LOG2M, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_smem<LOG2M>()));
+    B2_CUDA(cudaFuncSetAttribute(wh_corr_kernel<LOG2M, LR, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_smem<LOG2M, LR>()));
     done = true;
   }
   CorrArgs ca;
   ca.x = x; ca.y = y; ca.partial = h->d_partial; ca.tw = h->d_tw_c; ca.N = h->N; ca.xs = make_xs_map(h->N, h->delayMin);
   ca.nBins = h->nBins; ca.L = h->L; ca.nSegTotal = h->nSeg; ca.segPerCta = h->segPerCta;
-  wh_corr_kernel<LOG2M, TIN><<<h->gridCorr, P::NT, corr_smem<LOG2M>(), st>>>(ca);
+  wh_corr_kernel<LOG2M, LR, TIN><<<h->gridCorr, P::NT, corr_smem<LOG2M, LR>(), st>>>(ca);
   B2_LAUNCH_CHECK();
   return B200DD_OK;
 }
 
-template <int LOG2M, class TIN> int wh_launch_apply(b200dd_wh *h, const void *x, const void *y, void *y_out, cudaStream_t st) {
-  using P = Plan<LOG2M>;
+template <int LOG2M, int LR, class TIN> int wh_launch_apply(b200dd_wh *h, const void *x, const void *y, void *y_out, cudaStream_t st) {
+  using P = Plan<LOG2M, LR>;
   bool &done = is_f32<TIN>() ? h->attr_apply_f32 : h->attr_apply_f64;
   if (!done) {
-    B2_CUDA(cudaFuncSetAttribute(wh_apply_kernel<LOG2M, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M>()));
-    B2_CUDA(cudaFuncSetAttribute(wh_wspec_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M>()));
+    B2_CUDA(cudaFuncSetAttribute(wh_apply_kernel<LOG2M, LR, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M, LR>()));
+    B2_CUDA(cudaFuncSetAttribute(wh_wspec_kernel<LOG2M, LR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M, LR>()));
     done = true;
   }
-  wh_wspec_kernel<LOG2M><<<1, P::NT, fft_smem<LOG2M>(), st>>>(h->d_w, h->nBins, h->d_what, h->d_tw_a);
+  wh_wspec_kernel<LOG2M, LR><<<1, P::NT, fft_smem<LOG2M, LR>(), st>>>(h->d_w, h->nBins, h->d_what, h->d_tw_a);
   B2_LAUNCH_CHECK();
   ApplyArgs aa;
   aa.x = x; aa.y = y; aa.y_out = y_out; aa.what = h->d_what; aa.tw = h->d_tw_a; aa.status = h->d_status;
   aa.N = h->N; aa.xs = make_xs_map(h->N, h->delayMin); aa.nBins = h->nBins; aa.Lout = h->Lout;
-  wh_apply_kernel<LOG2M, TIN><<<h->gridApply, P::NT, fft_smem<LOG2M>(), st>>>(aa);
+  wh_apply_kernel<LOG2M, LR, TIN><<<h->gridApply, P::NT, fft_smem<LOG2M, LR>(), st>>>(aa);
   B2_LAUNCH_CHECK();
   return B200DD_OK;
 }
@@ -579,10 +585,10 @@ template <class TIN> int wh_dispatch(b200dd_wh *h, const void *x, const void *y,
   int rc = B200DD_ERR_GEOMETRY;
   if (ev) B2_CUDA(cudaEventRecord(ev[0], st));
   switch (h->log2m_c) {
-    case 9: rc = wh_launch_corr<9, TIN>(h, x, y, st); break;
-    case 10: rc = wh_launch_corr<10, TIN>(h, x, y, st); break;
-    case 11: rc = wh_launch_corr<11, TIN>(h, x, y, st); break;
-    case 12: rc = wh_launch_corr<12, TIN>(h, x, y, st); break;
+    case 9: rc = h->lr == 3 ? wh_launch_corr<9, 3, TIN>(h, x, y, st) : wh_launch_corr<9, 4, TIN>(h, x, y, st); break;
+    case 10: rc = h->lr == 3 ? wh_launch_corr<10, 3, TIN>(h, x, y, st) : wh_launch_corr<10, 4, TIN>(h, x, y, st); break;
+    case 11: rc = h->lr == 3 ? wh_launch_corr<11, 3, TIN>(h, x, y, st) : wh_launch_corr<11, 4, TIN>(h, x, y, st); break;
+    case 12: rc = h->lr == 3 ? wh_launch_corr<12, 3, TIN>(h, x, y, st) : wh_launch_corr<12, 4, TIN>(h, x, y, st); break;
   }
   if (rc != B200DD_OK) return rc == B200DD_ERR_GEOMETRY ? geom_fail("WienerHopf FFT length out of range") : rc;
   if (ev) B2_CUDA(cudaEventRecord(ev[1], st));
@@ -591,10 +597,10 @@ template <class TIN> int wh_dispatch(b200dd_wh *h, const void *x, const void *y,
   if (ev) B2_CUDA(cudaEventRecord(ev[2], st));
   rc = B200DD_ERR_GEOMETRY;
   switch (h->log2m_a) {
-    case 9: rc = wh_launch_apply<9, TIN>(h, x, y, y_out, st); break;
-    case 10: rc = wh_launch_apply<10, TIN>(h, x, y, y_out, st); break;
-    case 11: rc = wh_launch_apply<11, TIN>(h, x, y, y_out, st); break;
-    case 12: rc = wh_launch_apply<12, TIN>(h, x, y, y_out, st); break;
+    case 9: rc = h->lr == 3 ? wh_launch_apply<9, 3, TIN>(h, x, y, y_out, st) : wh_launch_apply<9, 4, TIN>(h, x, y, y_out, st); break;
+    case 10: rc = h->lr == 3 ? wh_launch_apply<10, 3, TIN>(h, x, y, y_out, st) : wh_launch_apply<10, 4, TIN>(h, x, y, y_out, st); break;
+    case 11: rc = h->lr == 3 ? wh_launch_apply<11, 3, TIN>(h, x, y, y_out, st) : wh_launch_apply<11, 4, TIN>(h, x, y, y_out, st); break;
+    case 12: rc = h->lr == 3 ? wh_launch_apply<12, 3, TIN>(h, x, y, y_out, st) : wh_launch_apply<12, 4, TIN>(h, x, y, y_out, st); break;
   }
   if (rc != B200DD_OK) return rc == B200DD_ERR_GEOMETRY ? geom_fail("WienerHopf FFT length out of range") : rc;
   if (ev) B2_CUDA(cudaEventRecord(ev[3], st));
@@ -621,6 +627,7 @@ int wh_pick_log2m(const b200dd_wh *h, const char *env1, const char *env2) {
 }
 
 void wh_plan(b200dd_wh *h) {
+  if (const char *e = getenv("B200DD_WH_RADIX")) h->lr = atoi(e) == 8 ? 3 : 4;
   h->log2m_c = wh_pick_log2m(h, "B200DD_WH_LOG2M", "B200DD_WH_CORR_LOG2M");
   h->log2m_a = wh_pick_log2m(h, "B200DD_WH_LOG2M", "B200DD_WH_APPLY_LOG2M");
   if (!h->log2m_c || !h->log2m_a) return;

@@ -118,3 +118,18 @@ def test_linearity_in_y_for_fixed_weights_property():
     ok, yf = WienerHopf(-5, 100, n).process(x, y)
     assert ok
     assert np.linalg.norm(yf - y) < 0.05 * np.linalg.norm(y)
+
+
+@pytest.mark.parametrize("radix,log2m", [(8, 9), (8, 10), (8, 11), (8, 12), (16, 9), (16, 10), (16, 11), (16, 12)])
+def test_every_fft_plan_gives_the_same_filter(radix, log2m, relerr, monkeypatch):
+    """Base radix 8 / 16 and every FFT length of the FP64 kernels (B200DD_WH_RADIX, B200DD_WH_LOG2M)."""
+    monkeypatch.setenv("B200DD_WH_RADIX", str(radix))
+    monkeypatch.setenv("B200DD_WH_LOG2M", str(log2m))
+    n, dm, dM = 50021, -5, 70
+    sc = _scene(n, 13)
+    wh = WienerHopf(dm, dM, n)
+    ok, y = wh.process(sc.x, sc.y)
+    ok_ref, y_ref = O.wienerhopf_process(sc.x, sc.y, dm, dM)
+    assert ok and ok_ref
+    e = relerr(y, y_ref)
+    assert e[0] < 1e-9 and e[1] < 1e-9, f"radix {radix} M=2^{log2m}: {e}"
