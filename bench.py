@@ -43,7 +43,7 @@ CLUTTER = (-10, 400)
 DET = dict(pfa=1e-5, nGuard=2, nTrain=6, minDelay=5, minDoppler=15.0, nCentroid=6)
 WORKLOAD = ("cfg2: WienerHopf(410 taps)+Ambiguity(300 delay x 257 Doppler)+set_metrics+CFAR/Centroid/Interpolate, "
             "1 s CPI @ 2 MS/s, N=2e6 per channel")
-KERNELS_PER_STEP = 4 + 2 + 2 + 3 + 2 + 2  # wh(corr,solve,wspec,apply) caf(range,doppler) metrics(2) cfar(3) centroid(2) interp(2)
+KERNELS_PER_STEP = 4 + 2 + 2 + 3 + 1  # wh(corr,solve,wspec,apply) caf(range,doppler) metrics(2) cfar(flag,scan,emit) tail(centroid+interp)
 
 
 def ncu_traffic(kernel="caf_range_kernel"):

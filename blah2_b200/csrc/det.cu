@@ -251,25 +251,26 @@ struct CentroidArgs {
   uint8_t *keep;
 };
 
+__device__ __forceinline__ bool centroid_keep(const CentroidArgs &a, uint32_t i, uint32_t n) {
+  const double di = a.in.delay[i], fi = a.in.doppler[i], si = a.in.snr[i];
+  // Centroid.cpp:28,34-37: uint16_t window edges (wrap), double Doppler edges
+  const uint16_t dmin = (uint16_t)((int)di - (int)a.nDelay);
+  const uint16_t dmax = (uint16_t)((int)di + (int)a.nDelay);
+  const double span = __dmul_rn((double)a.nDoppler, a.resolution);
+  const double fmin = __dsub_rn(fi, span), fmax = __dadd_rn(fi, span);
+  for (uint32_t j = 0; j < n; j++) {
+    if (j == i) continue;
+    const double dj = a.in.delay[j], fj = a.in.doppler[j];
+    if (dj > (double)dmin && dj < (double)dmax && fj > fmin && fj < fmax) {
+      if (si < a.in.snr[j]) return false;
+    }
+  }
+  return true;
+}
+
 __global__ void __launch_bounds__(kBlock) centroid_kernel(CentroidArgs a) {
   const uint32_t n = min(*a.n, a.cap);
-  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-    const double di = a.in.delay[i], fi = a.in.doppler[i], si = a.in.snr[i];
-    // Centroid.cpp:28,34-37: uint16_t window edges (wrap), double Doppler edges
-    const uint16_t dmin = (uint16_t)((int)di - (int)a.nDelay);
-    const uint16_t dmax = (uint16_t)((int)di + (int)a.nDelay);
-    const double span = __dmul_rn((double)a.nDoppler, a.resolution);
-    const double fmin = __dsub_rn(fi, span), fmax = __dadd_rn(fi, span);
-    bool keep = true;
-    for (uint32_t j = 0; j < n; j++) {
-      if (j == i) continue;
-      const double dj = a.in.delay[j], fj = a.in.doppler[j];
-      if (dj > (double)dmin && dj < (double)dmax && fj > fmin && fj < fmax) {
-        if (si < a.in.snr[j]) { keep = false; break; }
-      }
-    }
-    a.keep[i] = keep ? 1 : 0;
-  }
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) a.keep[i] = centroid_keep(a, i, n) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------ Interpolate
@@ -301,61 +302,63 @@ __device__ __forceinline__ int hz_to_bin(const double *axis, int n, double hz) {
   return 0;
 }
 
-template <class TMAP> __global__ void __launch_bounds__(kBlock) interp_kernel(InterpArgs a) {
-  const uint32_t n = min(*a.n, a.cap);
+template <class TMAP> __device__ __forceinline__ void interp_one(const InterpArgs &a, uint32_t i, double noisePower) {
   const TMAP *map = reinterpret_cast<const TMAP *>(a.map);
-  const double noisePower = a.noise_dev ? *a.noise_dev : a.noisePower;
-  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-    const double d = a.in.delay[i], f = a.in.doppler[i], s = a.in.snr[i];
-    double intDelay = d, intDoppler = f, intSnrDelay = s;
-    const double intSnrDoppler = s;  // never updated in the reference (Interpolate.cpp:80)
-    bool keep = true;
-    const int row = hz_to_bin(a.doppler, a.nDop, f);
-    const double d0 = (double)a.delay[0];
-    auto db = [&](int r, int c) { return db_abs(ld_cell(map, (size_t)r * a.nDel + c)) - noisePower; };
-    if (a.doDelay) {
-      if (d == d0 || d == (double)a.delay[a.nDel - 1]) keep = false;  // :46-49
-      if (keep) {
-        const int c = (int)(d - d0);
-        if (c - 1 < 0 || c + 1 >= a.nDel) keep = false;  // fence (UB in the reference)
-        if (keep) {
-          const double s0 = db(row, c - 1), s1 = db(row, c), s2 = db(row, c + 1);  // :50-52
-          if (s1 < s0 || s1 < s2) keep = false;                                  // :54-58
-          if (keep) {
-            const double num = __dsub_rn(s0, s2);
-            const double den = __dmul_rn(2.0, __dadd_rn(__dsub_rn(s0, __dmul_rn(2.0, s1)), s2));
-            const double off = __ddiv_rn(num, den);                                     // :59
-            intSnrDelay = __dsub_rn(s1, __ddiv_rn(__dmul_rn(num, off), 4.0));           // :60
-            intDelay = __dadd_rn(d, off);                                               // :61
-          }
-        }
-      }
-    }
-    if (keep && a.doDoppler) {
-      if (f == a.doppler[0] || f == a.doppler[a.nDop - 1]) keep = false;  // :67-70
-      if (keep) {
-        const int c = (int)(d - d0);
-        if (row - 1 < 0 || row + 1 >= a.nDop || c < 0 || c >= a.nDel) keep = false;  // fence
-        if (keep) {
-          const double s0 = db(row - 1, c), s1 = db(row, c), s2 = db(row + 1, c);  // :71-73
-          if (s1 < s0 || s1 < s2) keep = false;                                  // :75-78
-          if (keep) {
-            const double num = __dsub_rn(s0, s2);
-            const double den = __dmul_rn(2.0, __dadd_rn(__dsub_rn(s0, __dmul_rn(2.0, s1)), s2));
-            const double off = __ddiv_rn(num, den);                                     // :79
-            intSnrDelay = __dsub_rn(s1, __ddiv_rn(__dmul_rn(num, off), 4.0));           // :80 (sic)
-            intDoppler = __dadd_rn(f, __dmul_rn(__dsub_rn(a.doppler[1], a.doppler[0]), off));  // :81
-          }
-        }
-      }
-    }
-    a.keep[i] = keep ? 1 : 0;
+  const double d = a.in.delay[i], f = a.in.doppler[i], s = a.in.snr[i];
+  double intDelay = d, intDoppler = f, intSnrDelay = s;
+  const double intSnrDoppler = s;  // never updated in the reference (Interpolate.cpp:80)
+  bool keep = true;
+  const int row = hz_to_bin(a.doppler, a.nDop, f);
+  const double d0 = (double)a.delay[0];
+  auto db = [&](int r, int c) { return db_abs(ld_cell(map, (size_t)r * a.nDel + c)) - noisePower; };
+  if (a.doDelay) {
+    if (d == d0 || d == (double)a.delay[a.nDel - 1]) keep = false;  // :46-49
     if (keep) {
-      a.out.delay[i] = intDelay;
-      a.out.doppler[i] = intDoppler;
-      a.out.snr[i] = fmax(fmax(intSnrDelay, intSnrDoppler), s);  // :86
+      const int c = (int)(d - d0);
+      if (c - 1 < 0 || c + 1 >= a.nDel) keep = false;  // fence (UB in the reference)
+      if (keep) {
+        const double s0 = db(row, c - 1), s1 = db(row, c), s2 = db(row, c + 1);  // :50-52
+        if (s1 < s0 || s1 < s2) keep = false;                                  // :54-58
+        if (keep) {
+          const double num = __dsub_rn(s0, s2);
+          const double den = __dmul_rn(2.0, __dadd_rn(__dsub_rn(s0, __dmul_rn(2.0, s1)), s2));
+          const double off = __ddiv_rn(num, den);                                     // :59
+          intSnrDelay = __dsub_rn(s1, __ddiv_rn(__dmul_rn(num, off), 4.0));           // :60
+          intDelay = __dadd_rn(d, off);                                               // :61
+        }
+      }
     }
   }
+  if (keep && a.doDoppler) {
+    if (f == a.doppler[0] || f == a.doppler[a.nDop - 1]) keep = false;  // :67-70
+    if (keep) {
+      const int c = (int)(d - d0);
+      if (row - 1 < 0 || row + 1 >= a.nDop || c < 0 || c >= a.nDel) keep = false;  // fence
+      if (keep) {
+        const double s0 = db(row - 1, c), s1 = db(row, c), s2 = db(row + 1, c);  // :71-73
+        if (s1 < s0 || s1 < s2) keep = false;                                  // :75-78
+        if (keep) {
+          const double num = __dsub_rn(s0, s2);
+          const double den = __dmul_rn(2.0, __dadd_rn(__dsub_rn(s0, __dmul_rn(2.0, s1)), s2));
+          const double off = __ddiv_rn(num, den);                                     // :79
+          intSnrDelay = __dsub_rn(s1, __ddiv_rn(__dmul_rn(num, off), 4.0));           // :80 (sic)
+          intDoppler = __dadd_rn(f, __dmul_rn(__dsub_rn(a.doppler[1], a.doppler[0]), off));  // :81
+        }
+      }
+    }
+  }
+  a.keep[i] = keep ? 1 : 0;
+  if (keep) {
+    a.out.delay[i] = intDelay;
+    a.out.doppler[i] = intDoppler;
+    a.out.snr[i] = fmax(fmax(intSnrDelay, intSnrDoppler), s);  // :86
+  }
+}
+
+template <class TMAP> __global__ void __launch_bounds__(kBlock) interp_kernel(InterpArgs a) {
+  const uint32_t n = min(*a.n, a.cap);
+  const double noisePower = a.noise_dev ? *a.noise_dev : a.noisePower;
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) interp_one<TMAP>(a, i, noisePower);
 }
 
 // ordered compaction of (delay, doppler, snr) by keep[]; single block of 1024
@@ -367,9 +370,8 @@ struct CompactArgs {
   uint32_t cap;
 };
 
-__global__ void __launch_bounds__(1024) compact_kernel(CompactArgs a) {
-  __shared__ uint32_t wsum[33];
-  const uint32_t n = min(*a.n_in, a.cap);
+// ordered compaction by one block of 1024 threads; returns the number kept
+__device__ __forceinline__ uint32_t compact_block(const CompactArgs &a, uint32_t n, uint32_t *wsum) {
   uint32_t carry = 0;
   for (uint32_t base = 0; base < n; base += 1024) {
     const uint32_t i = base + threadIdx.x;
@@ -384,7 +386,47 @@ __global__ void __launch_bounds__(1024) compact_kernel(CompactArgs a) {
     }
     carry += tot;
   }
-  if (threadIdx.x == 0) *a.n_out = carry;
+  return carry;
+}
+
+__global__ void __launch_bounds__(1024) compact_kernel(CompactArgs a) {
+  __shared__ uint32_t wsum[33];
+  const uint32_t n = min(*a.n_in, a.cap);
+  const uint32_t kept = compact_block(a, n, wsum);
+  if (threadIdx.x == 0) *a.n_out = kept;
+}
+
+// Centroid -> compaction -> Interpolate -> compaction in ONE launch by one CTA (device-resident chain:
+// detection lists are short, the four launches it replaces cost more than the work).  Same device
+// functions as the stand-alone kernels, so results are identical.
+struct TailArgs {
+  CentroidArgs ce;   // in = list A, n = count after CFAR
+  InterpArgs ia;     // in = out = list B
+  DetList A, B;
+  uint8_t *keep;
+  uint32_t *n_mid, *n_out;
+  uint32_t cap;
+  int do_interp;
+};
+
+template <class TMAP> __global__ void __launch_bounds__(1024) det_tail_kernel(TailArgs t) {
+  __shared__ uint32_t wsum[33];
+  const uint32_t n0 = min(*t.ce.n, t.cap);
+  for (uint32_t i = threadIdx.x; i < n0; i += 1024) t.keep[i] = centroid_keep(t.ce, i, n0) ? 1 : 0;
+  __syncthreads();
+  CompactArgs c1;
+  c1.in = t.A; c1.out = t.B; c1.keep = t.keep; c1.cap = t.cap;
+  const uint32_t n1 = compact_block(c1, n0, wsum);
+  if (threadIdx.x == 0) *t.n_mid = n1;
+  __syncthreads();
+  if (!t.do_interp) return;
+  const double noisePower = t.ia.noise_dev ? *t.ia.noise_dev : t.ia.noisePower;
+  for (uint32_t i = threadIdx.x; i < n1; i += 1024) interp_one<TMAP>(t.ia, i, noisePower);
+  __syncthreads();
+  CompactArgs c2;
+  c2.in = t.B; c2.out = t.A; c2.keep = t.keep; c2.cap = t.cap;
+  const uint32_t n2 = compact_block(c2, n1, wsum);
+  if (threadIdx.x == 0) *t.n_out = n2;
 }
 
 }  // namespace
@@ -447,6 +489,23 @@ int run_chain(b200dd_det *h, int last_stage, const TMAP *d_map, uint32_t nDop, u
   B2_LAUNCH_CHECK();
   *final_buf = 0;
   int count_slot = 0;
+  if (noise_dev && last_stage >= B200DD_DET_CENTROID) {
+    TailArgs t;
+    t.ce.in = list_of(h, 0); t.ce.n = h->d_n + 0; t.ce.cap = h->cap;
+    t.ce.nDelay = h->p.n_centroid_delay & 0xFFFF; t.ce.nDoppler = h->p.n_centroid_doppler & 0xFFFF;
+    t.ce.resolution = h->p.resolution_doppler; t.ce.keep = h->d_keep;
+    t.ia.in = list_of(h, 1); t.ia.out = list_of(h, 1); t.ia.n = h->d_n + 1; t.ia.cap = h->cap; t.ia.map = d_map;
+    t.ia.nDop = (int)nDop; t.ia.nDel = (int)nDel; t.ia.delay = h->d_delay; t.ia.doppler = h->d_doppler;
+    t.ia.noisePower = noisePower; t.ia.noise_dev = noise_dev; t.ia.doDelay = h->p.interp_delay;
+    t.ia.doDoppler = h->p.interp_doppler; t.ia.keep = h->d_keep;
+    t.A = list_of(h, 0); t.B = list_of(h, 1); t.keep = h->d_keep; t.n_mid = h->d_n + 1; t.n_out = h->d_n + 2;
+    t.cap = h->cap; t.do_interp = last_stage >= B200DD_DET_INTERPOLATE;
+    det_tail_kernel<TMAP><<<1, 1024, 0, st>>>(t);
+    B2_LAUNCH_CHECK();
+    *final_buf = t.do_interp ? 0 : 1;
+    *count_slot_out = t.do_interp ? 2 : 1;
+    return B200DD_OK;
+  }
   if (last_stage >= B200DD_DET_CENTROID) {
     CentroidArgs ce;
     ce.in = list_of(h, 0); ce.n = h->d_n + 0; ce.cap = h->cap;
