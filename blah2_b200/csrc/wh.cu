@@ -270,7 +270,7 @@ __device__ __forceinline__ double pow2_inv(double v) {    // 2^(-e) where v = m 
 // keep p and F near 1 (so r, phi, X stay within the magnitude of the right-hand side).  T starts at
 // t_0 = A(0,0); one division per element at the very end.  tools/schur_prototype.py has the same
 // recursion in numpy with the accuracy check against LAPACK.
-template <int EPT> __global__ void __launch_bounds__(1024, 1) wh_solve_kernel(SolveArgs s) {
+template <int EPT> __global__ void __launch_bounds__(2048 / EPT, 1) wh_solve_kernel(SolveArgs s) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = s.nBins;
   double2 *alb0 = reinterpret_cast<double2 *>(smem_raw);  // generator a_i, ping-pong (neighbour shift)
@@ -583,18 +583,19 @@ int wh_launch_solve(b200dd_wh *h, cudaStream_t st) {
   const size_t solve_smem = (size_t)h->nBins * 6 * sizeof(double2);
   const size_t solve_smem_max = (size_t)kMaxBins * 6 * sizeof(double2);  // attribute is per function, not per handle
   if (!h->attr_solve) {
-    B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
-    B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
+    B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
     h->attr_solve = true;
   }
   SolveArgs sa;
   sa.partial = h->d_partial; sa.nPartial = h->gridCorr; sa.nBins = h->nBins;
   sa.a_out = h->d_a; sa.b_out = h->d_b; sa.w_out = h->d_w; sa.status = h->d_status;
-  if (h->nBins <= 1024) {
-    const int threads = ((h->nBins + 31) / 32) * 32;
-    wh_solve_kernel<1><<<1, threads, solve_smem, st>>>(sa);
-  } else {
-    wh_solve_kernel<2><<<1, 1024, solve_smem, st>>>(sa);
+  // Four matrix rows per thread: the per-step cost of this kernel is instruction ISSUE (every warp re-derives
+  // the step's scalars and runs the loop overhead), so fewer, fatter warps win: 410 taps = 4 warps, one per
+  // scheduler (profiles/r01_summary.md).
+  {
+    const int per = (h->nBins + 3) / 4;
+    const int threads = ((per + 31) / 32) * 32;
+    wh_solve_kernel<4><<<1, threads, solve_smem, st>>>(sa);
   }
   B2_LAUNCH_CHECK();
   return B200DD_OK;
