@@ -248,29 +248,13 @@ struct SolveArgs {
   int *status;  // 0 ok, 1 failed
 };
 
-// exact powers of two from the exponent field (integer ops only, no rounding anywhere they are applied)
-__device__ __forceinline__ double pow2_scale(double p) {  // 2^(1-e) where p*p = m 2^e, m in [0.5, 1)
+// 2^(1-e) where p*p = m 2^e, m in [0.5, 1): exact power of two, integer ops only
+__device__ __forceinline__ double pow2_scale(double p) {
   const int ex = (__double2hiint(p * p) >> 20) & 0x7ff;
   return __hiloint2double((2046 - ex) << 20, 0);
 }
-__device__ __forceinline__ double pow2_inv(double v) {    // 2^(-e) where v = m 2^e, m in [0.5, 1)
-  const int ex = (__double2hiint(v) >> 20) & 0x7ff;
-  return __hiloint2double((2045 - ex) << 20, 0);
-}
 
-// The recursion of the header comment with EVERY recurrence in fraction-free form, so that no division,
-// reciprocal or square root exists anywhere in the n steps (FP64 latency on this part is ~40 cycles and
-// the profile of the previous version showed the step time was the chain pivot -> p_new -> 1/p_new ->
-// sigma executed by every warp: profiles/r01_summary.md):
-//   Schur generator   a_i <- s (p a_{i-1} - conj(b) b_i),  b_i <- s (p b_i - b a_{i-1}),  p <- s (p^2 - |b|^2)
-//   innovations       r_i <- u (p r_i - a_i r_k)                      (all r carry the factor F, F <- F u p)
-//   predictor         phi_i <- u (p phi_i - b conj(phi_{k+1-i}))       (same factor F)
-//   solution          X_i <- c (X_i + r_k conj(phi_{k-i})),  c = p_new u^2 / s,   x = X / T,  T <- T c
-// with b = b_{k+1} and r_k the values published by threads k+1 and k, and s, u exact powers of two that
-// keep p and F near 1 (so r, phi, X stay within the magnitude of the right-hand side).  T starts at
-// t_0 = A(0,0); one division per element at the very end.  tools/schur_prototype.py has the same
-// recursion in numpy with the accuracy check against LAPACK.
-template <int EPT> __global__ void __launch_bounds__(2048 / EPT, 1) wh_solve_kernel(SolveArgs s) {
+template <int EPT> __global__ void __launch_bounds__(1024, 1) wh_solve_kernel(SolveArgs s) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = s.nBins;
   double2 *alb0 = reinterpret_cast<double2 *>(smem_raw);  // generator a_i, ping-pong (neighbour shift)
@@ -290,10 +274,9 @@ template <int EPT> __global__ void __launch_bounds__(2048 / EPT, 1) wh_solve_ker
     al[e] = be[e] = rr[e] = xx[e] = make_double2(0.0, 0.0);
     if (i < n) {
       double2 sa = make_double2(0.0, 0.0), sb = make_double2(0.0, 0.0);
-#pragma unroll 4
       for (int p = 0; p < s.nPartial; p++) {
-        const double2 va = __ldg(s.partial + ((size_t)p * 2) * n + i);
-        const double2 vb = __ldg(s.partial + ((size_t)p * 2 + 1) * n + i);
+        const double2 va = s.partial[((size_t)p * 2) * n + i];
+        const double2 vb = s.partial[((size_t)p * 2 + 1) * n + i];
         sa.x += va.x; sa.y += va.y;
         sb.x += vb.x; sb.y += vb.y;
       }
@@ -315,84 +298,81 @@ template <int EPT> __global__ void __launch_bounds__(2048 / EPT, 1) wh_solve_ker
       al[e].x *= inv_t0; al[e].y *= inv_t0;  // a_i^(0) = t_i / t_0  (p_0 = 1)
       be[e] = i ? al[e] : make_double2(0.0, 0.0);
       alb0[i] = al[e];
-      phb0[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // phi^(1) = [1]
+      phb0[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // phi^(1) = [1], sigma = 1 / t_0
       phb1[i] = make_double2(0.0, 0.0);
       if (i == 0) pub_r[0] = rr[e];
       if (i == 1) pub_b[0] = be[e];
     }
   }
   __syncthreads();
-  double p = 1.0, sc = 1.0, F = 1.0, T = ok ? t0 : 1.0;
-  double u = pow2_inv(F * p);
+  double p = 1.0, inv_p = 1.0, sc = 1.0, sigma = inv_t0;
   double2 *ac = alb0, *an = alb1, *pc = phb0, *pn_ = phb1;
   if (ok) {
     for (int k = 0; k < n - 1; k++) {
       const double2 b = pub_b[k], rk = pub_r[k];
-      const double ps = p * sc, pu = p * u;
+      const double2 rho = make_double2(b.x * inv_p, b.y * inv_p);
+      const double ps = p * sc;
       const double2 bs = make_double2(b.x * sc, b.y * sc);
-      const double2 bu = make_double2(b.x * u, b.y * u);
-      const double2 rku = make_double2(rk.x * u, rk.y * u);
       const double pnew = ps * p - (bs.x * b.x + bs.y * b.y);  // p_{k+1} = s (p^2 - |b|^2)
       if (!(pnew > 0.0)) { ok = false; break; }  // uniform: every thread reads the same published pivot
-      const double c = pnew * (u * u) * pow2_inv(sc * 0.5);     // p_new u^2 / s   (1/s exact: s is a power of two)
+      const double2 q = make_double2(rk.x * inv_p, rk.y * inv_p);   // r_k / p_k
+      const double2 g = make_double2(rk.x * sigma, rk.y * sigma);   // r_k sigma
 #pragma unroll
       for (int e = 0; e < EPT; e++) {
         const int i = tid + e * NTS;
         if (i > k && i < n) {
-          // ---- (1) Schur generator + innovations
+          // ---- (1) Schur: generator update and fused forward substitution
           const double2 at = ac[i - 1];
-          double2 na, nb, nr;
+          double2 na, nb;
           na.x = ps * at.x - (bs.x * be[e].x + bs.y * be[e].y);   // s (p at - conj(b) be)
           na.y = ps * at.y - (bs.x * be[e].y - bs.y * be[e].x);
           nb.x = ps * be[e].x - (bs.x * at.x - bs.y * at.y);      // s (p be - b at)
           nb.y = ps * be[e].y - (bs.x * at.y + bs.y * at.x);
-          nr.x = pu * rr[e].x - (al[e].x * rku.x - al[e].y * rku.y);  // u (p r - a r_k)
-          nr.y = pu * rr[e].y - (al[e].x * rku.y + al[e].y * rku.x);
           an[i] = na;
           if (i == k + 2) pub_b[k + 1] = nb;
-          if (i == k + 1) pub_r[k + 1] = nr;
+          rr[e].x -= al[e].x * q.x - al[e].y * q.y;               // r_i -= a_i (r_k / p_k)
+          rr[e].y -= al[e].x * q.y + al[e].y * q.x;
+          if (i == k + 1) pub_r[k + 1] = rr[e];
           al[e] = na;
           be[e] = nb;
-          rr[e] = nr;
         }
         if (i <= k + 1 && i < n) {
-          // ---- (2) predictor and solution
+          // ---- (2) Levinson: x_i += (r_k sigma) conj(phi[k-i]) (i <= k);
+          //          phi'[i] = phi[i] (i <= k) - rho conj(phi[k+1-i]) (i >= 1)
           const double2 ph_i = (i <= k) ? pc[i] : make_double2(0.0, 0.0);
           const double2 ph_m = (i >= 1) ? pc[k + 1 - i] : make_double2(0.0, 0.0);
-          if (i <= k) {  // X_i <- c (X_i + r_k conj(phi[k-i]))
+          if (i <= k) {
             const double2 ph_x = pc[k - i];
-            const double tx = xx[e].x + (rk.x * ph_x.x + rk.y * ph_x.y);
-            const double ty = xx[e].y + (rk.y * ph_x.x - rk.x * ph_x.y);
-            xx[e].x = c * tx;
-            xx[e].y = c * ty;
+            xx[e].x += g.x * ph_x.x + g.y * ph_x.y;
+            xx[e].y += g.y * ph_x.x - g.x * ph_x.y;
           }
-          double2 np_;  // phi'_i = u (p phi_i - b conj(phi[k+1-i]))
-          np_.x = pu * ph_i.x - (bu.x * ph_m.x + bu.y * ph_m.y);
-          np_.y = pu * ph_i.y - (bu.y * ph_m.x - bu.x * ph_m.y);
+          double2 np_;
+          np_.x = ph_i.x - (rho.x * ph_m.x + rho.y * ph_m.y);
+          np_.y = ph_i.y - (rho.y * ph_m.x - rho.x * ph_m.y);
           pn_[i] = np_;
         }
       }
-      T *= c;
-      F = F * pu;                  // F u p
+      const double inv_pn = 1.0 / pnew;
+      sigma = sigma * sc * p * p * inv_pn;  // sigma / (1 - |rho|^2)
       p = pnew;
+      inv_p = inv_pn;
       sc = pow2_scale(pnew);
-      u = pow2_inv(F * pnew);
       __syncthreads();
       double2 *t = ac; ac = an; an = t;
       t = pc; pc = pn_; pn_ = t;
     }
   }
   if (ok) {
-    // last innovation: X_i += r_{n-1} conj(phi[n-1-i]);  x = X / T
+    // last innovation: x_i += (r_{n-1} sigma) conj(phi[n-1-i])
     const double2 rk = pub_r[n - 1];
-    const double inv_T = 1.0 / T;
+    const double2 g = make_double2(rk.x * sigma, rk.y * sigma);
 #pragma unroll
     for (int e = 0; e < EPT; e++) {
       const int i = tid + e * NTS;
       if (i < n) {
         const double2 ph_x = pc[n - 1 - i];
-        xx[e].x = (xx[e].x + (rk.x * ph_x.x + rk.y * ph_x.y)) * inv_T;
-        xx[e].y = (xx[e].y + (rk.y * ph_x.x - rk.x * ph_x.y)) * inv_T;
+        xx[e].x += g.x * ph_x.x + g.y * ph_x.y;
+        xx[e].y += g.y * ph_x.x - g.x * ph_x.y;
       }
     }
   }
@@ -583,19 +563,18 @@ int wh_launch_solve(b200dd_wh *h, cudaStream_t st) {
   const size_t solve_smem = (size_t)h->nBins * 6 * sizeof(double2);
   const size_t solve_smem_max = (size_t)kMaxBins * 6 * sizeof(double2);  // attribute is per function, not per handle
   if (!h->attr_solve) {
-    B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
+    B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
+    B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
     h->attr_solve = true;
   }
   SolveArgs sa;
   sa.partial = h->d_partial; sa.nPartial = h->gridCorr; sa.nBins = h->nBins;
   sa.a_out = h->d_a; sa.b_out = h->d_b; sa.w_out = h->d_w; sa.status = h->d_status;
-  // Four matrix rows per thread: the per-step cost of this kernel is instruction ISSUE (every warp re-derives
-  // the step's scalars and runs the loop overhead), so fewer, fatter warps win: 410 taps = 4 warps, one per
-  // scheduler (profiles/r01_summary.md).
-  {
-    const int per = (h->nBins + 3) / 4;
-    const int threads = ((per + 31) / 32) * 32;
-    wh_solve_kernel<4><<<1, threads, solve_smem, st>>>(sa);
+  if (h->nBins <= 1024) {
+    const int threads = ((h->nBins + 31) / 32) * 32;
+    wh_solve_kernel<1><<<1, threads, solve_smem, st>>>(sa);
+  } else {
+    wh_solve_kernel<2><<<1, 1024, solve_smem, st>>>(sa);
   }
   B2_LAUNCH_CHECK();
   return B200DD_OK;
