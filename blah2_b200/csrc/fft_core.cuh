@@ -45,9 +45,61 @@ template <> struct V2<double> { using type = double2; };
 template <class T> using cpx = typename V2<T>::type;
 
 template <class T> B2_HD cpx<T> mk(T x, T y) { cpx<T> r; r.x = x; r.y = y; return r; }
-B2_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+
+// ---------------------------------------------------------------------------------
+// Packed FP32 (sm_100a): add/sub/mul/fma.rn.f32x2 operate on a (re, im) register pair in ONE instruction
+// (SASS FADD2 / FMUL2 / FFMA2, with per-operand broadcast, swap and per-half negate modifiers that ptxas
+// folds from the surrounding moves).  A complex add is 1 instruction instead of 2, a complex multiply 2-3
+// instead of 4; the FP32 FFT kernels are instruction-issue bound (profiles/r01_summary.md), so this is
+// where their time goes.  Results are the IEEE round-to-nearest results of the same scalar operations.
+// Host builds (tests/native/fft_sim.cu) and B2_NO_PACKED_F32 use the scalar forms.
+// ---------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__) && !defined(B2_NO_PACKED_F32)
+#define B2_PACKED_F32 1
+namespace p2 {
+__device__ __forceinline__ float2 add(float2 a, float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 sub(float2 a, float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 mul(float2 a, float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 fma(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+}  // namespace p2
+#endif
+
+B2_HD float2 cadd(float2 a, float2 b) {
+#ifdef B2_PACKED_F32
+  return p2::add(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
 B2_HD double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-B2_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+B2_HD float2 csub(float2 a, float2 b) {
+#ifdef B2_PACKED_F32
+  return p2::sub(a, b);
+#else
+  return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
 B2_HD double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 // a * b
 template <class C> B2_HD C cmul(C a, C b) { C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
@@ -57,6 +109,29 @@ template <class C> B2_HD C cmulc(C a, C b) { C r; r.x = a.x * b.x + a.y * b.y; r
 template <class C> B2_HD void cfmac(C &acc, C a, C b) {
   acc.x += a.x * b.x + a.y * b.y;
   acc.y += a.y * b.x - a.x * b.y;
+}
+#ifdef B2_PACKED_F32
+// (ax bx - ay by, ax by + ay bx) = (ax, ax) * (bx, by) + (ay, ay) * (-by, bx)
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return p2::fma(make_float2(a.y, a.y), make_float2(-b.y, b.x), p2::mul(make_float2(a.x, a.x), b));
+}
+// (ax bx + ay by, ay bx - ax by) = (bx, bx) * (ax, ay) + (by, by) * (ay, -ax)
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+  return p2::fma(make_float2(b.y, b.y), make_float2(a.y, -a.x), p2::mul(make_float2(b.x, b.x), a));
+}
+__device__ __forceinline__ void cfmac(float2 &acc, float2 a, float2 b) {
+  acc = p2::fma(make_float2(b.x, b.x), a, acc);
+  acc = p2::fma(make_float2(b.y, b.y), make_float2(a.y, -a.x), acc);
+}
+#endif
+// a * a
+B2_HD double2 csqr(double2 a) { return make_double2(a.x * a.x - a.y * a.y, (a.x + a.x) * a.y); }
+B2_HD float2 csqr(float2 a) {
+#ifdef B2_PACKED_F32
+  return cmul(a, a);
+#else
+  return make_float2(a.x * a.x - a.y * a.y, (a.x + a.x) * a.y);
+#endif
 }
 template <class C> B2_HD C cconj(C a) { a.y = -a.y; return a; }
 template <class C, class T> B2_HD C cscale(C a, T s) { a.x *= s; a.y *= s; return a; }
@@ -103,6 +178,16 @@ template <class T> B2_HD constexpr T cos32(int k) {
 }
 template <class T> B2_HD constexpr T sin32(int k) { return cos32<T>(k - 8); }
 
+// a * c + b * s elementwise on the (re, im) pair: every constant rotation is one of these
+B2_HD double2 rot_pair(double2 a, double2 b, double c, double s) { return make_double2(a.x * c + b.x * s, a.y * c + b.y * s); }
+B2_HD float2 rot_pair(float2 a, float2 b, float c, float s) {
+#ifdef B2_PACKED_F32
+  return p2::fma(b, make_float2(s, s), p2::mul(a, make_float2(c, c)));
+#else
+  return make_float2(a.x * c + b.x * s, a.y * c + b.y * s);
+#endif
+}
+
 // v *= exp(DIR * 2 pi i * K / RS), all compile time
 template <class T, int K, int RS, int DIR> B2_HD void rot_const(cpx<T> &v) {
   if constexpr (K == 0) {
@@ -113,18 +198,17 @@ template <class T, int K, int RS, int DIR> B2_HD void rot_const(cpx<T> &v) {
   } else if constexpr (8 * K == RS) {  // * (1 + DIR i) / sqrt2
     const T h = T(0.70710678118654752440084436210485);
     T x = v.x, y = v.y;
-    if constexpr (DIR < 0) { v.x = (x + y) * h; v.y = (y - x) * h; } else { v.x = (x - y) * h; v.y = (x + y) * h; }
+    if constexpr (DIR < 0) v = rot_pair(mk<T>(x, y), mk<T>(y, -x), h, h); else v = rot_pair(mk<T>(x, y), mk<T>(-y, x), h, h);
   } else if constexpr (8 * K == 3 * RS) {  // * (-1 + DIR i) / sqrt2
     const T h = T(0.70710678118654752440084436210485);
     T x = v.x, y = v.y;
-    if constexpr (DIR < 0) { v.x = (y - x) * h; v.y = -(x + y) * h; } else { v.x = -(x + y) * h; v.y = (x - y) * h; }
+    if constexpr (DIR < 0) v = rot_pair(mk<T>(y, -x), mk<T>(-x, -y), h, h); else v = rot_pair(mk<T>(-x, -y), mk<T>(-y, x), h, h);
   } else {
     constexpr int k32 = K * (32 / RS);
     const T c = cos32<T>(k32);
     const T s = T(DIR) * sin32<T>(k32);
     T x = v.x, y = v.y;
-    v.x = x * c - y * s;
-    v.y = x * s + y * c;
+    v = rot_pair(mk<T>(x, y), mk<T>(-y, x), c, s);   // (x c - y s, y c + x s)
   }
 }
 
@@ -203,7 +287,7 @@ B2_HD int fft_butterfly_core(int b, int log2S, const cpx<T> *__restrict__ tw, LD
     wp[0] = tw[tstep];
 #pragma unroll
     for (int j = 1; j < ilog2<R>(); j++)
-      wp[j] = mk<T>(wp[j - 1].x * wp[j - 1].x - wp[j - 1].y * wp[j - 1].y, (wp[j - 1].x + wp[j - 1].x) * wp[j - 1].y);
+      wp[j] = csqr(wp[j - 1]);
     cpx<T> run = wp[0];  // w^(q with its lowest set bit cleared), valid when that is non-zero
     cpx<T> hold = wp[0];
 #pragma unroll

@@ -44,8 +44,10 @@ def run(name, log2m=None, parts=None, iters=20, nbuf=8):
     amb.close()
 
 if __name__ == "__main__":
-    for name in sys.argv[1:] or ["cfg1", "cfg3"]:
+    sweep = "--sweep" in sys.argv
+    for name in [a for a in sys.argv[1:] if not a.startswith("--")] or ["cfg1", "cfg3"]:
         run(name)
-        for l in (10, 11, 12, 13):
-            for p in (1, 2, 4, 8):
-                run(name, l, p)
+        if sweep:
+            for l in (10, 11, 12, 13):
+                for p in (1, 2, 4, 8):
+                    run(name, l, p)
