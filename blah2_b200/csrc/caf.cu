@@ -111,21 +111,74 @@ struct RangeArgs {
   int batch0;  // first batch of this launch (sharded single-CPI mode); x, y point at batch 0 of the CPI
 };
 
-// resident CTAs per SM the register allocator must leave room for (<= 128 regs/thread)
-template <int LOG2M> constexpr int range_min_ctas() {
-  return Plan<LOG2M>::NT >= 512 ? 1 : (512 / Plan<LOG2M>::NT > 16 ? 16 : 512 / Plan<LOG2M>::NT);
+// ---- TMA (bulk async copy) staging of the IQ segments ---------------------------------------------
+// One elected thread per CTA issues cp.async.bulk global -> shared (SASS UBLKCP) for the NEXT segment's x
+// and y windows while the CTA computes the current one; completion is signalled on an mbarrier
+// (expect_tx / complete_tx), the other threads only spin on its phase bit.  Bulk copies need 16-byte
+// aligned addresses and sizes but float2 segments start on any 8-byte boundary (nCorr and the hop are
+// arbitrary), so the copy covers the 16-byte-aligned INTERIOR of the wanted range and the at most one
+// element on either side is read with an ordinary load -- no byte outside the caller's buffers is touched.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!done);
 }
 
-template <int LOG2M>
-__global__ void __launch_bounds__(Plan<LOG2M>::NT, range_min_ctas<LOG2M>()) caf_range_kernel(RangeArgs a) {
+// [g0, g1) wanted elements of a float2 array -> [s0, s1) the 16-byte aligned interior (may be empty)
+struct StageRange {
+  long long g0, s0, s1;
+};
+__device__ __forceinline__ StageRange stage_range(const float2 *base, long long g0, long long g1) {
+  StageRange r;
+  r.g0 = g0;
+  r.s0 = g0 + (long long)((reinterpret_cast<uintptr_t>(base + g0) >> 3) & 1);
+  r.s1 = g1 - (long long)((reinterpret_cast<uintptr_t>(base + g1) >> 3) & 1);
+  if (r.s1 < r.s0) r.s1 = r.s0;
+  return r;
+}
+
+// resident CTAs per SM the register allocator must leave room for
+template <int LOG2M, bool STAGE> constexpr int range_min_ctas() {
+  constexpr int NT = Plan<LOG2M>::NT;
+  if (STAGE) {  // shared memory (two FFT buffers + two staging buffers) is the limit, not registers
+    constexpr int smem = 2 * Plan<LOG2M>::MP * 8 + 2 * Plan<LOG2M>::M * 8 + 1024;
+    constexpr int by_smem = (227 * 1024) / smem;
+    return by_smem < 1 ? 1 : (by_smem > 8 ? 8 : by_smem);
+  }
+  return NT >= 512 ? 1 : (512 / NT > 16 ? 16 : 512 / NT);  // <= 128 regs/thread
+}
+
+template <int LOG2M, bool STAGE>
+__global__ void __launch_bounds__(Plan<LOG2M>::NT, range_min_ctas<LOG2M, STAGE>()) caf_range_kernel(RangeArgs a) {
   using P = Plan<LOG2M>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float2 *A = reinterpret_cast<float2 *>(smem_raw);
   float2 *B = A + P::MP;
+  float2 *SX = B + P::MP;   // staging (STAGE only): x segment, then the y window
+  float2 *SY = SX + P::M;
+  __shared__ uint64_t mbar;
   const int tid = threadIdx.x;
   const int batch = a.batch0 + blockIdx.x;
-  const float2 *__restrict__ xb = a.x + (size_t)batch * a.nCorr;
-  const float2 *__restrict__ yb = a.y + (size_t)batch * a.nCorr;
+  const long long boff = (long long)batch * a.nCorr;
+  const float2 *__restrict__ xb = a.x + boff;
+  const float2 *__restrict__ yb = a.y + boff;
   const float2 zero = make_float2(0.f, 0.f);
 
   float2 Z[16];
@@ -137,18 +190,70 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, range_min_ctas<LOG2M>()) caf_
   // its own inverse FFT and the parts are added, in a fixed order, by the Doppler kernel's loader.
   const int seg0 = blockIdx.y * a.segPerPart;
   const int seg1 = min(a.nSeg, seg0 + a.segPerPart);
+
+  // wanted element ranges of segment `seg`, relative to the start of the batch
+  auto seg_ranges = [&](int seg, StageRange &rx, StageRange &ry) {
+    const int n0 = seg * a.L;
+    const int len = min(a.L, a.nCorr - n0);
+    const int yoff = n0 + a.lagMin;
+    const int j0 = max(yoff, 0), j1 = max(j0, min(yoff + len + a.nDel - 1, a.nCorr));
+    rx = stage_range(xb, n0, n0 + len);
+    ry = stage_range(yb, j0, j1);
+  };
+  auto issue = [&](int seg) {  // one thread
+    StageRange rx, ry;
+    seg_ranges(seg, rx, ry);
+    const uint32_t bx = (uint32_t)(rx.s1 - rx.s0) * 8u, by = (uint32_t)(ry.s1 - ry.s0) * 8u;
+    mbar_expect_tx(&mbar, bx + by);
+    if (bx) bulk_g2s(SX, xb + rx.s0, bx, &mbar);
+    if (by) bulk_g2s(SY, yb + ry.s0, by, &mbar);
+  };
+  uint32_t phase = 0;
+  if constexpr (STAGE) {
+    if (tid == 0) {
+      mbar_init(&mbar, 1);
+      if (seg0 < seg1) issue(seg0);
+    }
+    __syncthreads();
+  }
+
   for (int seg = seg0; seg < seg1; seg++) {
     const int n0 = seg * a.L;
     const int len = min(a.L, a.nCorr - n0);
     const int ylen = len + a.nDel - 1;   // window entries that can reach a wanted lag
     const int yoff = n0 + a.lagMin;
-    auto ldx = [&](int m) { return m < len ? __ldg(xb + n0 + m) : zero; };
-    auto ldy = [&](int m) {
-      const int j = yoff + m;
-      return (m < ylen && j >= 0 && j < a.nCorr) ? __ldg(yb + j) : zero;
-    };
     auto stA = [&](int i, float2 v) { A[pad(i)] = v; };
     auto stB = [&](int i, float2 v) { B[pad(i)] = v; };
+    StageRange rx, ry;
+    if constexpr (STAGE) seg_ranges(seg, rx, ry);
+    // loaders: element m of the zero-padded x segment / of the y window masked to the batch
+    auto ldx = [&](int m) {
+      if constexpr (STAGE) {
+        const long long g = (long long)n0 + m;
+        const int idx = (int)(g - rx.s0);
+        float2 v = SX[min(max(idx, 0), P::M - 1)];
+        if (m < len && (g < rx.s0 || g >= rx.s1)) v = __ldg(xb + g);   // at most one element per side
+        return m < len ? v : zero;
+      } else {
+        return m < len ? __ldg(xb + n0 + m) : zero;
+      }
+    };
+    auto ldy = [&](int m) {
+      const int j = yoff + m;
+      const bool valid = m < ylen && j >= 0 && j < a.nCorr;
+      if constexpr (STAGE) {
+        const int idx = (int)((long long)j - ry.s0);
+        float2 v = SY[min(max(idx, 0), P::M - 1)];
+        if (valid && (j < ry.s0 || j >= ry.s1)) v = __ldg(yb + j);
+        return valid ? v : zero;
+      } else {
+        return valid ? __ldg(yb + j) : zero;
+      }
+    };
+    if constexpr (STAGE) {
+      mbar_wait(&mbar, phase);
+      phase ^= 1;
+    }
     if (seg > seg0) __syncthreads();  // previous segment's last pass has finished reading A/B
     if constexpr (P::R0 == 16) {
       fft_butterfly<float, 16, -1, LOG2M>(tid, P::log2S(0), a.tw, ldx, stA);
@@ -161,6 +266,9 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, range_min_ctas<LOG2M>()) caf_
       }
     }
     __syncthreads();
+    if constexpr (STAGE) {  // staging buffers are free again: fetch the next segment under the remaining passes
+      if (tid == 0 && seg + 1 < seg1) issue(seg + 1);
+    }
 #pragma unroll 1
     for (int p = 1; p < P::NP - 1; p++) {
       smem_pass<float, LOG2M, -1>(A, a.tw, p, tid);
@@ -336,19 +444,31 @@ __global__ void caf_widen_kernel(const float2 *__restrict__ in, double2 *__restr
 
 // ------------------------------------------------------------------ launch dispatch
 
-template <int LOG2M> int launch_range(const RangeArgs &a, int nDop, int nParts, cudaStream_t st) {
+template <int LOG2M, bool STAGE> int launch_range_impl(const RangeArgs &a, int nDop, int nParts, cudaStream_t st) {
   using P = Plan<LOG2M>;
-  const size_t smem = 2 * (size_t)P::MP * sizeof(float2);
+  const size_t smem = 2 * (size_t)P::MP * sizeof(float2) + (STAGE ? 2 * (size_t)P::M * sizeof(float2) : 0);
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    B2_CUDA(cudaFuncSetAttribute(caf_range_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_CUDA(cudaFuncSetAttribute(caf_range_kernel<LOG2M, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done[dev & 63] = true;
   }
-  caf_range_kernel<LOG2M><<<dim3(nDop, nParts), P::NT, smem, st>>>(a);
+  caf_range_kernel<LOG2M, STAGE><<<dim3(nDop, nParts), P::NT, smem, st>>>(a);
   B2_LAUNCH_CHECK();
   return B200DD_OK;
+}
+
+// TMA staging needs 2 more M-element buffers (fits up to M = 4096).  Measured on B200 it is equal at
+// config 1/2 and 7 % slower at config 3/4 than direct loads (profiles/r01_summary.md), so it is opt-in:
+// B200DD_CAF_TMA=1.
+template <int LOG2M> int launch_range(const RangeArgs &a, int nDop, int nParts, cudaStream_t st) {
+  const char *e = getenv("B200DD_CAF_TMA");  // read per call: the parity tests toggle it
+  const int env = e ? atoi(e) : 0;
+  if constexpr (LOG2M <= 12) {
+    if (env == 1) return launch_range_impl<LOG2M, true>(a, nDop, nParts, st);
+  }
+  return launch_range_impl<LOG2M, false>(a, nDop, nParts, st);
 }
 
 template <int LOG2M> int launch_doppler(const DopplerArgs &a, cudaStream_t st) {

@@ -235,7 +235,9 @@ __global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, 1) wh_corr_kernel(CorrArg
 //          sigma <- sigma / (1 - |rho_k|^2),        x <- [x; 0] + r_k sigma J conj(phi).
 //
 // One CTA, one matrix row per thread (two above 1024 taps), ONE __syncthreads per step; thread i runs
-// part (2) while i <= k+1 and part (1) while i > k, so the CTA stays busy for all n steps.  No factor
+// part (2) while i <= k+1 and part (1) while i > k, so the CTA stays busy for all n steps.  This generic
+// kernel serves n > 992 taps; smaller systems (the reference's 410 taps) use wh_solve_short_kernel below:
+// same recursion, shorter per-warp instruction streams.  No factor
 // is stored (an earlier two-sweep version spent most of its time scattering L to global memory:
 // profiles/r01_summary.md).  Prototype and accuracy check against LAPACK (1e-15 at 2048 taps):
 // tools/schur_prototype.py.  The Schur recursion is backward stable for positive-definite Toeplitz
@@ -381,6 +383,220 @@ template <int EPT> __global__ void __launch_bounds__(1024, 1) wh_solve_kernel(So
     const int i = tid + e * NTS;
     if (i < n) s.w_out[i] = ok ? xx[e] : make_double2(0.0, 0.0);
   }
+  if (tid == 0) *s.status = ok ? 0 : 1;
+}
+
+// 1/p for a pivot that the power-of-two scaling keeps near 1: hardware seed (2^-20) + two Newton steps,
+// no branches, ~1 ulp.
+__device__ __forceinline__ double rcp_newton(double p) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(p));
+  double e = fma(-p, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-p, x, 1.0);
+  x = fma(x, e, x);
+  return x;
+}
+
+// ---- short-path variant (n <= 992 taps; the reference's configuration is 410) -----------------------
+// Profiling the kernel above showed each warp issuing one instruction per ~8.4 clocks: an in-order warp
+// running a ~105-instruction, almost fully dependent stream per step (pivot chain, IEEE reciprocal, and
+// both recursions for the warp that straddles row k) while the other warps wait at the barrier for it;
+// tools/ubench/sync_rates.cu puts the floor of a 13-warp "LDS -> 3 dependent DFMA -> STS -> barrier" step
+// at ~240 clocks against the ~880 measured.  Same recursion, shorter per-warp streams:
+//   * a warp whose rows are all > k+2 runs the Schur update only, a warp whose rows are all <= k the
+//     Levinson update only (warp-uniform branches);
+//   * the one or two "corner" warps holding rows k+1, k+2 run both, branch-free on clamped indices with
+//     the results committed by selects, so that the two dependency chains overlap;
+//   * the pivot chain p_{k+1} = s (p^2 - |b|^2), 1/p_{k+1}, s_{k+1}, sigma_{k+1} only depends on b_k and
+//     p_k -- values known at the START of step k -- so ONE extra warp computes it beside the elementwise
+//     work of step k instead of every warp computing it in front of step k+1.
+// Per step the owners of rows k+2 / k+1 publish the raw b_{k+1} / r_{k+1}, the scalar warp publishes the
+// state; consumers form the products they need (b s, r/p, b/p, r sigma).  One __syncthreads per step.
+// Measured history of this kernel: profiles/r01_summary.md §1.
+struct SolveState { double2 ps_p, invp_sigma, sc_; };
+
+template <int MAXT> __global__ void __launch_bounds__(MAXT, 1) wh_solve_short_kernel(SolveArgs s) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = s.nBins;
+  double2 *alb0 = reinterpret_cast<double2 *>(smem_raw);  // generator a_i, ping-pong (neighbour shift)
+  double2 *alb1 = alb0 + n;
+  double2 *phb0 = alb1 + n;    // predictor phi_i, ping-pong (mirrored access)
+  double2 *phb1 = phb0 + n;
+  __shared__ double s_t0;
+  __shared__ SolveState St[2];
+  __shared__ double2 Bv[2], Rv[2];  // raw b_k, r_k, double buffered on the parity of k
+  const int tid = threadIdx.x;
+  const int NTS = (n + 31) & ~31;
+  const bool scalar_warp = tid >= NTS;
+  const int i = tid;  // row (row warps)
+  const int row_lo = tid & ~31, row_hi = row_lo + 31;
+  const double2 zero = make_double2(0.0, 0.0);
+
+  // fixed-order reduction of the per-CTA partial correlations (deterministic), 8 loads in flight
+  double2 sa = zero, sb = zero;
+  if (!scalar_warp && i < n) {
+    const double2 *src = s.partial + i;
+    int p = 0;
+    for (; p + 4 <= s.nPartial; p += 4) {
+      double2 va[4], vb[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        va[u] = __ldg(src + (size_t)(p + u) * 2 * n);
+        vb[u] = __ldg(src + ((size_t)(p + u) * 2 + 1) * n);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        sa.x += va[u].x; sa.y += va[u].y;
+        sb.x += vb[u].x; sb.y += vb[u].y;
+      }
+    }
+    for (; p < s.nPartial; p++) {
+      const double2 va = __ldg(src + (size_t)p * 2 * n), vb = __ldg(src + ((size_t)p * 2 + 1) * n);
+      sa.x += va.x; sa.y += va.y;
+      sb.x += vb.x; sb.y += vb.y;
+    }
+    s.a_out[i] = sa;
+    s.b_out[i] = sb;
+    if (i == 0) s_t0 = sa.x;
+  }
+  __syncthreads();
+  const double t0 = s_t0;
+  bool ok = (t0 > 0.0) && isfinite(t0);
+  const double inv_t0 = ok ? 1.0 / t0 : 1.0;
+  double2 al = zero, be = zero, rr = zero, xx = zero;
+  if (!scalar_warp && i < n) {
+    al = make_double2(sa.x * inv_t0, -sa.y * inv_t0);  // a_i^(0) = conj(a[i]) / t_0  (p_0 = 1)
+    be = i ? al : zero;
+    rr = sb;
+    alb0[i] = al;
+    phb0[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // phi^(1) = [1], sigma_0 = 1 / t_0
+    phb1[i] = zero;
+    if (i == 0) {
+      Rv[0] = rr;
+      St[0].ps_p = make_double2(1.0, 1.0);
+      St[0].invp_sigma = make_double2(1.0, inv_t0);
+      St[0].sc_ = make_double2(1.0, 0.0);
+    }
+    if (i == 1) Bv[0] = be;
+  }
+  __syncthreads();
+  double2 *ac = alb0, *an = alb1, *pc = phb0, *pn_ = phb1;
+  if (ok) {
+    for (int k = 0; k < n - 1; k++) {
+      const int par = k & 1;
+      const double2 c0 = St[par].ps_p;
+      const double ps = c0.x, p = c0.y;
+      if (scalar_warp) {
+        // ---- p_{k+1} = s (p^2 - |b|^2) and everything derived from it, for the next step
+        const double2 b = Bv[par];
+        const double sc = St[par].sc_.x, sigma = St[par].invp_sigma.y;
+        const double pnew = ps * p - ((b.x * sc) * b.x + (b.y * sc) * b.y);
+        const double inv_pn = rcp_newton(pnew);
+        const double scn = pow2_scale(pnew);
+        const double sign = sigma * ps * p * inv_pn;  // sigma / (1 - |rho|^2)
+        if ((tid & 31) == 0) {
+          St[par ^ 1].ps_p = make_double2(pnew * scn, pnew);
+          St[par ^ 1].invp_sigma = make_double2(inv_pn, sign);
+          St[par ^ 1].sc_ = make_double2(scn, 0.0);
+        }
+      } else if (row_lo > k + 2) {
+        // ---- warp entirely below the active corner: Schur rows only
+        const double2 at = ac[i - 1];
+        const double2 b = Bv[par], r = Rv[par];
+        const double sc = St[par].sc_.x, inv_p = St[par].invp_sigma.x;
+        const double2 bs = make_double2(b.x * sc, b.y * sc);
+        const double2 q = make_double2(r.x * inv_p, r.y * inv_p);  // r_k / p_k
+        if (i < n) {
+          double2 na, nb;
+          na.x = ps * at.x - (bs.x * be.x + bs.y * be.y);   // s (p at - conj(b) be)
+          na.y = ps * at.y - (bs.x * be.y - bs.y * be.x);
+          nb.x = ps * be.x - (bs.x * at.x - bs.y * at.y);   // s (p be - b at)
+          nb.y = ps * be.y - (bs.x * at.y + bs.y * at.x);
+          an[i] = na;
+          rr.x -= al.x * q.x - al.y * q.y;                  // r_i -= a_i (r_k / p_k)
+          rr.y -= al.x * q.y + al.y * q.x;
+          al = na;
+          be = nb;
+        }
+      } else if (row_hi <= k) {
+        // ---- warp entirely above it: Levinson rows only
+        //      x_i += (r_k sigma) conj(phi[k-i]);  phi'[i] = phi[i] - rho conj(phi[k+1-i]) (i >= 1), rho = b / p
+        const double2 ph_i = pc[i], ph_x = pc[k - i];
+        double2 ph_m = pc[k + 1 - (i ? i : 1)];
+        const double2 b = Bv[par], r = Rv[par];
+        const double2 is = St[par].invp_sigma;
+        const double2 rho = make_double2(b.x * is.x, b.y * is.x);
+        const double2 g = make_double2(r.x * is.y, r.y * is.y);
+        ph_m = i ? ph_m : zero;
+        xx.x += g.x * ph_x.x + g.y * ph_x.y;
+        xx.y += g.y * ph_x.x - g.x * ph_x.y;
+        double2 np_;
+        np_.x = ph_i.x - (rho.x * ph_m.x + rho.y * ph_m.y);
+        np_.y = ph_i.y - (rho.y * ph_m.x - rho.x * ph_m.y);
+        pn_[i] = np_;
+      } else {
+        // ---- the corner: rows on both sides and the owners of rows k+1 / k+2.  Everything is computed
+        //      unconditionally on clamped indices and committed by selects: one basic block.
+        const int ic = min(i, n - 1);
+        const double2 at = ac[max(ic - 1, 0)];
+        const double2 ph_i = pc[ic];
+        const double2 ph_m = pc[min(max(k + 1 - ic, 0), n - 1)];
+        const double2 ph_x = pc[min(max(k - ic, 0), n - 1)];
+        const double2 b = Bv[par], r = Rv[par];
+        const double sc = St[par].sc_.x;
+        const double2 is = St[par].invp_sigma;
+        const double2 bs = make_double2(b.x * sc, b.y * sc);
+        const double2 q = make_double2(r.x * is.x, r.y * is.x);
+        const double2 rho = make_double2(b.x * is.x, b.y * is.x);
+        const double2 g = make_double2(r.x * is.y, r.y * is.y);
+        const bool isS = i > k && i < n, isL = i <= k + 1 && i < n;
+        // (1) Schur
+        double2 na, nb, nr;
+        na.x = ps * at.x - (bs.x * be.x + bs.y * be.y);
+        na.y = ps * at.y - (bs.x * be.y - bs.y * be.x);
+        nb.x = ps * be.x - (bs.x * at.x - bs.y * at.y);
+        nb.y = ps * be.y - (bs.x * at.y + bs.y * at.x);
+        nr.x = rr.x - (al.x * q.x - al.y * q.y);
+        nr.y = rr.y - (al.x * q.y + al.y * q.x);
+        if (isS) an[i] = na;
+        if (i == k + 2 && i < n) Bv[par ^ 1] = nb;  // b_{k+1}
+        if (i == k + 1) Rv[par ^ 1] = nr;           // r_{k+1}
+        al = isS ? na : al;
+        be = isS ? nb : be;
+        rr = isS ? nr : rr;
+        // (2) Levinson
+        const double2 pi_ = i <= k ? ph_i : zero;
+        const double2 pm_ = i >= 1 ? ph_m : zero;
+        const double nx = xx.x + (g.x * ph_x.x + g.y * ph_x.y);
+        const double ny = xx.y + (g.y * ph_x.x - g.x * ph_x.y);
+        xx.x = i <= k ? nx : xx.x;
+        xx.y = i <= k ? ny : xx.y;
+        double2 np_;
+        np_.x = pi_.x - (rho.x * pm_.x + rho.y * pm_.y);
+        np_.y = pi_.y - (rho.y * pm_.x - rho.x * pm_.y);
+        if (isL) pn_[i] = np_;
+      }
+      if (!(p > 0.0)) { ok = false; break; }  // uniform: every thread read the same published pivot
+      __syncthreads();
+      double2 *t = ac; ac = an; an = t;
+      t = pc; pc = pn_; pn_ = t;
+    }
+  }
+  if (ok) {
+    const int par = (n - 1) & 1;
+    if (!(St[par].ps_p.y > 0.0)) ok = false;  // the last pivot
+    if (!scalar_warp && i < n) {
+      // last innovation: x_i += (r_{n-1} sigma) conj(phi[n-1-i])
+      const double2 r = Rv[par];
+      const double sigma = St[par].invp_sigma.y;
+      const double2 g = make_double2(r.x * sigma, r.y * sigma);
+      const double2 ph_x = pc[n - 1 - i];
+      xx.x += g.x * ph_x.x + g.y * ph_x.y;
+      xx.y += g.y * ph_x.x - g.x * ph_x.y;
+    }
+  }
+  if (!scalar_warp && i < n) s.w_out[i] = ok ? xx : zero;
   if (tid == 0) *s.status = ok ? 0 : 1;
 }
 
@@ -565,13 +781,22 @@ int wh_launch_solve(b200dd_wh *h, cudaStream_t st) {
   if (!h->attr_solve) {
     B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
     B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
+    B2_CUDA(cudaFuncSetAttribute(wh_solve_short_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
+    B2_CUDA(cudaFuncSetAttribute(wh_solve_short_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
     h->attr_solve = true;
   }
   SolveArgs sa;
   sa.partial = h->d_partial; sa.nPartial = h->gridCorr; sa.nBins = h->nBins;
   sa.a_out = h->d_a; sa.b_out = h->d_b; sa.w_out = h->d_w; sa.status = h->d_status;
-  if (h->nBins <= 1024) {
-    const int threads = ((h->nBins + 31) / 32) * 32;
+  const int threads = ((h->nBins + 31) / 32) * 32;
+  static const int split_env = [] {
+    const char *e = getenv("B200DD_WH_SOLVE_SHORT");
+    return e ? atoi(e) : 1;
+  }();
+  if (split_env && threads + 32 <= 1024) {  // includes the reference's configuration (410 taps)
+    if (threads + 32 <= 512) wh_solve_short_kernel<512><<<1, threads + 32, solve_smem, st>>>(sa);
+    else wh_solve_short_kernel<1024><<<1, threads + 32, solve_smem, st>>>(sa);
+  } else if (h->nBins <= 1024) {
     wh_solve_kernel<1><<<1, threads, solve_smem, st>>>(sa);
   } else {
     wh_solve_kernel<2><<<1, 1024, solve_smem, st>>>(sa);
