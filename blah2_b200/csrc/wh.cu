@@ -172,6 +172,20 @@ __global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, 1) wh_corr_kernel(CorrArg
       const double2 v = ld_iq(y, i);
       return m < wlen ? v : zero;
     };
+    // hint the NEXT segment's x and y windows into L2 (one 128-byte line per thread and array): this CTA is
+    // alone on its SM, so nothing else hides the DRAM latency of the pass-0 loads (25 % of the stall samples
+    // sat on their first use: profiles/r01_summary.md)
+    if (s + 1 < s1) {
+      constexpr uint32_t per_line = 128 / sizeof(TIN);
+      for (uint32_t e = (uint32_t)tid * per_line; e < (uint32_t)P::M; e += (uint32_t)P::NT * per_line) {
+        uint32_t i = n0 + (uint32_t)a.L + e;
+        i = i >= a.N ? i - a.N : i;
+        if (i < a.N) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(y + i));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(x + xs(i)));
+        }
+      }
+    }
     double2 vxp[R], v[R];
     fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldxp, vxp);
     __syncthreads();
@@ -663,6 +677,15 @@ __global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, wh_min_ctas<LOG2M, LR>())
     const double2 v = ld_iq(x, xs((uint32_t)ic));
     return (i >= 0 && i < (int64_t)a.N && m < hist + nOut) ? v : zero;
   };
+  // the weight spectrum (M x 16 B, the same for every CTA) and this block's surveillance samples are
+  // needed two FFT passes from now: pull them towards the SM while the forward transform runs
+  {
+    const char *wsp = reinterpret_cast<const char *>(a.what);
+    for (int o = tid * 128; o < P::M * (int)sizeof(double2); o += P::NT * 128)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(wsp + o));
+    constexpr int per_line = 128 / (int)sizeof(TIN);
+    for (int e = tid * per_line; e < nOut; e += P::NT * per_line) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + i0 + e));
+  }
   double2 v[R];
   fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldw, v);
 #pragma unroll
