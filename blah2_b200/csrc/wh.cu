@@ -677,15 +677,6 @@ __global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, wh_min_ctas<LOG2M, LR>())
     const double2 v = ld_iq(x, xs((uint32_t)ic));
     return (i >= 0 && i < (int64_t)a.N && m < hist + nOut) ? v : zero;
   };
-  // the weight spectrum (M x 16 B, the same for every CTA) and this block's surveillance samples are
-  // needed two FFT passes from now: pull them towards the SM while the forward transform runs
-  {
-    const char *wsp = reinterpret_cast<const char *>(a.what);
-    for (int o = tid * 128; o < P::M * (int)sizeof(double2); o += P::NT * 128)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(wsp + o));
-    constexpr int per_line = 128 / (int)sizeof(TIN);
-    for (int e = tid * per_line; e < nOut; e += P::NT * per_line) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + i0 + e));
-  }
   double2 v[R];
   fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldw, v);
 #pragma unroll
