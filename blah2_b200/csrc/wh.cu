@@ -431,15 +431,17 @@ __device__ __forceinline__ double rcp_newton(double p) {
 struct SolveState { double2 ps_p, invp_sigma, sc_; };
 
 template <int MAXT> __global__ void __launch_bounds__(MAXT, 1) wh_solve_short_kernel(SolveArgs s) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // shared arrays are addressed as sm[offset + i] with the ping-pong offsets derived from the parity of k:
+  // swapping generic POINTERS instead made every path of every step start with an S2R SR_CgaCtaId + LEA
+  // (generic -> shared window conversion) in front of its first load
+  extern __shared__ __align__(16) double2 sm[];
   const int n = s.nBins;
-  double2 *alb0 = reinterpret_cast<double2 *>(smem_raw);  // generator a_i, ping-pong (neighbour shift)
-  double2 *alb1 = alb0 + n;
-  double2 *phb0 = alb1 + n;    // predictor phi_i, ping-pong (mirrored access)
-  double2 *phb1 = phb0 + n;
+  const int ALB0 = 0, ALB1 = n;          // generator a_i, ping-pong (neighbour shift)
+  const int PHB0 = 2 * n, PHB1 = 3 * n;  // predictor phi_i, ping-pong (mirrored access)
   __shared__ double s_t0;
-  __shared__ SolveState St[2];
-  __shared__ double2 Bv[2], Rv[2];  // raw b_k, r_k, double buffered on the parity of k
+  // step scalars live in the dynamic array too (a dynamically indexed STATIC shared array costs an
+  // S2R SR_CgaCtaId + LEA per access path): state of parity q at SC + 3 q, raw b_k / r_k at SC + 6 + q / SC + 8 + q
+  const int SC = 4 * n;
   const int tid = threadIdx.x;
   const int NTS = (n + 31) & ~31;
   const bool scalar_warp = tid >= NTS;
@@ -452,6 +454,21 @@ template <int MAXT> __global__ void __launch_bounds__(MAXT, 1) wh_solve_short_ke
   if (!scalar_warp && i < n) {
     const double2 *src = s.partial + i;
     int p = 0;
+    if (MAXT <= 512) {  // 128 registers available: 16 loads in flight
+      for (; p + 8 <= s.nPartial; p += 8) {
+        double2 va[8], vb[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          va[u] = __ldg(src + (size_t)(p + u) * 2 * n);
+          vb[u] = __ldg(src + ((size_t)(p + u) * 2 + 1) * n);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          sa.x += va[u].x; sa.y += va[u].y;
+          sb.x += vb[u].x; sb.y += vb[u].y;
+        }
+      }
+    }
     for (; p + 4 <= s.nPartial; p += 4) {
       double2 va[4], vb[4];
 #pragma unroll
@@ -483,42 +500,43 @@ template <int MAXT> __global__ void __launch_bounds__(MAXT, 1) wh_solve_short_ke
     al = make_double2(sa.x * inv_t0, -sa.y * inv_t0);  // a_i^(0) = conj(a[i]) / t_0  (p_0 = 1)
     be = i ? al : zero;
     rr = sb;
-    alb0[i] = al;
-    phb0[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // phi^(1) = [1], sigma_0 = 1 / t_0
-    phb1[i] = zero;
+    sm[ALB0 + i] = al;
+    sm[PHB0 + i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // phi^(1) = [1], sigma_0 = 1 / t_0
+    sm[PHB1 + i] = zero;
     if (i == 0) {
-      Rv[0] = rr;
-      St[0].ps_p = make_double2(1.0, 1.0);
-      St[0].invp_sigma = make_double2(1.0, inv_t0);
-      St[0].sc_ = make_double2(1.0, 0.0);
+      sm[SC + 8 + (0)] = rr;
+      sm[SC + 3 * (0)] = make_double2(1.0, 1.0);
+      sm[SC + 3 * (0) + 1] = make_double2(1.0, inv_t0);
+      sm[SC + 3 * (0) + 2] = make_double2(1.0, 0.0);
     }
-    if (i == 1) Bv[0] = be;
+    if (i == 1) sm[SC + 6 + (0)] = be;
   }
   __syncthreads();
-  double2 *ac = alb0, *an = alb1, *pc = phb0, *pn_ = phb1;
   if (ok) {
     for (int k = 0; k < n - 1; k++) {
       const int par = k & 1;
-      const double2 c0 = St[par].ps_p;
+      const double2 *ac = sm + (par ? ALB1 : ALB0), *pc = sm + (par ? PHB1 : PHB0);
+      double2 *an = sm + (par ? ALB0 : ALB1), *pn_ = sm + (par ? PHB0 : PHB1);
+      const double2 c0 = sm[SC + 3 * (par)];
       const double ps = c0.x, p = c0.y;
       if (scalar_warp) {
         // ---- p_{k+1} = s (p^2 - |b|^2) and everything derived from it, for the next step
-        const double2 b = Bv[par];
-        const double sc = St[par].sc_.x, sigma = St[par].invp_sigma.y;
+        const double2 b = sm[SC + 6 + (par)];
+        const double sc = sm[SC + 3 * (par) + 2].x, sigma = sm[SC + 3 * (par) + 1].y;
         const double pnew = ps * p - ((b.x * sc) * b.x + (b.y * sc) * b.y);
         const double inv_pn = rcp_newton(pnew);
         const double scn = pow2_scale(pnew);
         const double sign = sigma * ps * p * inv_pn;  // sigma / (1 - |rho|^2)
         if ((tid & 31) == 0) {
-          St[par ^ 1].ps_p = make_double2(pnew * scn, pnew);
-          St[par ^ 1].invp_sigma = make_double2(inv_pn, sign);
-          St[par ^ 1].sc_ = make_double2(scn, 0.0);
+          sm[SC + 3 * (par ^ 1)] = make_double2(pnew * scn, pnew);
+          sm[SC + 3 * (par ^ 1) + 1] = make_double2(inv_pn, sign);
+          sm[SC + 3 * (par ^ 1) + 2] = make_double2(scn, 0.0);
         }
       } else if (row_lo > k + 2) {
         // ---- warp entirely below the active corner: Schur rows only
         const double2 at = ac[i - 1];
-        const double2 b = Bv[par], r = Rv[par];
-        const double sc = St[par].sc_.x, inv_p = St[par].invp_sigma.x;
+        const double2 b = sm[SC + 6 + (par)], r = sm[SC + 8 + (par)];
+        const double sc = sm[SC + 3 * (par) + 2].x, inv_p = sm[SC + 3 * (par) + 1].x;
         const double2 bs = make_double2(b.x * sc, b.y * sc);
         const double2 q = make_double2(r.x * inv_p, r.y * inv_p);  // r_k / p_k
         if (i < n) {
@@ -538,8 +556,8 @@ template <int MAXT> __global__ void __launch_bounds__(MAXT, 1) wh_solve_short_ke
         //      x_i += (r_k sigma) conj(phi[k-i]);  phi'[i] = phi[i] - rho conj(phi[k+1-i]) (i >= 1), rho = b / p
         const double2 ph_i = pc[i], ph_x = pc[k - i];
         double2 ph_m = pc[k + 1 - (i ? i : 1)];
-        const double2 b = Bv[par], r = Rv[par];
-        const double2 is = St[par].invp_sigma;
+        const double2 b = sm[SC + 6 + (par)], r = sm[SC + 8 + (par)];
+        const double2 is = sm[SC + 3 * (par) + 1];
         const double2 rho = make_double2(b.x * is.x, b.y * is.x);
         const double2 g = make_double2(r.x * is.y, r.y * is.y);
         ph_m = i ? ph_m : zero;
@@ -557,9 +575,9 @@ template <int MAXT> __global__ void __launch_bounds__(MAXT, 1) wh_solve_short_ke
         const double2 ph_i = pc[ic];
         const double2 ph_m = pc[min(max(k + 1 - ic, 0), n - 1)];
         const double2 ph_x = pc[min(max(k - ic, 0), n - 1)];
-        const double2 b = Bv[par], r = Rv[par];
-        const double sc = St[par].sc_.x;
-        const double2 is = St[par].invp_sigma;
+        const double2 b = sm[SC + 6 + (par)], r = sm[SC + 8 + (par)];
+        const double sc = sm[SC + 3 * (par) + 2].x;
+        const double2 is = sm[SC + 3 * (par) + 1];
         const double2 bs = make_double2(b.x * sc, b.y * sc);
         const double2 q = make_double2(r.x * is.x, r.y * is.x);
         const double2 rho = make_double2(b.x * is.x, b.y * is.x);
@@ -574,8 +592,8 @@ template <int MAXT> __global__ void __launch_bounds__(MAXT, 1) wh_solve_short_ke
         nr.x = rr.x - (al.x * q.x - al.y * q.y);
         nr.y = rr.y - (al.x * q.y + al.y * q.x);
         if (isS) an[i] = na;
-        if (i == k + 2 && i < n) Bv[par ^ 1] = nb;  // b_{k+1}
-        if (i == k + 1) Rv[par ^ 1] = nr;           // r_{k+1}
+        if (i == k + 2 && i < n) sm[SC + 6 + (par ^ 1)] = nb;  // b_{k+1}
+        if (i == k + 1) sm[SC + 8 + (par ^ 1)] = nr;           // r_{k+1}
         al = isS ? na : al;
         be = isS ? nb : be;
         rr = isS ? nr : rr;
@@ -593,17 +611,16 @@ template <int MAXT> __global__ void __launch_bounds__(MAXT, 1) wh_solve_short_ke
       }
       if (!(p > 0.0)) { ok = false; break; }  // uniform: every thread read the same published pivot
       __syncthreads();
-      double2 *t = ac; ac = an; an = t;
-      t = pc; pc = pn_; pn_ = t;
     }
   }
   if (ok) {
     const int par = (n - 1) & 1;
-    if (!(St[par].ps_p.y > 0.0)) ok = false;  // the last pivot
+    const double2 *pc = sm + (par ? PHB1 : PHB0);
+    if (!(sm[SC + 3 * (par)].y > 0.0)) ok = false;  // the last pivot
     if (!scalar_warp && i < n) {
       // last innovation: x_i += (r_{n-1} sigma) conj(phi[n-1-i])
-      const double2 r = Rv[par];
-      const double sigma = St[par].invp_sigma.y;
+      const double2 r = sm[SC + 8 + (par)];
+      const double sigma = sm[SC + 3 * (par) + 1].y;
       const double2 g = make_double2(r.x * sigma, r.y * sigma);
       const double2 ph_x = pc[n - 1 - i];
       xx.x += g.x * ph_x.x + g.y * ph_x.y;
@@ -790,8 +807,8 @@ template <int LOG2M, int LR, class TIN> int wh_launch_apply(b200dd_wh *h, const 
 }
 
 int wh_launch_solve(b200dd_wh *h, cudaStream_t st) {
-  const size_t solve_smem = (size_t)h->nBins * 6 * sizeof(double2);
-  const size_t solve_smem_max = (size_t)kMaxBins * 6 * sizeof(double2);  // attribute is per function, not per handle
+  const size_t solve_smem = ((size_t)h->nBins * 6 + 16) * sizeof(double2);
+  const size_t solve_smem_max = ((size_t)kMaxBins * 6 + 16) * sizeof(double2);  // attribute is per function, not per handle
   if (!h->attr_solve) {
     B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
     B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
@@ -803,10 +820,8 @@ int wh_launch_solve(b200dd_wh *h, cudaStream_t st) {
   sa.partial = h->d_partial; sa.nPartial = h->gridCorr; sa.nBins = h->nBins;
   sa.a_out = h->d_a; sa.b_out = h->d_b; sa.w_out = h->d_w; sa.status = h->d_status;
   const int threads = ((h->nBins + 31) / 32) * 32;
-  static const int split_env = [] {
-    const char *e = getenv("B200DD_WH_SOLVE_SHORT");
-    return e ? atoi(e) : 1;
-  }();
+  const char *senv = getenv("B200DD_WH_SOLVE_SHORT");  // read per call: the parity tests toggle it
+  const int split_env = senv ? atoi(senv) : 1;
   if (split_env && threads + 32 <= 1024) {  // includes the reference's configuration (410 taps)
     if (threads + 32 <= 512) wh_solve_short_kernel<512><<<1, threads + 32, solve_smem, st>>>(sa);
     else wh_solve_short_kernel<1024><<<1, threads + 32, solve_smem, st>>>(sa);

@@ -20,7 +20,10 @@ CASES = [
     (65536, 0, 100, 3),         # delayMin = 0
     (200000, -10, 400, 4),      # the reference's default clutter window (config/config.yml:29-32)
     (100000, 2, 60, 5),         # delayMin > 0 (reference's uint32 wrap semantics)
-    (300000, -10, 1200, 6),     # many taps -> longer FFT plan
+    (300000, -10, 1200, 6),     # many taps -> longer FFT plan, generic solve kernel (two rows per thread)
+    (150000, -10, 700, 7),      # 710 taps: short-path solve kernel with the 1024-thread bound
+    (400000, -10, 2030, 8),     # the largest supported system (2040 taps)
+    (4096, 0, 1, 9),            # a single tap
 ]
 
 
@@ -44,7 +47,8 @@ def test_filter_matches_oracle_fp64_host_path(case, relerr):
     e = relerr(y, y_ref)
     assert e[0] < 1e-9 and e[1] < 1e-9, f"filtered surveillance {e}"
     # it must actually cancel clutter (when the tap window covers the direct path at lag 0)
-    if dm <= 0:
+    # (a single tap cannot: the scene's clutter is spread over several lags)
+    if dm <= 0 and dM - dm >= 20:
         assert np.linalg.norm(y) < 0.1 * np.linalg.norm(sc.y)
 
 
@@ -133,3 +137,19 @@ def test_every_fft_plan_gives_the_same_filter(radix, log2m, relerr, monkeypatch)
     assert ok and ok_ref
     e = relerr(y, y_ref)
     assert e[0] < 1e-9 and e[1] < 1e-9, f"radix {radix} M=2^{log2m}: {e}"
+
+
+@pytest.mark.parametrize("case", [(20011, -10, 40, 2), (200000, -10, 400, 4)])
+def test_both_solve_kernels_give_the_same_weights(case, relerr, monkeypatch):
+    """B200DD_WH_SOLVE_SHORT=0 selects the generic one-row-per-thread kernel for small systems too; the
+    short-path kernel (default) runs the same recursion with a Newton reciprocal instead of a division."""
+    n, dm, dM, seed = case
+    sc = _scene(n, seed)
+    ws = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("B200DD_WH_SOLVE_SHORT", mode)
+        wh = WienerHopf(dm, dM, n)
+        ok, _ = wh.process(sc.x, sc.y)
+        assert ok
+        ws[mode] = wh.debug_weights()[0]
+    assert relerr(ws["1"], ws["0"])[0] < 1e-11

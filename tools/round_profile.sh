@@ -5,6 +5,7 @@ O=gpurun_out
 mkdir -p $O
 KF='regex:caf_|wh_|metrics_|cfar_|det_|pl_|scan_|centroid_|compact_|interp_|fft_'
 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 > $O/${TAG}_pytest.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" >> $O/${TAG}_pytest.log 2>&1
 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
 python bench.py --streams 1 --no-cpu-baseline > $O/${TAG}_bench_s1.json 2>> $O/${TAG}_bench.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench.err
