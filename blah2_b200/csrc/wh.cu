@@ -92,6 +92,7 @@ struct CorrArgs {
   uint32_t N;
   XsMap xs;
   int nBins, L, nSegTotal, segPerCta;
+  double2 *xw_out;    // [nSeg][R][NT] spectra of the reference windows, kept for the filter stage (or null)
 };
 
 // forward FFT of M points from a loader, result in registers (position order of fft_core.cuh)
@@ -190,6 +191,13 @@ __global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, 1) wh_corr_kernel(CorrArg
     fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldxp, vxp);
     __syncthreads();
     fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldxw, v);
+    // The window x[sL .. sL+M) is exactly the overlap-save window the FIR stage needs for the outputs
+    // [sL + nBins-1, (s+1)L + nBins-1): keep its spectrum so that stage does not transform x again.
+    if (a.xw_out) {
+      double2 *dst = a.xw_out + (size_t)s * P::M + tid;
+#pragma unroll
+      for (int r = 0; r < R; r++) dst[r * P::NT] = v[r];
+    }
 #pragma unroll
     for (int r = 0; r < R; r++) {
       double2 acc = Za[r * P::NT + tid];
@@ -658,6 +666,7 @@ struct ApplyArgs {
   uint32_t N;
   XsMap xs;
   int nBins, Lout;
+  const double2 *xw;  // window spectra written by the correlation stage (same FFT plan), or null
 };
 
 template <class TOUT> __device__ __forceinline__ void st_iq(TOUT *p, uint32_t i, double2 v);
@@ -677,13 +686,29 @@ __global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, wh_min_ctas<LOG2M, LR>())
   const TIN *__restrict__ x = reinterpret_cast<const TIN *>(a.x);
   const TIN *__restrict__ y = reinterpret_cast<const TIN *>(a.y);
   TIN *__restrict__ yo = reinterpret_cast<TIN *>(a.y_out);
-  const uint32_t i0 = (uint32_t)blockIdx.x * (uint32_t)a.Lout;
-  const int nOut = (int)min((uint32_t)a.Lout, a.N - i0);
+  // Output blocks.  Without kept spectra: block b = [b Lout, (b+1) Lout).  With them the blocks are shifted by
+  // the filter history so that block s+1 owns exactly the outputs of the correlation stage's window s, and
+  // block 0 produces the first nBins-1 outputs (zero history) with a transform of its own.
+  const int hist = a.nBins - 1;
+  const bool kept = a.xw != nullptr && blockIdx.x > 0;
+  uint32_t i0;
+  int nOut;
+  if (a.xw == nullptr) {
+    i0 = (uint32_t)blockIdx.x * (uint32_t)a.Lout;
+    nOut = (int)min((uint32_t)a.Lout, a.N - i0);
+  } else if (blockIdx.x == 0) {
+    i0 = 0;
+    nOut = (int)min((uint32_t)hist, a.N);
+  } else {
+    const uint64_t start = (uint64_t)(blockIdx.x - 1) * (uint64_t)a.Lout + (uint64_t)hist;
+    i0 = (uint32_t)min(start, (uint64_t)a.N);
+    nOut = (int)min((uint32_t)a.Lout, a.N - i0);
+  }
+  if (nOut <= 0) return;
   if (*a.status != 0) {  // failed solve: surveillance channel passes through untouched
     for (int m = tid; m < nOut; m += P::NT) st_iq<TIN>(yo, i0 + m, ld_iq(y, i0 + m));
     return;
   }
-  const int hist = a.nBins - 1;
   const double2 zero = make_double2(0.0, 0.0);
   // window element m <-> shifted-reference index i0 - hist + m (zero history before sample 0);
   // branch-free: load from a clamped valid index, mask afterwards
@@ -695,7 +720,13 @@ __global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, wh_min_ctas<LOG2M, LR>())
     return (i >= 0 && i < (int64_t)a.N && m < hist + nOut) ? v : zero;
   };
   double2 v[R];
-  fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldw, v);
+  if (kept) {
+    const double2 *src = a.xw + (size_t)(blockIdx.x - 1) * P::M + tid;
+#pragma unroll
+    for (int r = 0; r < R; r++) v[r] = src[r * P::NT];
+  } else {
+    fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldw, v);
+  }
 #pragma unroll
   for (int r = 0; r < R; r++) v[r] = cmul(v[r], a.what[R * tid + brev<R>(r)]);
   __syncthreads();
@@ -761,6 +792,7 @@ struct b200dd_wh {
   double2 *d_tw_c = nullptr, *d_tw_a = nullptr, *d_partial = nullptr, *d_a = nullptr, *d_b = nullptr, *d_w = nullptr, *d_what = nullptr;
   int *d_status = nullptr;
   double2 *d_xd = nullptr, *d_yd = nullptr;  // host path staging (complex128)
+  double2 *d_xw = nullptr;                   // [nSeg][M] reference-window spectra kept between the two FFT stages
   int num_sms = 148;
   bool attr_corr_f32 = false, attr_corr_f64 = false, attr_apply_f32 = false, attr_apply_f64 = false, attr_solve = false;
 };
@@ -783,6 +815,7 @@ template <int LOG2M, int LR, class TIN> int wh_launch_corr(b200dd_wh *h, const v
   CorrArgs ca;
   ca.x = x; ca.y = y; ca.partial = h->d_partial; ca.tw = h->d_tw_c; ca.N = h->N; ca.xs = make_xs_map(h->N, h->delayMin);
   ca.nBins = h->nBins; ca.L = h->L; ca.nSegTotal = h->nSeg; ca.segPerCta = h->segPerCta;
+  ca.xw_out = h->d_xw;
   wh_corr_kernel<LOG2M, LR, TIN><<<h->gridCorr, P::NT, corr_smem<LOG2M, LR>(), st>>>(ca);
   B2_LAUNCH_CHECK();
   return B200DD_OK;
@@ -801,7 +834,8 @@ template <int LOG2M, int LR, class TIN> int wh_launch_apply(b200dd_wh *h, const 
   ApplyArgs aa;
   aa.x = x; aa.y = y; aa.y_out = y_out; aa.what = h->d_what; aa.tw = h->d_tw_a; aa.status = h->d_status;
   aa.N = h->N; aa.xs = make_xs_map(h->N, h->delayMin); aa.nBins = h->nBins; aa.Lout = h->Lout;
-  wh_apply_kernel<LOG2M, LR, TIN><<<h->gridApply, P::NT, fft_smem<LOG2M, LR>(), st>>>(aa);
+  aa.xw = h->d_xw;
+  wh_apply_kernel<LOG2M, LR, TIN><<<h->d_xw ? h->nSeg + 1 : h->gridApply, P::NT, fft_smem<LOG2M, LR>(), st>>>(aa);
   B2_LAUNCH_CHECK();
   return B200DD_OK;
 }
@@ -946,6 +980,13 @@ int b200dd_wh_create(int32_t delay_min, int32_t delay_max, uint32_t n_samples, i
     B2_CUDA(cudaMalloc(&h->d_what, sizeof(double2) * M));
     B2_CUDA(cudaMalloc(&h->d_status, sizeof(int)));
     B2_CUDA(cudaMemset(h->d_status, 0, sizeof(int)));
+    // B200DD_WH_REUSE=1 (needs the same FFT plan in both stages): keep the reference-window spectra of the
+    // correlation stage for the filter stage (16 M bytes per segment; skipped above 1 GB).  Measured on B200
+    // it saves 8 us in the filter kernel and costs as much elsewhere (70 MB of extra traffic per CPI through
+    // L2 while four CPIs are in flight: profiles/r01_summary.md), so it is opt-in.
+    const char *re = getenv("B200DD_WH_REUSE");
+    const size_t xw_bytes = sizeof(double2) * (size_t)h->nSeg * (size_t)Mc;
+    if (h->log2m_c == h->log2m_a && re && atoi(re) == 1 && xw_bytes <= ((size_t)1 << 30)) B2_CUDA(cudaMalloc(&h->d_xw, xw_bytes));
     return B200DD_OK;
   };
   int rc = body();
@@ -968,6 +1009,7 @@ void b200dd_wh_destroy(b200dd_wh *h) {
     free_dev(h->d_what);
     free_dev(h->d_status);
     free_dev(h->d_xd);
+    free_dev(h->d_xw);
     free_dev(h->d_yd);
     if (h->stream) cudaStreamDestroy(h->stream);
   }

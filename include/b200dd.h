@@ -35,6 +35,14 @@
  *
  * There is no CPU fallback: every *_process* entry point runs CUDA kernels for sm_100a
  * and fails with B200DD_ERR_CUDA when no usable device is present.
+ *
+ * Environment (all optional; defaults are the measured best on B200, profiles/r01_summary.md):
+ *   B200DD_CAF_LOG2M / B200DD_CAF_PARTS      range-correlation FFT length (2^k) / CTAs per batch
+ *   B200DD_CAF_TMA=1                         stage IQ segments through shared memory with bulk async copies
+ *   B200DD_WH_LOG2M, B200DD_WH_CORR_LOG2M, B200DD_WH_APPLY_LOG2M, B200DD_WH_RADIX   WienerHopf FFT plans
+ *   B200DD_WH_SOLVE_SHORT=0                  generic Toeplitz solve kernel also for <= 992 taps
+ *   B200DD_WH_REUSE=1                        filter stage reuses the correlation stage's window spectra
+ * None of them changes results beyond the rounding of a different FFT factorisation.
  */
 #ifndef B200DD_H
 #define B200DD_H
