@@ -309,7 +309,7 @@ struct DopplerArgs {
   int nParts;
   float2 *out;          // [nDop][nDel] map
   const float2 *chirp;  // exp(-i pi k^2 / nDop), k < nDop
-  const float2 *bhat;   // FFT_M2 of the wrapped conj chirp, digit-reversed position order
+  const float2 *bhat;   // FFT_M2 of the wrapped conj chirp, register-major order [r][tid]
   const float2 *tw;     // exp(-2 pi i j / M2)
   int nDop, nDel;
   int col0, nCols, ldOut;  // column tile [col0, col0 + nCols) of the map; out has row stride ldOut, tile-relative columns
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT) caf_doppler_kernel(DopplerArg
   float2 v[16];
   fwd_last_to_regs<float, LOG2M>(A, tid, v);
 #pragma unroll
-  for (int r = 0; r < 16; r++) v[r] = cmul(v[r], __ldg(a.bhat + 16 * tid + brev<16>(r)));
+  for (int r = 0; r < 16; r++) v[r] = cmul(v[r], __ldg(a.bhat + r * P::NT + tid));
   __syncthreads();
   inv_first_from_regs<float, LOG2M>(A, tid, v);
   __syncthreads();
@@ -382,7 +382,8 @@ __global__ void caf_sum_parts_kernel(const float2 *__restrict__ parts, int nPart
   }
 }
 
-// natural-order input -> digit-reversed POSITION order output (plan-creation helper)
+// natural-order input -> spectrum in REGISTER-MAJOR order out[r][tid] (register r of thread tid as
+// fwd_last_to_regs leaves it): the consumer's 16 loads per thread are coalesced (plan-creation helper)
 template <int LOG2M>
 __global__ void __launch_bounds__(Plan<LOG2M>::NT) fft_forward_kernel(const float2 *in, float2 *out, const float2 *tw) {
   using P = Plan<LOG2M>;
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT) fft_forward_kernel(const floa
   float2 v[16];
   fwd_last_to_regs<float, LOG2M>(A, tid, v);
 #pragma unroll
-  for (int r = 0; r < 16; r++) out[16 * tid + brev<16>(r)] = v[r];
+  for (int r = 0; r < 16; r++) out[r * P::NT + tid] = v[r];
 }
 
 // complex128 -> complex64, optional pre-rotation by exp(+j 2 pi mid i / fs) (Ambiguity.cpp:95-102)

@@ -653,7 +653,9 @@ __global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, 1) wh_wspec_kernel(const 
   double2 v[R];
   fwd_fft_regs<LOG2M, LR>(A, tw, tid, [&](int i) { return i < nBins ? w[i] : make_double2(0.0, 0.0); }, v);
 #pragma unroll
-  for (int r = 0; r < R; r++) what[R * tid + brev<R>(r)] = v[r];
+  // register-major layout [r][tid]: the filter kernel's 16 loads per thread are then coalesced (consecutive
+  // lanes read consecutive 16-byte elements) instead of 32 scattered sectors per instruction (-16 % on K5)
+  for (int r = 0; r < R; r++) what[r * P::NT + tid] = v[r];
 }
 
 struct ApplyArgs {
@@ -728,7 +730,7 @@ __global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, wh_min_ctas<LOG2M, LR>())
     fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldw, v);
   }
 #pragma unroll
-  for (int r = 0; r < R; r++) v[r] = cmul(v[r], a.what[R * tid + brev<R>(r)]);
+  for (int r = 0; r < R; r++) v[r] = cmul(v[r], a.what[r * P::NT + tid]);
   __syncthreads();
   const double scale = 1.0 / (double)P::M;
   // conv[m] valid for m >= hist; output i = i0 + m - hist.  The final inverse pass is written out here so
