@@ -155,19 +155,22 @@ __device__ __forceinline__ StageRange stage_range(const float2 *base, long long 
 }
 
 // resident CTAs per SM the register allocator must leave room for
-template <int LOG2M, bool STAGE> constexpr int range_min_ctas() {
-  constexpr int NT = Plan<LOG2M>::NT;
+template <int LOG2M, bool STAGE, int LR = 4> constexpr int range_min_ctas() {
+  constexpr int NT = Plan<LOG2M, LR>::NT;
   if (STAGE) {  // shared memory (two FFT buffers + two staging buffers) is the limit, not registers
-    constexpr int smem = 2 * Plan<LOG2M>::MP * 8 + 2 * Plan<LOG2M>::M * 8 + 1024;
+    constexpr int smem = 2 * Plan<LOG2M, LR>::MP * 8 + 2 * Plan<LOG2M, LR>::M * 8 + 1024;
     constexpr int by_smem = (227 * 1024) / smem;
     return by_smem < 1 ? 1 : (by_smem > 8 ? 8 : by_smem);
   }
   return NT >= 512 ? 1 : (512 / NT > 16 ? 16 : 512 / NT);  // <= 128 regs/thread
 }
 
-template <int LOG2M, bool STAGE>
-__global__ void __launch_bounds__(Plan<LOG2M>::NT, range_min_ctas<LOG2M, STAGE>()) caf_range_kernel(RangeArgs a) {
-  using P = Plan<LOG2M>;
+// LR = log2 of the base radix: 4 (M/16 threads, three passes at M = 2048) or 3 (M/8 threads: twice the warps
+// per batch for CPIs with too few batches to fill the GPU, at the price of one more pass; B200DD_CAF_RADIX=8)
+template <int LOG2M, bool STAGE, int LR = 4>
+__global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, range_min_ctas<LOG2M, STAGE, LR>()) caf_range_kernel(RangeArgs a) {
+  using P = Plan<LOG2M, LR>;
+  constexpr int R = P::R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2 *A = reinterpret_cast<float2 *>(smem_raw);
   float2 *B = A + P::MP;
@@ -181,9 +184,9 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, range_min_ctas<LOG2M, STAGE>(
   const float2 *__restrict__ yb = a.y + boff;
   const float2 zero = make_float2(0.f, 0.f);
 
-  float2 Z[16];
+  float2 Z[R];
 #pragma unroll
-  for (int r = 0; r < 16; r++) Z[r] = zero;
+  for (int r = 0; r < R; r++) Z[r] = zero;
 
   // blockIdx.y = part: a contiguous group of segments of this batch.  Splitting a batch over
   // several CTAs buys occupancy for small CPIs (257 batches cannot fill 148 SMs); each part ends with
@@ -222,8 +225,8 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, range_min_ctas<LOG2M, STAGE>(
     const int len = min(a.L, a.nCorr - n0);
     const int ylen = len + a.nDel - 1;   // window entries that can reach a wanted lag
     const int yoff = n0 + a.lagMin;
-    auto stA = [&](int i, float2 v) { A[pad(i)] = v; };
-    auto stB = [&](int i, float2 v) { B[pad(i)] = v; };
+    auto stA = [&](int i, float2 v) { A[padr<LR>(i)] = v; };
+    auto stB = [&](int i, float2 v) { B[padr<LR>(i)] = v; };
     StageRange rx, ry;
     if constexpr (STAGE) seg_ranges(seg, rx, ry);
     // loaders: element m of the zero-padded x segment / of the y window masked to the batch
@@ -255,9 +258,9 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, range_min_ctas<LOG2M, STAGE>(
       phase ^= 1;
     }
     if (seg > seg0) __syncthreads();  // previous segment's last pass has finished reading A/B
-    if constexpr (P::R0 == 16) {
-      fft_butterfly<float, 16, -1, LOG2M>(tid, P::log2S(0), a.tw, ldx, stA);
-      fft_butterfly<float, 16, -1, LOG2M>(tid, P::log2S(0), a.tw, ldy, stB);
+    if constexpr (P::R0 == R) {
+      fft_butterfly<float, R, -1, LOG2M>(tid, P::log2S(0), a.tw, ldx, stA);
+      fft_butterfly<float, R, -1, LOG2M>(tid, P::log2S(0), a.tw, ldy, stB);
     } else {
 #pragma unroll 1
       for (int b = tid; b < P::M / P::R0; b += P::NT) {
@@ -271,29 +274,29 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT, range_min_ctas<LOG2M, STAGE>(
     }
 #pragma unroll 1
     for (int p = 1; p < P::NP - 1; p++) {
-      smem_pass<float, LOG2M, -1>(A, a.tw, p, tid);
-      smem_pass<float, LOG2M, -1>(B, a.tw, p, tid);
+      smem_pass<float, LOG2M, -1, LR>(A, a.tw, p, tid);
+      smem_pass<float, LOG2M, -1, LR>(B, a.tw, p, tid);
       __syncthreads();
     }
-    float2 vx[16], vy[16];
-    fwd_last_to_regs<float, LOG2M>(A, tid, vx);
-    fwd_last_to_regs<float, LOG2M>(B, tid, vy);
+    float2 vx[R], vy[R];
+    fwd_last_to_regs<float, LOG2M, LR>(A, tid, vx);
+    fwd_last_to_regs<float, LOG2M, LR>(B, tid, vy);
 #pragma unroll
-    for (int r = 0; r < 16; r++) cfmac(Z[r], vy[r], vx[r]);  // Z += Y conj(X)
+    for (int r = 0; r < R; r++) cfmac(Z[r], vy[r], vx[r]);  // Z += Y conj(X)
   }
 
   __syncthreads();
-  inv_first_from_regs<float, LOG2M>(A, tid, Z);
+  inv_first_from_regs<float, LOG2M, LR>(A, tid, Z);
   __syncthreads();
 #pragma unroll 1
   for (int p = P::NP - 2; p >= 1; p--) {
-    smem_pass<float, LOG2M, +1>(A, a.tw, p, tid);
+    smem_pass<float, LOG2M, +1, LR>(A, a.tw, p, tid);
     __syncthreads();
   }
   // final inverse pass: natural-order lag index m = delay bin; keep m < nDel only
   const float scale = 1.0f / (float)P::M;
   float2 *__restrict__ Rrow = a.R + ((size_t)blockIdx.y * a.nDop + batch) * a.nDel;
-  auto ldA = [&](int i) { return A[pad(i)]; };
+  auto ldA = [&](int i) { return A[padr<LR>(i)]; };
   auto stR = [&](int m, float2 v) {
     if (m < a.nDel) Rrow[m] = make_float2(v.x * scale, v.y * scale);
   };
@@ -445,27 +448,31 @@ __global__ void caf_widen_kernel(const float2 *__restrict__ in, double2 *__restr
 
 // ------------------------------------------------------------------ launch dispatch
 
-template <int LOG2M, bool STAGE> int launch_range_impl(const RangeArgs &a, int nDop, int nParts, cudaStream_t st) {
-  using P = Plan<LOG2M>;
+template <int LOG2M, bool STAGE, int LR = 4> int launch_range_impl(const RangeArgs &a, int nDop, int nParts, cudaStream_t st) {
+  using P = Plan<LOG2M, LR>;
   const size_t smem = 2 * (size_t)P::MP * sizeof(float2) + (STAGE ? 2 * (size_t)P::M * sizeof(float2) : 0);
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    B2_CUDA(cudaFuncSetAttribute(caf_range_kernel<LOG2M, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_CUDA(cudaFuncSetAttribute(caf_range_kernel<LOG2M, STAGE, LR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done[dev & 63] = true;
   }
-  caf_range_kernel<LOG2M, STAGE><<<dim3(nDop, nParts), P::NT, smem, st>>>(a);
+  caf_range_kernel<LOG2M, STAGE, LR><<<dim3(nDop, nParts), P::NT, smem, st>>>(a);
   B2_LAUNCH_CHECK();
   return B200DD_OK;
 }
 
 // TMA staging needs 2 more M-element buffers (fits up to M = 4096).  Measured on B200 it is equal at
 // config 1/2 and 7 % slower at config 3/4 than direct loads (profiles/r01_summary.md), so it is opt-in:
-// B200DD_CAF_TMA=1.
+// B200DD_CAF_TMA=1.  B200DD_CAF_RADIX=8 selects the radix-8 plan (M/8 threads per CTA).
 template <int LOG2M> int launch_range(const RangeArgs &a, int nDop, int nParts, cudaStream_t st) {
   const char *e = getenv("B200DD_CAF_TMA");  // read per call: the parity tests toggle it
   const int env = e ? atoi(e) : 0;
+  const char *r = getenv("B200DD_CAF_RADIX");
+  if constexpr (LOG2M >= 9 && LOG2M <= 12) {
+    if (r && atoi(r) == 8) return launch_range_impl<LOG2M, false, 3>(a, nDop, nParts, st);
+  }
   if constexpr (LOG2M <= 12) {
     if (env == 1) return launch_range_impl<LOG2M, true>(a, nDop, nParts, st);
   }
