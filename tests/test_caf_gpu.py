@@ -105,6 +105,20 @@ def test_every_range_fft_length_gives_the_same_map(log2m, relerr, monkeypatch):
     assert e[0] < TOL and e[1] < TOL, f"log2m={log2m} map {e}"
 
 
+@pytest.mark.parametrize("log2m", [9, 10, 11, 12])
+def test_radix8_range_plan_gives_the_same_map(log2m, relerr, monkeypatch):
+    """B200DD_CAF_RADIX=8: M/8 threads per CTA and one more pass (twice the warps per batch)."""
+    monkeypatch.setenv("B200DD_CAF_LOG2M", str(log2m))
+    monkeypatch.setenv("B200DD_CAF_RADIX", "8")
+    geom = (-5, 60, -200, 200, 100000, 100000, True)
+    x, y = random_iq(geom[5], seed=5)
+    amb, m = _run(geom, x, y)
+    g = O.ambiguity_geometry(*geom)
+    ref, _, _ = O.ambiguity_process(x, y, g)
+    e = relerr(m.data, ref)
+    assert e[0] < TOL and e[1] < TOL, f"radix 8, log2m={log2m} map {e}"
+
+
 @pytest.mark.parametrize("parts", [1, 2, 3, 100])
 def test_batch_split_into_parts_gives_the_same_map(parts, relerr, monkeypatch):
     monkeypatch.setenv("B200DD_CAF_LOG2M", "9")
