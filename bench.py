@@ -10,14 +10,15 @@ CfarDetector1D -> Centroid -> Interpolate on synthetic IQ (blah2_b200/scene.py).
 Contract (one JSON line on rank 0):
   value   IQ Msamples/s, whole job over all N GPUs, inputs resident in HBM (float2), CUDA-event
           timed on the launching stream, max over ranks;  maps_per_s = value / (N_samples/1e6).
-  e2e     same metric through the public host API (Pipeline.process on PINNED complex128 host
-          buffers): H2D of x and y and D2H of the map + detections inside the timed region.
+  e2e     same metric through the public host API (Pipeline.submit_host / fetch = C ABI
+          b200dd_pipeline_submit_host / _fetch, PINNED complex128 host buffers): H2D of x and y and D2H of
+          the map + detections inside the timed region, every step.
   roofline  the CAF range-correlation kernel (the kernel BASELINE.json's metric names), timed live
           with CUDA events around that kernel (b200dd_caf_profile_device), algorithmic bytes per
           launch = 16 N_used + 8 nDop nDel, against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline  the reference's own src/process code (oracle/_ref, unmodified sources + our FFT /
           Armadillo shims) on ONE host thread for ONE CPI of the same workload.
-  --impl reference: the same reference code on all host threads it can use (one CPI per thread).
+  --impl reference: the same reference code, one host process per concurrent CPI (time-bounded).
 Multi-GPU: independent CPIs sharded over ranks ("weak" scaling, no data-path collective); the only
 collective is the final NCCL gather of every rank's last map to rank 0 (inside the timed region).
 """
@@ -116,22 +117,41 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _cpu_chain():
+    """(run(x, y) -> (stage_ms, n_detections), kind): the compiled reference (oracle/_ref) when it was built,
+    else the numpy port of the same algorithm (oracle/blah2_oracle.py)."""
+    from oracle import refpath as R
+    if R.available():
+        ch = R.Chain(GEOM["delayMin"], GEOM["delayMax"], GEOM["dopplerMin"], GEOM["dopplerMax"], FS, N, True, clutter=CLUTTER,
+                     **DET)
+
+        def run(x, y):
+            r = ch.run(x, y, want_map=False)
+            return [float(v) for v in r["stage_ms"]], int(len(r["detections"][0]))
+        return run, "reference"
+    from oracle import blah2_oracle as O
+    g = O.ambiguity_geometry(GEOM["delayMin"], GEOM["delayMax"], GEOM["dopplerMin"], GEOM["dopplerMax"], FS, N, True)
+
+    def run(x, y):
+        t0 = time.perf_counter()
+        r = O.chain(x, y, g, clutter=CLUTTER, det=DET)
+        return [0.0, (time.perf_counter() - t0) * 1e3, 0.0], int(len(r["detections"][0]))
+    return run, "port"
+
+
 def _ref_worker(conn, seed):
     """One host process = one stream of CPIs through the reference's own classes (separate address spaces:
     the reference's per-sample deque traffic makes threads contend on the allocator)."""
     from blah2_b200.scene import make_scene
-    from oracle import refpath as R
 
     sc = make_scene(N, FS, seed=seed)
-    ch = R.Chain(GEOM["delayMin"], GEOM["delayMax"], GEOM["dopplerMin"], GEOM["dopplerMax"], FS, N, True, clutter=CLUTTER,
-                 **DET)
-    conn.send("ready")
+    run, kind = _cpu_chain()
+    conn.send("ready:" + kind)
     while True:
         cmd = conn.recv()
         if cmd == "stop":
             break
-        r = ch.run(sc.x, sc.y, want_map=False)
-        conn.send(list(r["stage_ms"]))
+        conn.send(run(sc.x, sc.y)[0])
 
 
 def run_reference(args, rank, world):
@@ -153,8 +173,11 @@ def run_reference(args, rank, world):
         p = ctx.Process(target=_ref_worker, args=(b, 20260923), daemon=True)
         p.start()
         workers.append((p, a))
+    kind = "reference"
     for _, c in workers:
-        assert c.recv() == "ready"
+        msg = c.recv()
+        assert msg.startswith("ready:")
+        kind = msg.split(":", 1)[1]
 
     def step():
         for _, c in workers:
@@ -187,9 +210,11 @@ def run_reference(args, rank, world):
         "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "step": f"{procs_n} CPIs, one per host process", "steps_requested": requested},
-        "cpu_baseline": {"value": round(value, 4), "unit": "Msamples/s", "cores": procs_n, "kind": "reference",
-                         "sample": f"{cpis} full CPIs ({procs_n} concurrent host processes); unmodified reference src/process "
-                                   "sources linked to this repo's FFTW/Armadillo shims (stock FFTW not in the image)",
+        "cpu_baseline": {"value": round(value, 4), "unit": "Msamples/s", "cores": procs_n, "kind": kind,
+                         "sample": f"{cpis} full CPIs ({procs_n} concurrent host processes); " +
+                                   ("unmodified reference src/process sources linked to this repo's FFTW/Armadillo shims "
+                                    "(stock FFTW not in the image)" if kind == "reference" else
+                                    "numpy port of the reference algorithm (oracle/_ref was not built)"),
                          "stage_ms": {"clutter_filter": round(float(st[0]), 1),
                                       "ambiguity_processing": round(float(st[1]), 1),
                                       "detector": round(float(st[2]), 2)}, "host_cores": cores},
@@ -229,6 +254,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -407,24 +435,18 @@ def main():
                    "maxPower": round(last["maxPower"], 4), "filter_ok": not last["skipped"]},
     }
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import refpath as R
-        if R.available():
-            ch = R.Chain(GEOM["delayMin"], GEOM["delayMax"], GEOM["dopplerMin"], GEOM["dopplerMax"], FS, N, True,
-                         clutter=CLUTTER, **DET)
-            t0 = time.perf_counter()
-            rr = ch.run(sc.x, sc.y, want_map=False)
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": round(N / dt / 1e6, 4), "unit": "Msamples/s", "cores": 1, "kind": "reference",
-                                    "sample": "1 full CPI of the same workload on 1 host thread (reference src/process "
-                                              "sources unmodified + this repo's FFTW/Armadillo shims)",
-                                    "stage_ms": {"clutter_filter": round(float(rr["stage_ms"][0]), 1),
-                                                 "ambiguity_processing": round(float(rr["stage_ms"][1]), 1),
-                                                 "detector": round(float(rr["stage_ms"][2]), 2)},
-                                    "host_cores": os.cpu_count(),
-                                    "n_detections": int(len(rr["detections"][0]))}
-        else:
-            line["cpu_baseline"] = {"value": None, "unit": "Msamples/s", "cores": 0, "kind": "reference",
-                                    "sample": "oracle/_ref/libblah2ref.so missing"}
+        run, kind = _cpu_chain()
+        t0 = time.perf_counter()
+        stage_ms, n_det = run(sc.x, sc.y)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": round(N / dt / 1e6, 4), "unit": "Msamples/s", "cores": 1, "kind": kind,
+                                "sample": "1 full CPI of the same workload on 1 host thread (" +
+                                          ("reference src/process sources unmodified + this repo's FFTW/Armadillo shims"
+                                           if kind == "reference" else "numpy port, oracle/_ref was not built") + ")",
+                                "stage_ms": {"clutter_filter": round(stage_ms[0], 1),
+                                             "ambiguity_processing": round(stage_ms[1], 1),
+                                             "detector": round(stage_ms[2], 2)},
+                                "host_cores": os.cpu_count(), "n_detections": n_det}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
