@@ -390,12 +390,36 @@ def main():
                 prof["wh_corr"].append(c); prof["wh_solve"].append(s_); prof["wh_apply"].append(a_)
     kms = {k: float(np.mean(v)) for k, v in prof.items()}
 
+    # ---- SpectrumAnalyser(n, 2000) (blah2.cpp:198,263-265) on the resident reference channel: not part of the
+    # step above (BASELINE's configs do not include it); its folding pass is the path's purely HBM-bound kernel ----
+    spectrum = None
+    if rank == 0:
+        from blah2_b200.process import SpectrumAnalyser
+        spectrum = {"api": "SpectrumAnalyser(n, 2000.0).process_device(float2 x)", "kernel": "spec_fold_kernel",
+                    "algorithmic_bytes": "8 nfft (x read once)"}
+        big = [torch.randn(20_000_000, dtype=torch.complex64, device="cuda") for _ in range(2)]
+        for label, n_, bufs in (("n2e6", N, xs), ("n2e7", 20_000_000, big)):
+            sa = SpectrumAnalyser(n_, 2000.0, device=local_rank)
+            f_, r_ = [], []
+            with torch.cuda.stream(stream):
+                for i in range(3 + 20):
+                    a_, b_ = sa.profile_device(bufs[i % len(bufs)], st)
+                    if i >= 3:
+                        f_.append(a_); r_.append(b_)
+            fm, rm = float(np.mean(f_)), float(np.mean(r_))
+            spectrum[label] = {"n_spectrum": sa.nSpectrum, "decimation": sa.decimation, "fold_ms": round(fm, 5),
+                               "reduce_dft_ms": round(rm, 5), "achieved_gbs": round(8 * sa.nfft / (fm * 1e-3) / 1e9, 1)}
+            sa.close()
+        del big
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     peak, peak_src = measured_peaks()
+    for label in ("n2e6", "n2e7"):
+        spectrum[label]["frac"] = round(spectrum[label]["achieved_gbs"] / peak, 4)
     bytes_range = 16 * g.n_used + 8 * cells                 # x, y read once; range matrix written once
     bytes_caf = 16 * g.n_used + 8 * cells                   # SURVEY s8(d) B_caf (map written; R stays in L2)
     bytes_step = 2 * 16 * N + 8 * N + 8 * cells             # two compulsory passes over x,y + y' + map
@@ -431,6 +455,7 @@ def main():
                      "step": {"algorithmic_bytes": bytes_step,
                               "frac": round(bytes_step / (ms_total / args.steps * 1e-3) / 1e9 / peak, 4)}},
         "kernel_ms": {k: round(v, 5) for k, v in kms.items()},
+        "spectrum": spectrum,
         "result": {"n_detections": int(last["detections"].get_nDetections()), "noisePower": round(last["noisePower"], 4),
                    "maxPower": round(last["maxPower"], 4), "filter_ok": not last["skipped"]},
     }

@@ -57,6 +57,11 @@ class PipelineParams(C.Structure):
                 ("clutter_delay_max", C.c_int32), ("detection_enable", C.c_int32), ("det", DetParams)]
 
 
+class SpectrumGeometry(C.Structure):
+    _fields_ = [("decimation", C.c_uint32), ("n_spectrum", C.c_uint32), ("nfft", C.c_uint32),
+                ("n_frequency", C.c_uint32), ("fold_chunks", C.c_uint32), ("fold_rows_per_chunk", C.c_uint32)]
+
+
 class CpiResult(C.Structure):
     _fields_ = [("filter_status", C.c_int32), ("n_detections", C.c_uint32), ("noise_power", C.c_double),
                 ("max_power", C.c_double)]
@@ -107,6 +112,17 @@ SIGNATURES = [
                                            C.POINTER(C.c_uint32)]),
     ("b200dd_det_interpolate_host", C.c_int, [_VP, _VP, _VP, _VP, C.c_uint32, _VP, C.c_uint32, C.c_uint32, _VP, _VP,
                                               C.c_double, _VP, _VP, _VP, C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("b200dd_spectrum_create", C.c_int, [C.c_uint32, C.c_double, C.c_int32, C.POINTER(_VP)]),
+    ("b200dd_spectrum_destroy", None, [_VP]),
+    ("b200dd_spectrum_get_geometry", C.c_int, [_VP, C.POINTER(SpectrumGeometry)]),
+    ("b200dd_spectrum_get_frequency", C.c_int, [_VP, _VP, C.c_uint32]),
+    ("b200dd_spectrum_process_host", C.c_int, [_VP, _VP, C.c_uint32, _VP]),
+    ("b200dd_spectrum_process_device", C.c_int, [_VP, _VP, C.c_uint32, _VP, _VP]),
+    ("b200dd_spectrum_process_device_f64", C.c_int, [_VP, _VP, C.c_uint32, _VP, _VP]),
+    ("b200dd_spectrum_fetch", C.c_int, [_VP, _VP, _VP]),
+    ("b200dd_spectrum_profile_device", C.c_int, [_VP, _VP, C.c_uint32, _VP, C.POINTER(C.c_float),
+                                                 C.POINTER(C.c_float)]),
+    ("b200dd_spectrum_stream", _VP, [_VP]),
     ("b200dd_pipeline_create", C.c_int, [C.POINTER(PipelineParams), C.POINTER(_VP)]),
     ("b200dd_pipeline_destroy", None, [_VP]),
     ("b200dd_pipeline_get_geometry", C.c_int, [_VP, C.POINTER(CafGeometry)]),
@@ -118,6 +134,8 @@ SIGNATURES = [
     ("b200dd_pipeline_submit_device", C.c_int, [_VP, _VP, _VP, C.c_uint32, _VP, _VP]),
     ("b200dd_pipeline_fetch", C.c_int, [_VP, C.POINTER(CpiResult), _VP, _VP, _VP, C.c_uint32, _VP]),
     ("b200dd_pipeline_stream", _VP, [_VP]),
+    ("b200dd_pipeline_enable_spectrum", C.c_int, [_VP, C.c_double, C.POINTER(C.c_uint32)]),
+    ("b200dd_pipeline_fetch_spectrum", C.c_int, [_VP, _VP, C.c_uint32]),
 ]
 
 _lib = None

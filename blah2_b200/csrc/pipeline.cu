@@ -51,6 +51,8 @@ struct b200dd_pipeline {
   b200dd_caf *caf = nullptr;
   b200dd_wh *wh = nullptr;
   b200dd_det *det = nullptr;
+  b200dd_spectrum *spec = nullptr;  // optional first stage (blah2.cpp:263-265)
+  uint32_t spec_bins = 0, spec_nfft = 0;
   b200dd_caf_geometry g;
   std::vector<int32_t> delay;
   std::vector<double> doppler;
@@ -113,6 +115,7 @@ void b200dd_pipeline_destroy(b200dd_pipeline *h) {
     b200dd_caf_destroy(h->caf);
     b200dd_wh_destroy(h->wh);
     b200dd_det_destroy(h->det);
+    b200dd_spectrum_destroy(h->spec);
     free_dev(h->d_yf);
     free_dev(h->d_xd);
     free_dev(h->d_yd);
@@ -147,6 +150,11 @@ int b200dd_pipeline_submit_device(b200dd_pipeline *h, const void *d_x, const voi
   void *st = stream ? stream : (void *)h->stream;
   const void *y = d_y;
   int rc;
+  if (h->spec) {  // spectrumAnalyser->process(x), blah2.cpp:264, before the filter touches anything
+    if (n < h->spec_nfft) return arg_fail("b200dd_pipeline_submit_device: the spectrum stage needs nfft samples");
+    rc = b200dd_spectrum_process_device(h->spec, d_x, n, nullptr, st);
+    if (rc != B200DD_OK) return rc;
+  }
   if (h->wh) {
     rc = b200dd_wh_process_device(h->wh, d_x, d_y, h->d_yf, st);  // failed solve -> y passes through
     if (rc != B200DD_OK) return rc;
@@ -209,9 +217,18 @@ int b200dd_pipeline_submit_host(b200dd_pipeline *h, const double *x, const doubl
     }
     if (!h->d_mapd) B2_CUDA(cudaMalloc(&h->d_mapd, sizeof(double2) * (size_t)h->g.n_doppler_bins * h->g.n_delay_bins));
   }
-  B2_CUDA(cudaMemcpyAsync(h->d_xd, x, sizeof(double2) * need, cudaMemcpyHostToDevice, st));
+  uint32_t need_x = need;
+  if (h->spec && h->spec_nfft > need_x) {  // the spectrum reads nfft <= n_samples samples of x (SpectrumAnalyser.cpp:36-39)
+    if (n < h->spec_nfft) return arg_fail("b200dd_pipeline_submit_host: the spectrum stage needs nfft samples");
+    need_x = h->spec_nfft;
+  }
+  B2_CUDA(cudaMemcpyAsync(h->d_xd, x, sizeof(double2) * need_x, cudaMemcpyHostToDevice, st));
   B2_CUDA(cudaMemcpyAsync(h->d_yd, y, sizeof(double2) * need, cudaMemcpyHostToDevice, st));
   int rc;
+  if (h->spec) {  // on the caller's doubles, unrounded
+    rc = b200dd_spectrum_process_device_f64(h->spec, h->d_xd, need_x, nullptr, st);
+    if (rc != B200DD_OK) return rc;
+  }
   if (h->wh) {
     // the filter sees the caller's complex128 samples unrounded (FP64 kernels, in place)
     rc = b200dd_wh_process_device_f64(h->wh, h->d_xd, h->d_yd, h->d_yd, st);
@@ -241,8 +258,12 @@ int b200dd_pipeline_submit_host(b200dd_pipeline *h, const double *x, const doubl
 int b200dd_pipeline_submit_host_rspduo(b200dd_pipeline *h, const int16_t *iq, uint32_t n, double *map_out) {
   if (!h || !iq) return arg_fail("b200dd_pipeline_submit_host_rspduo: null argument");
   const uint32_t N = h->p.caf.n_samples;
-  const uint32_t need = h->wh ? N : h->g.n_used;
+  uint32_t need = h->wh ? N : h->g.n_used;
   if (h->wh ? (n != N) : (n < need)) return arg_fail("b200dd_pipeline_submit_host_rspduo: wrong number of samples");
+  if (h->spec && h->spec_nfft > need) {
+    if (n < h->spec_nfft) return arg_fail("b200dd_pipeline_submit_host_rspduo: the spectrum stage needs nfft samples");
+    need = h->spec_nfft;  // <= n_samples; the CAF still consumes n_used of them
+  }
   DeviceGuard guard(h->device);
   cudaStream_t st = h->stream;
   if (!h->d_iq16) {
@@ -267,6 +288,30 @@ int b200dd_pipeline_submit_host_rspduo(b200dd_pipeline *h, const int16_t *iq, ui
     B2_CUDA(cudaMemcpyAsync(map_out, h->d_mapd, sizeof(double2) * cells, cudaMemcpyDeviceToHost, st));
   }
   return B200DD_OK;
+}
+
+int b200dd_pipeline_enable_spectrum(b200dd_pipeline *h, double bandwidth, uint32_t *n_spectrum) {
+  if (!h) return arg_fail("b200dd_pipeline_enable_spectrum: null handle");
+  DeviceGuard guard(h->device);
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  b200dd_spectrum_destroy(h->spec);
+  h->spec = nullptr;
+  h->spec_bins = h->spec_nfft = 0;
+  const int rc = b200dd_spectrum_create(h->p.caf.n_samples, bandwidth, h->device, &h->spec);
+  if (rc != B200DD_OK) return rc;
+  b200dd_spectrum_geometry sg;
+  b200dd_spectrum_get_geometry(h->spec, &sg);
+  h->spec_bins = sg.n_spectrum;
+  h->spec_nfft = sg.nfft;
+  if (n_spectrum) *n_spectrum = sg.n_spectrum;
+  return B200DD_OK;
+}
+
+int b200dd_pipeline_fetch_spectrum(b200dd_pipeline *h, double *spectrum_out, uint32_t cap) {
+  if (!h || !spectrum_out) return arg_fail("b200dd_pipeline_fetch_spectrum: null argument");
+  if (!h->spec) return arg_fail("b200dd_pipeline_fetch_spectrum: the spectrum stage is not enabled");
+  if (cap < h->spec_bins) return arg_fail("b200dd_pipeline_fetch_spectrum: capacity too small");
+  return b200dd_spectrum_fetch(h->spec, spectrum_out, h->stream);
 }
 
 int b200dd_pipeline_process_host(b200dd_pipeline *h, const double *x, const double *y, uint32_t n, double *map_out,

@@ -215,6 +215,64 @@ class WienerHopf:
             pass
 
 
+class SpectrumAnalyser:
+    """SpectrumAnalyser(n, bandwidth) -- src/process/spectrum/SpectrumAnalyser.h:48.
+
+    ``process(x)`` returns ``(spectrum, frequency)``: the two vectors the reference hands to
+    ``IqData::update_spectrum`` / ``update_frequency`` (SpectrumAnalyser.cpp:55,68)."""
+
+    def __init__(self, n, bandwidth, device=-1):
+        lib = capi.load()
+        h = C.c_void_p()
+        capi.check(lib.b200dd_spectrum_create(int(n), float(bandwidth), int(device), C.byref(h)))
+        self._lib, self._h = lib, h
+        g = capi.SpectrumGeometry()
+        capi.check(lib.b200dd_spectrum_get_geometry(h, C.byref(g)))
+        self.geometry = g
+        self.decimation, self.nSpectrum, self.nfft = int(g.decimation), int(g.n_spectrum), int(g.nfft)
+        self.frequency = np.empty(int(g.n_frequency), dtype=np.float64)
+        capi.check(lib.b200dd_spectrum_get_frequency(h, capi.ptr(self.frequency), int(g.n_frequency)))
+
+    def process(self, x):
+        """Host path: complex array with >= nfft samples (read, not consumed)."""
+        x = _c128(x)
+        out = np.empty(self.nSpectrum, dtype=np.complex128)
+        capi.check(self._lib.b200dd_spectrum_process_host(self._h, capi.ptr(x), x.shape[0], capi.ptr(out)))
+        return out, self.frequency.copy()
+
+    def process_device(self, d_x, d_spectrum=None, stream=None):
+        """Device path: torch complex64 (or complex128) CUDA tensor.  Asynchronous; pair with fetch()
+        when d_spectrum is None."""
+        n = d_x.numel()
+        f64 = getattr(d_x, "element_size", lambda: 8)() == 16
+        fn = self._lib.b200dd_spectrum_process_device_f64 if f64 else self._lib.b200dd_spectrum_process_device
+        capi.check(fn(self._h, capi.ptr(d_x), int(n), capi.ptr(d_spectrum), capi.ptr(stream) if stream else None))
+
+    def fetch(self, stream=None):
+        out = np.empty(self.nSpectrum, dtype=np.complex128)
+        capi.check(self._lib.b200dd_spectrum_fetch(self._h, capi.ptr(out), capi.ptr(stream) if stream else None))
+        return out
+
+    def profile_device(self, d_x, stream=None):
+        """(ms_fold, ms_rest): CUDA-event durations of the folding pass and of reduction + DFT."""
+        a, b = C.c_float(), C.c_float()
+        capi.check(self._lib.b200dd_spectrum_profile_device(self._h, capi.ptr(d_x), int(d_x.numel()),
+                                                            capi.ptr(stream) if stream else None, C.byref(a),
+                                                            C.byref(b)))
+        return a.value, b.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200dd_spectrum_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class _DetHandle:
     """One b200dd_det handle shared by the three detection classes of a pipeline."""
 
@@ -357,7 +415,7 @@ class Pipeline:
     intermediates resident on the device.  Parameters are named like config/config.yml."""
 
     def __init__(self, delayMin, delayMax, dopplerMin, dopplerMax, fs, nSamples, roundHamming=True, clutter=None,
-                 detection=None, device=-1, max_detections=4096):
+                 detection=None, device=-1, max_detections=4096, spectrum_bandwidth=None):
         lib = capi.load()
         p = capi.PipelineParams()
         p.caf = capi.CafParams(int(delayMin), int(delayMax), int(dopplerMin), int(dopplerMax), int(fs),
@@ -383,6 +441,17 @@ class Pipeline:
         self.cap = int(max_detections)
         self._od, self._of, self._os = (np.empty(self.cap, dtype=np.float64) for _ in range(3))
         self.n_samples = int(nSamples)
+        self.n_spectrum = 0
+        if spectrum_bandwidth is not None:  # spectrumAnalyser->process(x), blah2.cpp:263-265
+            ns = C.c_uint32()
+            capi.check(lib.b200dd_pipeline_enable_spectrum(h, float(spectrum_bandwidth), C.byref(ns)))
+            self.n_spectrum = int(ns.value)
+
+    def fetch_spectrum(self):
+        """Spectrum of the reference channel of the last submitted CPI (complex128, nSpectrum bins)."""
+        out = np.empty(self.n_spectrum, dtype=np.complex128)
+        capi.check(self._lib.b200dd_pipeline_fetch_spectrum(self._h, capi.ptr(out), self.n_spectrum))
+        return out
 
     def _result(self, res, want_map_arr=None):
         k = min(res.n_detections, self.cap)

@@ -16,6 +16,8 @@
  *                    Map::set_metrics
  *                    src/process/detection/CfarDetector1D.h:46-55, Centroid.h:35-44,
  *                    Interpolate.h:36-45, src/data/Map.cpp:188-206
+ *   b200dd_spectrum_*   SpectrumAnalyser::SpectrumAnalyser / SpectrumAnalyser::process
+ *                    src/process/spectrum/SpectrumAnalyser.h:48-57, SpectrumAnalyser.cpp:9-74
  *   b200dd_next_hamming   next_hamming, src/process/meta/HammingNumber.h:36
  *
  * Data conventions
@@ -254,6 +256,55 @@ B200DD_API int b200dd_det_interpolate_host(b200dd_det *h, const double *delay, c
                                 const double *mdoppler, double noise_power, double *o_delay, double *o_doppler,
                                 double *o_snr, uint32_t cap, uint32_t *n_out);
 
+/* ------------------------------------------------------------------ SpectrumAnalyser
+ *
+ * SpectrumAnalyser(n, bandwidth) / SpectrumAnalyser::process(IqData *x)
+ * (src/process/spectrum/SpectrumAnalyser.h:48-57, SpectrumAnalyser.cpp:9-74): the stage of the reference's
+ * process thread that runs on the reference channel right before the clutter filter (src/blah2.cpp:263-265).
+ * decimation = n / bandwidth, nSpectrum = n / decimation, nfft = nSpectrum * decimation (:15-17); the result is
+ * every decimation-th bin of the fft-shifted nfft-point spectrum of the first nfft samples (:36-54), which the
+ * reference stores with IqData::update_spectrum (:55).  The device kernels never form the nfft-point transform:
+ * one HBM-bound folding pass over x and an nSpectrum-point DFT (blah2_b200/csrc/spectrum.cu). */
+typedef struct b200dd_spectrum b200dd_spectrum;
+
+typedef struct {
+  uint32_t decimation;   /* SpectrumAnalyser.cpp:15 */
+  uint32_t n_spectrum;   /* :16, number of complex bins process() produces */
+  uint32_t nfft;         /* :17, samples of x consumed (read, not popped) */
+  uint32_t n_frequency;  /* entries of the frequency vector the reference's loop (:57-67) produces: its uint32_t
+                            counter starts at (2^32 - nSpectrum) / 2, so this is 0 for every realistic size */
+  /* implementation facts */
+  uint32_t fold_chunks;          /* row chunks of the folding pass (partial sums reduced in a fixed order) */
+  uint32_t fold_rows_per_chunk;
+} b200dd_spectrum_geometry;
+
+/* Returns B200DD_ERR_GEOMETRY where the reference is undefined (bandwidth <= 0, NaN, or bandwidth > n, which
+ * divides by zero at :16) or for more than 65536 spectrum bins. */
+B200DD_API int b200dd_spectrum_create(uint32_t n, double bandwidth, int32_t device, b200dd_spectrum **out);
+B200DD_API void b200dd_spectrum_destroy(b200dd_spectrum *h);
+B200DD_API int b200dd_spectrum_get_geometry(const b200dd_spectrum *h, b200dd_spectrum_geometry *out);
+/* The vector SpectrumAnalyser::process hands to IqData::update_frequency (n_frequency doubles, kHz). */
+B200DD_API int b200dd_spectrum_get_frequency(const b200dd_spectrum *h, double *frequency, uint32_t cap);
+
+/* SpectrumAnalyser::process on a HOST buffer: x = n >= nfft interleaved complex128 samples (only the first nfft
+ * are read); spectrum_out = n_spectrum complex128.  Synchronous. */
+B200DD_API int b200dd_spectrum_process_host(b200dd_spectrum *h, const double *x, uint32_t n, double *spectrum_out);
+/* Device-resident variants: d_x = float2[n] (or double2[n] for _f64) in device memory; d_spectrum =
+ * double2[n_spectrum] in device memory, or NULL to use the handle's own buffer (read with b200dd_spectrum_fetch).
+ * Asynchronous on `stream` (NULL = the handle's stream). */
+B200DD_API int b200dd_spectrum_process_device(b200dd_spectrum *h, const void *d_x, uint32_t n, void *d_spectrum,
+                                              void *stream);
+B200DD_API int b200dd_spectrum_process_device_f64(b200dd_spectrum *h, const void *d_x, uint32_t n, void *d_spectrum,
+                                                  void *stream);
+/* Copies the handle's buffer (result of the last process_device call with d_spectrum == NULL) to the host and
+ * synchronises the stream. */
+B200DD_API int b200dd_spectrum_fetch(b200dd_spectrum *h, double *spectrum_out, void *stream);
+/* Profiling aid: CUDA-event durations (ms) of the folding pass (the HBM-streaming kernel) and of the rest
+ * (reduction + nSpectrum-point DFT).  Synchronises the stream. */
+B200DD_API int b200dd_spectrum_profile_device(b200dd_spectrum *h, const void *d_x, uint32_t n, void *stream,
+                                              float *ms_fold, float *ms_rest);
+B200DD_API void *b200dd_spectrum_stream(b200dd_spectrum *h);
+
 /* ------------------------------------------------------------------ whole CPI pipeline
  *
  * One coherent-processing interval through the body of the reference's process thread
@@ -313,6 +364,14 @@ B200DD_API int b200dd_pipeline_submit_device(b200dd_pipeline *h, const void *d_x
 B200DD_API int b200dd_pipeline_fetch(b200dd_pipeline *h, b200dd_cpi_result *result, double *o_delay,
                                      double *o_doppler, double *o_snr, uint32_t cap, void *stream);
 B200DD_API void *b200dd_pipeline_stream(b200dd_pipeline *h);
+
+/* Optional first stage of the process thread (src/blah2.cpp:263-265): SpectrumAnalyser(n_samples, bandwidth) on
+ * the reference channel of every CPI submitted afterwards, evaluated on the samples already resident on the
+ * device (no extra transfer).  *n_spectrum (nullable) receives the number of bins.  The spectrum of the last
+ * submitted CPI is read with b200dd_pipeline_fetch_spectrum (call it after b200dd_pipeline_fetch, or it
+ * synchronises the pipeline's stream itself). */
+B200DD_API int b200dd_pipeline_enable_spectrum(b200dd_pipeline *h, double bandwidth, uint32_t *n_spectrum);
+B200DD_API int b200dd_pipeline_fetch_spectrum(b200dd_pipeline *h, double *spectrum_out, uint32_t cap);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,42 @@ def next_hamming(value: int) -> int:
 
 
 # --------------------------------------------------------------------------------------
+# SpectrumAnalyser  (src/process/spectrum/SpectrumAnalyser.cpp:9-74)
+# --------------------------------------------------------------------------------------
+def spectrum_geometry(n: int, bandwidth: float):
+    """(decimation, nSpectrum, nfft) as the constructor computes them (SpectrumAnalyser.cpp:15-17):
+    ``decimation = n/bandwidth`` is a double division truncated into a uint32_t member, the other
+    two are uint32_t integer arithmetic."""
+    decimation = int(float(n) / float(bandwidth)) & 0xFFFFFFFF
+    nSpectrum = (n // decimation) & 0xFFFFFFFF
+    nfft = (nSpectrum * decimation) & 0xFFFFFFFF
+    return decimation, nSpectrum, nfft
+
+
+def spectrum_frequency(n: int, bandwidth: float) -> np.ndarray:
+    """The vector handed to IqData::update_frequency (SpectrumAnalyser.cpp:57-67).  The loop counter
+    ``i`` is a uint32_t (:34), so ``i = -nSpectrum/2`` is (2^32 - nSpectrum) / 2 and ``i < nSpectrum/2``
+    is false at once for every nSpectrum < 2^31: the reference publishes an EMPTY frequency vector
+    (confirmed on the compiled reference, tests/golden/spectrum_*.npz).  Restated literally."""
+    decimation, nSpectrum, _ = spectrum_geometry(n, bandwidth)
+    offset = bandwidth / 2 if decimation % 2 == 0 else 0.0
+    start = ((-nSpectrum) & 0xFFFFFFFF) // 2
+    stop = nSpectrum // 2
+    i = np.arange(start, stop, dtype=np.float64) if start < stop else np.zeros(0)
+    return ((i * bandwidth) + offset + 204640000) / 1000
+
+
+def spectrum_process(x: np.ndarray, n: int, bandwidth: float):
+    """SpectrumAnalyser::process (SpectrumAnalyser.cpp:31-74): nfft-point forward DFT of the first nfft
+    samples (:36-40), ``fftshift[i] = X[(i + int(nfft/2) + 1) % nfft]`` (:43-47), every decimation-th
+    entry kept (:50-54).  Returns (spectrum, frequency); x is read, not consumed (get_data copies, :35)."""
+    decimation, nSpectrum, nfft = spectrum_geometry(n, bandwidth)
+    X = np.fft.fft(np.asarray(x, dtype=np.complex128)[:nfft])
+    i = np.arange(0, nfft, decimation, dtype=np.int64)
+    return X[(i + nfft // 2 + 1) % nfft], spectrum_frequency(n, bandwidth)
+
+
+# --------------------------------------------------------------------------------------
 # Ambiguity constructor  (src/process/ambiguity/Ambiguity.cpp:11-82)
 # --------------------------------------------------------------------------------------
 @dataclass

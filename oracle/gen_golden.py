@@ -81,6 +81,14 @@ def main():
                         map=r["map"], delay=ra["delay"], doppler=ra["doppler"],
                         metrics=np.array([r["noisePower"], r["maxPower"]]),
                         cfar=np.array(d1), centroid=np.array(d2), interp=np.array(d3))
+    # 6. SpectrumAnalyser::process (blah2.cpp:263-265).  bandwidth 2000 is what blah2.cpp:198 hard-codes; the
+    #    other cases exercise nfft < n, odd decimation, decimation 1 and a non-integer bandwidth.
+    for name, (n, bw, seed) in [("spectrum_a", (6000, 2000.0, 1)), ("spectrum_b", (5003, 97.0, 2)),
+                                ("spectrum_c", (3999, 2000.0, 3)), ("spectrum_d", (20000, 333.3, 4))]:
+        x, _ = random_iq(n, seed)
+        spec, freq, left = R.spectrum_process(x, n, bw)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), params=np.array([n, bw, seed], dtype=np.float64),
+                            spectrum=spec, frequency=freq, leftover=left)
     print("golden fixtures written to", OUT, g)
 
 

@@ -42,6 +42,9 @@ def lib():
         _lib.refpath_centroid.restype = C.c_uint32
         _lib.refpath_interpolate.restype = C.c_uint32
         _lib.refpath_last_error.restype = C.c_char_p
+        _lib.refpath_spectrum_process.restype = C.c_int
+        _lib.refpath_spectrum_process.argtypes = [C.c_uint32, C.c_double, C.c_void_p, C.c_uint32, C.c_void_p,
+                                                  C.c_void_p, C.c_uint32, C.c_void_p]
     return _lib
 
 
@@ -98,6 +101,19 @@ def wienerhopf_process(x, y, delayMin, delayMax):
     ok = _check(lib().refpath_wienerhopf_process(C.c_int32(delayMin), C.c_int32(delayMax), C.c_uint32(x.shape[0]),
                                                  _p(x), _p(y)))
     return bool(ok), y
+
+
+def spectrum_process(x, n, bandwidth, cap=1 << 17):
+    """The reference's SpectrumAnalyser(n, bandwidth).process on an IqData holding all of x:
+    (spectrum, frequency, samples left in x)."""
+    x = _c128(x)
+    spec = np.empty(cap, dtype=np.complex128)
+    freq = np.empty(cap, dtype=np.float64)
+    counts = np.zeros(3, dtype=np.uint32)
+    _check(lib().refpath_spectrum_process(C.c_uint32(int(n)), C.c_double(float(bandwidth)), _p(x), x.shape[0],
+                                          _p(spec), _p(freq), cap, _p(counts)))
+    assert counts[0] <= cap and counts[1] <= cap
+    return spec[:counts[0]].copy(), freq[:counts[1]].copy(), int(counts[2])
 
 
 def set_metrics(m):

@@ -180,3 +180,35 @@ def test_live_wienerhopf_positive_delay_min_uint32_wrap(relerr):
     assert ok_r == ok_o
     if ok_r:
         assert relerr(y_o, y_r)[0] < 1e-10
+
+
+# ---- SpectrumAnalyser (src/process/spectrum/SpectrumAnalyser.cpp) ----------------------
+def test_spectrum_geometry_like_blah2_cpp():
+    # blah2.cpp:198-199: SpectrumAnalyser(nSamples, 2000) -> SpectrumAnalyser.cpp:15-17
+    assert O.spectrum_geometry(2000000, 2000.0) == (1000, 2000, 2000000)
+    assert O.spectrum_geometry(20000000, 2000.0) == (10000, 2000, 20000000)
+    assert O.spectrum_geometry(5003, 97.0) == (51, 98, 4998)       # nfft < n
+    assert O.spectrum_geometry(3999, 2000.0) == (1, 3999, 3999)    # decimation 1
+
+
+@pytest.mark.parametrize("name", ["spectrum_a", "spectrum_b", "spectrum_c", "spectrum_d"])
+def test_golden_spectrum(name, relerr):
+    d = gold(name)
+    n, bw, seed = int(d["params"][0]), float(d["params"][1]), int(d["params"][2])
+    x, _ = random_iq(n, seed)
+    spec, freq = O.spectrum_process(x, n, bw)
+    assert spec.shape == d["spectrum"].shape
+    assert relerr(spec, d["spectrum"])[0] < 1e-13
+    # the reference's uint32_t loop counter leaves the frequency vector EMPTY (SpectrumAnalyser.cpp:34,63)
+    assert d["frequency"].shape == (0,) and freq.shape == (0,)
+    assert int(d["leftover"]) == n     # process() reads the FIFO, it does not consume it
+
+
+@have_ref
+def test_live_spectrum_vs_reference():
+    for n, bw, seed in [(4000, 100.0, 5), (10000, 2500.0, 6), (7777, 1234.5, 7)]:
+        x, _ = random_iq(n, seed)
+        s, f, left = R.spectrum_process(x, n, bw)
+        so, fo = O.spectrum_process(x, n, bw)
+        assert s.shape == so.shape and f.shape == fo.shape == (0,) and left == n
+        assert np.max(np.abs(s - so)) / np.max(np.abs(s)) < 1e-13

@@ -2,6 +2,7 @@
 
   python tools/profile_target.py cfg2 [iters]   one Pipeline (bench.py's workload), `iters` CPIs on one stream
   python tools/profile_target.py cfg3 [iters]   BASELINE configs[2]: CAF only, 2 s CPI @ 10 MS/s, 512 x 1025
+  python tools/profile_target.py spectrum [iters]   SpectrumAnalyser(n, 2000) at n = 2e6 and 2e7 (3 kernels each)
 
 Every CPI launches the same kernel sequence, so `ncu --launch-skip` can step over the warm-up CPIs.
 """
@@ -48,7 +49,19 @@ def cfg3(iters):
     print("cfg3 done", g.range_fft_len, g.range_segments, g.range_parts, g.doppler_fft_len)
 
 
+def spectrum(iters):
+    from blah2_b200.process import SpectrumAnalyser
+    for n in (2_000_000, 20_000_000):
+        sa = SpectrumAnalyser(n, 2000.0)
+        xs = [torch.randn(n, dtype=torch.complex64, device="cuda") for _ in range(2)]
+        for i in range(iters):
+            sa.process_device(xs[i % 2])
+        s = sa.fetch()
+        print("spectrum done", n, sa.decimation, sa.nSpectrum, float(np.abs(s).max()))
+        sa.close()
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-    {"cfg2": cfg2, "cfg3": cfg3}[which](iters)
+    {"cfg2": cfg2, "cfg3": cfg3, "spectrum": spectrum}[which](iters)
