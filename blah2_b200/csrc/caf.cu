@@ -307,6 +307,113 @@ __global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, range_min_ctas<LOG2M, STA
   }
 }
 
+// ---- segment groups: several warps-groups of one CTA work on DIFFERENT segments of the same batch -----------
+// A CPI with few batches (257 at BASELINE config 1/2) cannot fill 148 SMs with one 4-warp CTA per batch: the
+// profile shows 2 warps per scheduler and the FMA pipe 38 % busy (profiles/r01z_kernels.md).  Splitting a batch
+// into `parts` CTAs buys occupancy but costs one more inverse FFT per part.  Here the CTA has G groups of NT
+// threads instead; group g transforms segments g, g + G, ... in its own pair of shared-memory buffers and
+// synchronises only with itself (named barrier g + 1, NT threads), the cross-spectra are accumulated in each
+// group's registers, added in group order through shared memory (deterministic) and group 0 alone runs the ONE
+// inverse transform.  Same arithmetic as G = 1 up to the order of the segment sum.
+template <int LOG2M, int G> constexpr int grouped_min_ctas() {
+  constexpr int T = Plan<LOG2M>::NT * G;
+  return T >= 512 ? 1 : 512 / T;
+}
+
+template <int LOG2M, int G>
+__global__ void __launch_bounds__(Plan<LOG2M>::NT * G, grouped_min_ctas<LOG2M, G>()) caf_range_grouped_kernel(RangeArgs a) {
+  using P = Plan<LOG2M>;
+  constexpr int R = P::R, NT = P::NT;
+  static_assert(G >= 2 && G <= 8 && NT * G <= 1024 && NT % 32 == 0, "group layout");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int grp = threadIdx.x / NT;
+  const int tid = threadIdx.x - grp * NT;
+  float2 *A = reinterpret_cast<float2 *>(smem_raw) + (size_t)grp * 2 * P::MP;
+  float2 *B = A + P::MP;
+  auto gsync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(NT) : "memory"); };
+  const int batch = a.batch0 + blockIdx.x;
+  const long long boff = (long long)batch * a.nCorr;
+  const float2 *__restrict__ xb = a.x + boff;
+  const float2 *__restrict__ yb = a.y + boff;
+  const float2 zero = make_float2(0.f, 0.f);
+
+  float2 Z[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) Z[r] = zero;
+  const int seg0 = blockIdx.y * a.segPerPart;
+  const int seg1 = min(a.nSeg, seg0 + a.segPerPart);
+
+  for (int seg = seg0 + grp; seg < seg1; seg += G) {
+    const int n0 = seg * a.L;
+    const int len = min(a.L, a.nCorr - n0);
+    const int ylen = len + a.nDel - 1;
+    const int yoff = n0 + a.lagMin;
+    auto stA = [&](int i, float2 v) { A[pad(i)] = v; };
+    auto stB = [&](int i, float2 v) { B[pad(i)] = v; };
+    auto ldx = [&](int m) { return m < len ? __ldg(xb + n0 + m) : zero; };
+    auto ldy = [&](int m) {
+      const int j = yoff + m;
+      return (m < ylen && j >= 0 && j < a.nCorr) ? __ldg(yb + j) : zero;
+    };
+    if (seg >= seg0 + G) gsync();  // this group's previous segment has finished reading A/B
+    if constexpr (P::R0 == R) {
+      fft_butterfly<float, R, -1, LOG2M>(tid, P::log2S(0), a.tw, ldx, stA);
+      fft_butterfly<float, R, -1, LOG2M>(tid, P::log2S(0), a.tw, ldy, stB);
+    } else {
+#pragma unroll 1
+      for (int b = tid; b < P::M / P::R0; b += NT) {
+        fft_butterfly<float, P::R0, -1, LOG2M>(b, P::log2S(0), a.tw, ldx, stA);
+        fft_butterfly<float, P::R0, -1, LOG2M>(b, P::log2S(0), a.tw, ldy, stB);
+      }
+    }
+    gsync();
+#pragma unroll 1
+    for (int p = 1; p < P::NP - 1; p++) {
+      smem_pass<float, LOG2M, -1>(A, a.tw, p, tid);
+      smem_pass<float, LOG2M, -1>(B, a.tw, p, tid);
+      gsync();
+    }
+    float2 vx[R], vy[R];
+    fwd_last_to_regs<float, LOG2M>(A, tid, vx);
+    fwd_last_to_regs<float, LOG2M>(B, tid, vy);
+#pragma unroll
+    for (int r = 0; r < R; r++) cfmac(Z[r], vy[r], vx[r]);  // Z += Y conj(X)
+  }
+
+  // hand the groups' cross-spectra to group 0 (each group parks its 16 values per thread in its own A)
+  gsync();
+  if (grp > 0) {
+#pragma unroll
+    for (int r = 0; r < R; r++) A[r * NT + tid] = Z[r];
+  }
+  __syncthreads();
+  if (grp > 0) return;
+#pragma unroll 1
+  for (int g = 1; g < G; g++) {
+    const float2 *Ag = A + (size_t)g * 2 * P::MP;
+#pragma unroll
+    for (int r = 0; r < R; r++) Z[r] = cadd(Z[r], Ag[r * NT + tid]);
+  }
+  inv_first_from_regs<float, LOG2M>(A, tid, Z);
+  gsync();
+#pragma unroll 1
+  for (int p = P::NP - 2; p >= 1; p--) {
+    smem_pass<float, LOG2M, +1>(A, a.tw, p, tid);
+    gsync();
+  }
+  const float scale = 1.0f / (float)P::M;
+  float2 *__restrict__ Rrow = a.R + ((size_t)blockIdx.y * a.nDop + batch) * a.nDel;
+  auto ldA = [&](int i) { return A[pad(i)]; };
+  auto stR = [&](int m, float2 v) {
+    if (m < a.nDel) Rrow[m] = make_float2(v.x * scale, v.y * scale);
+  };
+  constexpr int S0 = 1 << P::log2S(0);
+#pragma unroll 1
+  for (int b = tid; b < P::M / P::R0; b += NT) {
+    if ((b & (S0 - 1)) < a.nDel) fft_butterfly<float, P::R0, +1, LOG2M>(b, P::log2S(0), a.tw, ldA, stR);
+  }
+}
+
 struct DopplerArgs {
   const float2 *R;      // [nParts][nDop][nDel] partial range matrices
   int nParts;
@@ -466,6 +573,37 @@ template <int LOG2M, bool STAGE, int LR = 4> int launch_range_impl(const RangeAr
 // TMA staging needs 2 more M-element buffers (fits up to M = 4096).  Measured on B200 it is equal at
 // config 1/2 and 7 % slower at config 3/4 than direct loads (profiles/r01_summary.md), so it is opt-in:
 // B200DD_CAF_TMA=1.  B200DD_CAF_RADIX=8 selects the radix-8 plan (M/8 threads per CTA).
+template <int LOG2M> int launch_range(const RangeArgs &a, int nDop, int nParts, cudaStream_t st);
+
+template <int LOG2M, int G> int launch_range_grouped(const RangeArgs &a, int nDop, int nParts, cudaStream_t st) {
+  using P = Plan<LOG2M>;
+  const size_t smem = (size_t)G * 2 * P::MP * sizeof(float2);
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    B2_CUDA(cudaFuncSetAttribute(caf_range_grouped_kernel<LOG2M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done[dev & 63] = true;
+  }
+  caf_range_grouped_kernel<LOG2M, G><<<dim3(nDop, nParts), P::NT * G, smem, st>>>(a);
+  B2_LAUNCH_CHECK();
+  return B200DD_OK;
+}
+
+// groups > 1: the grouped kernel (direct loads, radix 16) for the FFT lengths small CPIs use
+template <int LOG2M> int launch_range(const RangeArgs &a, int nDop, int nParts, int groups, cudaStream_t st) {
+  const char *e = getenv("B200DD_CAF_TMA"), *r = getenv("B200DD_CAF_RADIX");  // per call, like launch_range below
+  if ((e && atoi(e) == 1) || (r && atoi(r) == 8)) groups = 1;                  // those variants are ungrouped
+  if constexpr (LOG2M >= 10 && LOG2M <= 12) {
+    if constexpr (LOG2M <= 11) {  // 3+ groups of M = 4096 leave < 128 registers per thread (spills)
+      if (groups == 3) return launch_range_grouped<LOG2M, 3>(a, nDop, nParts, st);
+      if (groups >= 4) return launch_range_grouped<LOG2M, 4>(a, nDop, nParts, st);
+    }
+    if (groups >= 2) return launch_range_grouped<LOG2M, 2>(a, nDop, nParts, st);
+  }
+  return launch_range<LOG2M>(a, nDop, nParts, st);
+}
+
 template <int LOG2M> int launch_range(const RangeArgs &a, int nDop, int nParts, cudaStream_t st) {
   const char *e = getenv("B200DD_CAF_TMA");  // read per call: the parity tests toggle it
   const int env = e ? atoi(e) : 0;
@@ -503,13 +641,13 @@ template <int LOG2M> int launch_fft_forward(const float2 *in, float2 *out, const
   return B200DD_OK;
 }
 
-int dispatch_range(int log2m, const RangeArgs &a, int nDop, int nParts, cudaStream_t st) {
+int dispatch_range(int log2m, const RangeArgs &a, int nDop, int nParts, int groups, cudaStream_t st) {
   switch (log2m) {
     case 8: return launch_range<8>(a, nDop, nParts, st);
     case 9: return launch_range<9>(a, nDop, nParts, st);
-    case 10: return launch_range<10>(a, nDop, nParts, st);
-    case 11: return launch_range<11>(a, nDop, nParts, st);
-    case 12: return launch_range<12>(a, nDop, nParts, st);
+    case 10: return launch_range<10>(a, nDop, nParts, groups, st);
+    case 11: return launch_range<11>(a, nDop, nParts, groups, st);
+    case 12: return launch_range<12>(a, nDop, nParts, groups, st);
     case 13: return launch_range<13>(a, nDop, nParts, st);
   }
   return geom_fail("range FFT length out of range");
@@ -561,7 +699,7 @@ struct b200dd_caf {
   int device = 0;
   cudaStream_t stream = nullptr;
   // range stage plan
-  int log2m = 12, nSeg = 1, L = 0, nParts = 1, segPerPart = 1;
+  int log2m = 12, nSeg = 1, L = 0, nParts = 1, segPerPart = 1, nGroups = 1;
   int num_sms = 148;
   // doppler stage plan
   int log2m2 = 10;
@@ -603,15 +741,28 @@ void plan_range(b200dd_caf *h) {
     if (h->nSeg < 1) h->nSeg = 1;
     h->L = (nCorr + h->nSeg - 1) / h->nSeg;
     h->nSeg = (nCorr + h->L - 1) / h->L;
-    // occupancy: with fewer batches than ~2 CTAs per SM, split batches into parts.  (Measured on
-    // BASELINE config 1, 257 batches: 1..3 parts are within 3 % of each other -- the kernel is
-    // FP32-issue bound there, profiles/r01_summary.md -- so splitting is reserved for small nDop.)
-    const int ctas_wanted = 2 * h->num_sms;
-    int parts = (ctas_wanted + (int)h->g.nDop - 1) / (int)h->g.nDop;
-    if ((int)h->g.nDop >= h->num_sms) parts = 1;
+    // occupancy for CPIs with few batches (257 at BASELINE config 1/2 against 148 SMs): first give the CTA of a
+    // batch several segment GROUPS (caf_range_grouped_kernel: more warps per batch, still ONE inverse FFT),
+    // then, if that is still fewer than ~3 segment streams per SM, split the batch into parts (one more inverse
+    // FFT and one more partial range matrix each).  B200DD_CAF_GROUPS / B200DD_CAF_PARTS override.
+    const int nDop = (int)h->g.nDop;
+    int want = nDop >= 3 * h->num_sms ? 1 : (3 * h->num_sms + nDop - 1) / nDop;  // segment streams per batch
+    int gmax = best_l == 12 ? 2 : 4;
+    if (best_l < 10 || best_l > 12) gmax = 1;
+    if (const char *r = getenv("B200DD_CAF_RADIX")) { if (atoi(r) == 8) gmax = 1; }
+    if (const char *t = getenv("B200DD_CAF_TMA")) { if (atoi(t) == 1) gmax = 1; }
+    int groups = want < gmax ? want : gmax;
+    if (const char *e = getenv("B200DD_CAF_GROUPS")) groups = atoi(e);
+    if (groups > gmax) groups = gmax;
+    if (groups > h->nSeg) groups = h->nSeg;
+    if (groups < 1) groups = 1;
+    h->nGroups = groups;
+    int parts = (want + groups - 1) / groups;
+    if (nDop >= h->num_sms) parts = 1;
     if (const char *e = getenv("B200DD_CAF_PARTS")) parts = atoi(e);
     if (parts < 1) parts = 1;
-    if (parts > h->nSeg) parts = h->nSeg;
+    if (parts * groups > h->nSeg) parts = h->nSeg / groups;
+    if (parts < 1) parts = 1;
     h->segPerPart = (h->nSeg + parts - 1) / parts;
     h->nParts = (h->nSeg + h->segPerPart - 1) / h->segPerPart;
   }
@@ -670,7 +821,7 @@ int caf_run_device(b200dd_caf *h, const float2 *d_x, const float2 *d_y, float2 *
   ra.nDop = (int)g.nDop;
   ra.batch0 = 0;
   if (ev) B2_CUDA(cudaEventRecord(ev[0], st));
-  int rc = dispatch_range(h->log2m, ra, (int)g.nDop, h->nParts, st);
+  int rc = dispatch_range(h->log2m, ra, (int)g.nDop, h->nParts, h->nGroups, st);
   if (rc != B200DD_OK) return rc;
   if (ev) B2_CUDA(cudaEventRecord(ev[1], st));
   DopplerArgs da;
@@ -876,7 +1027,7 @@ int b200dd_caf_range_device(b200dd_caf *h, const void *d_x, const void *d_y, uin
   ra.tw = h->d_tw1;
   ra.nCorr = (int)g.nCorr; ra.nDel = (int)g.nDel; ra.lagMin = g.delayMin; ra.nSeg = h->nSeg; ra.L = h->L;
   ra.segPerPart = h->segPerPart; ra.nDop = (int)g.nDop; ra.batch0 = (int)batch0;
-  int rc = dispatch_range(h->log2m, ra, (int)n_batches, h->nParts, st);
+  int rc = dispatch_range(h->log2m, ra, (int)n_batches, h->nParts, h->nGroups, st);
   if (rc != B200DD_OK) return rc;
   const size_t plane = (size_t)g.nDop * g.nDel, first = (size_t)batch0 * g.nDel, count = (size_t)n_batches * g.nDel;
   caf_sum_parts_kernel<<<grid_for((uint32_t)count), 256, 0, st>>>(h->d_R, h->nParts, plane, first, count, (float2 *)d_R);

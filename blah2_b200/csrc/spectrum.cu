@@ -15,13 +15,14 @@
 // come from host tables indexed by exact integer residues; all arithmetic is FP64, so the result equals the
 // reference's FP64 FFT to rounding (tests: 1e-11 relative to max |spectrum|).
 //
-//   K_S1  spec_fold_kernel<TIN>   x (float2 / double2) -> per-chunk column sums  part[chunk][r]
+//   K_S1  spec_fold_kernel<TIN> / spec_fold2_kernel   x (float2 / double2) -> per-chunk column sums  part[chunk][r]
 //   K_S2  spec_reduce_kernel      g[r] = t2[r] * sum_chunk part[chunk][r]        (fixed order: deterministic)
-//   K_S3  spec_dft_kernel         spectrum[m] = sum_r g[r] W^(r m)               (direct, table-driven)
+//   K_S3  spec_dft_kernel         spectrum[m] = sum_r g[r] W^(r m)               (direct; phases = table seeds + running product)
 #include "common.cuh"
 
 #include <cmath>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 using namespace b2;
@@ -30,7 +31,7 @@ namespace {
 
 constexpr int FOLD_THREADS = 128;
 constexpr int FOLD_UNROLL = 8;
-constexpr int RED_WARPS = 8;
+constexpr int RED_WARPS = 32;
 constexpr int DFT_OUT = 8;      // outputs per CTA
 constexpr int DFT_SLICES = 32;  // threads per output, each summing r = slice, slice + 32, ...
 constexpr int DFT_THREADS = DFT_OUT * DFT_SLICES;
@@ -80,8 +81,54 @@ __global__ void __launch_bounds__(FOLD_THREADS) spec_fold_kernel(const TIN *__re
   part[(size_t)blockIdx.y * nSpec + r] = acc;
 }
 
-// K_S2.  CTA = 32 columns x RED_WARPS warps; warp w adds chunks w, w + 8, ... (ascending), the eight sums are then
-// added in warp order: a fixed tree, so the result does not depend on scheduling.
+// K_S1, two columns per thread (float2 input, nSpec even, 16-byte aligned x): one 16-byte load per row, a warp's row
+// load is 512 contiguous bytes and FOLD_UNROLL x 16 bytes are in flight per thread -- what it takes to keep HBM busy
+// with 8 CTAs of 4 warps per SM (the 8-byte version stops at 60 % of the DRAM peak, profiles/r01_summary.md s6).
+// Same sums in the same order as the scalar kernel: results are bit-identical.
+__global__ void __launch_bounds__(FOLD_THREADS, 6) spec_fold2_kernel(const float2 *__restrict__ x, const double2 *__restrict__ t1,
+                                                                  double2 *__restrict__ part, uint32_t nSpec, uint32_t dec,
+                                                                  uint32_t rowsPerChunk) {
+  const uint32_t r = 2u * (blockIdx.x * FOLD_THREADS + threadIdx.x);
+  if (r >= nSpec) return;  // nSpec is even: r + 1 < nSpec as well
+  const uint32_t q0 = blockIdx.y * rowsPerChunk;
+  const uint32_t q1 = min(dec, q0 + rowsPerChunk);
+  double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
+  const float4 *p = reinterpret_cast<const float4 *>(x + (size_t)q0 * nSpec + r);
+  const size_t rowStride = nSpec / 2;  // in float4
+  uint32_t q = q0;
+  for (; q + FOLD_UNROLL <= q1; q += FOLD_UNROLL) {
+    float4 v[FOLD_UNROLL];
+#pragma unroll
+    for (int u = 0; u < FOLD_UNROLL; u++) v[u] = __ldg(p + (size_t)u * rowStride);
+#pragma unroll
+    for (int u = 0; u < FOLD_UNROLL; u++) {
+      const double2 w = __ldg(t1 + q + u);
+      zfma(acc0, make_double2((double)v[u].x, (double)v[u].y), w);
+      zfma(acc1, make_double2((double)v[u].z, (double)v[u].w), w);
+    }
+    p += (size_t)FOLD_UNROLL * rowStride;
+  }
+  if (q < q1) {
+    float4 v[FOLD_UNROLL];
+#pragma unroll
+    for (int u = 0; u < FOLD_UNROLL; u++)
+      if (q + u < q1) v[u] = __ldg(p + (size_t)u * rowStride);
+#pragma unroll
+    for (int u = 0; u < FOLD_UNROLL; u++)
+      if (q + u < q1) {
+        const double2 w = __ldg(t1 + q + u);
+        zfma(acc0, make_double2((double)v[u].x, (double)v[u].y), w);
+        zfma(acc1, make_double2((double)v[u].z, (double)v[u].w), w);
+      }
+  }
+  double2 *dst = part + (size_t)blockIdx.y * nSpec + r;
+  dst[0] = acc0;
+  dst[1] = acc1;
+}
+
+// K_S2.  CTA = 32 columns x RED_WARPS warps; warp w adds chunks w, w + 32, ... (ascending), the 32 sums are then
+// added in warp order: a fixed tree, so the result does not depend on scheduling.  (Many warps, few loads each:
+// the kernel is one or two L2 round trips long.)
 __global__ void __launch_bounds__(32 * RED_WARPS) spec_reduce_kernel(const double2 *__restrict__ part, const double2 *__restrict__ t2,
                                                                      double2 *__restrict__ g, uint32_t nSpec, uint32_t nChunks) {
   __shared__ double2 s[RED_WARPS][32];
@@ -116,26 +163,27 @@ __global__ void __launch_bounds__(32 * RED_WARPS) spec_reduce_kernel(const doubl
   }
 }
 
-// K_S3.  spectrum[m] = sum_r g[r] W[(r m) mod nSpec], W[j] = exp(-2 pi i j / nSpec) from a host table (exact
-// residues, no recurrence).  CTA = DFT_OUT outputs x DFT_SLICES slices; slice s sums r = s, s + 32, ... ascending,
-// the 32 slice sums are added in slice order.  SMEM: g and W staged in shared memory (nSpec <= 6144), else read
-// through L1.
+// K_S3.  spectrum[m] = sum_r g[r] W^(r m), W = exp(-2 pi i / nSpec).  CTA = DFT_OUT outputs x DFT_SLICES slices; slice s
+// sums r = s, s + 32, ... ascending and the 32 slice sums are added in slice order (deterministic).  The phase of
+// thread (m, s) advances by the constant factor W^(32 m) per term: it is seeded from the host table at the exact
+// residue (r m) mod nSpec and RE-SEEDED from the table every DFT_RESEED terms, in between it is a running product
+// (error <= DFT_RESEED * 2^-52, far below the 1e-11 parity bar).  The first version looked every phase up in a
+// shared-memory table: 745 k bank conflicts per launch on the scattered 16-byte reads, 13.5 us (profiles/
+// r01_summary.md s6); the running product needs no table reads in the loop.  SMEM: g staged in shared memory
+// (nSpec <= 12288; reads are warp-broadcasts), else read through L1.
+constexpr int DFT_RESEED = 32;
+
 template <bool SMEM>
 __global__ void __launch_bounds__(DFT_THREADS) spec_dft_kernel(const double2 *__restrict__ g, const double2 *__restrict__ wtab,
                                                                double2 *__restrict__ out, uint32_t nSpec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double2 red[DFT_SLICES][DFT_OUT];
-  const double2 *gp = g, *wp = wtab;
+  const double2 *gp = g;
   if constexpr (SMEM) {
     double2 *sg = reinterpret_cast<double2 *>(smem_raw);
-    double2 *sw = sg + nSpec;
-    for (uint32_t i = threadIdx.x; i < nSpec; i += DFT_THREADS) {
-      sg[i] = __ldg(g + i);
-      sw[i] = __ldg(wtab + i);
-    }
+    for (uint32_t i = threadIdx.x; i < nSpec; i += DFT_THREADS) sg[i] = __ldg(g + i);
     __syncthreads();
     gp = sg;
-    wp = sw;
   }
   const int ml = threadIdx.x % DFT_OUT, sl = threadIdx.x / DFT_OUT;
   const uint32_t m = blockIdx.x * DFT_OUT + ml;
@@ -143,10 +191,19 @@ __global__ void __launch_bounds__(DFT_THREADS) spec_dft_kernel(const double2 *__
   if (m < nSpec) {
     const uint32_t step = (uint32_t)(((uint64_t)DFT_SLICES * m) % nSpec);
     uint32_t idx = (uint32_t)(((uint64_t)sl * m) % nSpec);
+    const double2 wstep = __ldg(wtab + step);
+    double2 w = __ldg(wtab + idx);
+    int since = 0;
     for (uint32_t r = sl; r < nSpec; r += DFT_SLICES) {
-      zfma(acc, gp[r], wp[idx]);
+      zfma(acc, gp[r], w);
       idx += step;
       if (idx >= nSpec) idx -= nSpec;
+      if (++since == DFT_RESEED) {
+        since = 0;
+        w = __ldg(wtab + idx);
+      } else {
+        w = make_double2(fma(w.x, wstep.x, -w.y * wstep.y), fma(w.x, wstep.y, w.y * wstep.x));
+      }
     }
   }
   red[sl][ml] = acc;
@@ -171,7 +228,8 @@ struct b200dd_spectrum {
   cudaStream_t stream = nullptr;
   uint32_t n = 0, decimation = 0, nSpectrum = 0, nfft = 0;
   double bandwidth = 0.0;
-  uint32_t rowsPerChunk = 0, nChunks = 0;
+  uint32_t rowsPerChunk = 0, nChunks = 0;    // 8-byte-load fold (any nSpectrum / alignment, double2 input)
+  uint32_t rowsPerChunk2 = 0, nChunks2 = 0;  // two-columns-per-thread fold
   double2 *d_t1 = nullptr, *d_t2 = nullptr, *d_w = nullptr, *d_part = nullptr, *d_g = nullptr, *d_out = nullptr;
   double2 *d_xd = nullptr;  // host-path staging
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -181,16 +239,26 @@ struct b200dd_spectrum {
 namespace {
 
 template <class TIN> int run_spectrum(b200dd_spectrum *h, const TIN *d_x, double2 *d_out, cudaStream_t st, bool timed) {
-  const dim3 gridF((h->nSpectrum + FOLD_THREADS - 1) / FOLD_THREADS, h->nChunks);
   if (timed) B2_CUDA(cudaEventRecord(h->ev[0], st));
-  spec_fold_kernel<TIN><<<gridF, FOLD_THREADS, 0, st>>>(d_x, h->d_t1, h->d_part, h->nSpectrum, h->decimation, h->rowsPerChunk);
+  bool vec2 = false;
+  if constexpr (std::is_same<TIN, float2>::value)
+    vec2 = h->nSpectrum % 2 == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0;
+  if (vec2) {
+    const dim3 gridF((h->nSpectrum / 2 + FOLD_THREADS - 1) / FOLD_THREADS, h->nChunks2);
+    spec_fold2_kernel<<<gridF, FOLD_THREADS, 0, st>>>((const float2 *)d_x, h->d_t1, h->d_part, h->nSpectrum, h->decimation,
+                                                     h->rowsPerChunk2);
+  } else {
+    const dim3 gridF((h->nSpectrum + FOLD_THREADS - 1) / FOLD_THREADS, h->nChunks);
+    spec_fold_kernel<TIN><<<gridF, FOLD_THREADS, 0, st>>>(d_x, h->d_t1, h->d_part, h->nSpectrum, h->decimation, h->rowsPerChunk);
+  }
   B2_LAUNCH_CHECK();
+  const uint32_t nChunks = vec2 ? h->nChunks2 : h->nChunks;
   if (timed) B2_CUDA(cudaEventRecord(h->ev[1], st));
-  spec_reduce_kernel<<<(h->nSpectrum + 31) / 32, 32 * RED_WARPS, 0, st>>>(h->d_part, h->d_t2, h->d_g, h->nSpectrum, h->nChunks);
+  spec_reduce_kernel<<<(h->nSpectrum + 31) / 32, 32 * RED_WARPS, 0, st>>>(h->d_part, h->d_t2, h->d_g, h->nSpectrum, nChunks);
   B2_LAUNCH_CHECK();
   const int gridD = (int)((h->nSpectrum + DFT_OUT - 1) / DFT_OUT);
-  if (h->nSpectrum <= 6144) {
-    const size_t smem = 2 * sizeof(double2) * (size_t)h->nSpectrum;
+  if (h->nSpectrum <= 12288) {
+    const size_t smem = sizeof(double2) * (size_t)h->nSpectrum;
     spec_dft_kernel<true><<<gridD, DFT_THREADS, smem, st>>>(h->d_g, h->d_w, d_out, h->nSpectrum);
   } else {
     spec_dft_kernel<false><<<gridD, DFT_THREADS, 0, st>>>(h->d_g, h->d_w, d_out, h->nSpectrum);
@@ -253,6 +321,15 @@ int b200dd_spectrum_create(uint32_t n, double bandwidth, int32_t device, b200dd_
   if (rows < (uint32_t)FOLD_UNROLL) rows = FOLD_UNROLL;
   h->rowsPerChunk = rows;
   h->nChunks = (decimation + rows - 1) / rows;
+  {
+    const uint32_t colTiles2 = (nSpectrum / 2 + FOLD_THREADS - 1) / FOLD_THREADS;
+    uint32_t want2 = (148u * 6u + (colTiles2 ? colTiles2 : 1) - 1) / (colTiles2 ? colTiles2 : 1);  // 6 resident CTAs per SM (80 registers)
+    if (want2 > 256) want2 = 256;
+    uint32_t rows2 = (decimation + want2 - 1) / want2;
+    if (rows2 < (uint32_t)FOLD_UNROLL) rows2 = FOLD_UNROLL;
+    h->rowsPerChunk2 = rows2;
+    h->nChunks2 = (decimation + rows2 - 1) / rows2;
+  }
   // phase tables (long double on the host, exact integer residues)
   const uint64_t k0 = (uint64_t)(nfft / 2) + 1;  // :46 int(nfft / 2) + 1
   std::vector<double2> t1(decimation), t2(nSpectrum), w(nSpectrum);
@@ -267,15 +344,15 @@ int b200dd_spectrum_create(uint32_t n, double bandwidth, int32_t device, b200dd_
     B2_CUDA(cudaMalloc(&h->d_t1, sizeof(double2) * decimation));
     B2_CUDA(cudaMalloc(&h->d_t2, sizeof(double2) * nSpectrum));
     B2_CUDA(cudaMalloc(&h->d_w, sizeof(double2) * nSpectrum));
-    B2_CUDA(cudaMalloc(&h->d_part, sizeof(double2) * (size_t)h->nChunks * nSpectrum));
+    B2_CUDA(cudaMalloc(&h->d_part, sizeof(double2) * (size_t)(h->nChunks > h->nChunks2 ? h->nChunks : h->nChunks2) * nSpectrum));
     B2_CUDA(cudaMalloc(&h->d_g, sizeof(double2) * nSpectrum));
     B2_CUDA(cudaMalloc(&h->d_out, sizeof(double2) * nSpectrum));
     B2_CUDA(cudaMemcpy(h->d_t1, t1.data(), sizeof(double2) * decimation, cudaMemcpyHostToDevice));
     B2_CUDA(cudaMemcpy(h->d_t2, t2.data(), sizeof(double2) * nSpectrum, cudaMemcpyHostToDevice));
     B2_CUDA(cudaMemcpy(h->d_w, w.data(), sizeof(double2) * nSpectrum, cudaMemcpyHostToDevice));
-    if (nSpectrum <= 6144)
+    if (nSpectrum <= 12288)
       B2_CUDA(cudaFuncSetAttribute(spec_dft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(2 * sizeof(double2) * (size_t)nSpectrum)));
+                                   (int)(sizeof(double2) * (size_t)nSpectrum)));
     return B200DD_OK;
   };
   const int rc = body();
@@ -309,8 +386,8 @@ int b200dd_spectrum_get_geometry(const b200dd_spectrum *h, b200dd_spectrum_geome
   out->n_spectrum = h->nSpectrum;
   out->nfft = h->nfft;
   out->n_frequency = (uint32_t)h->frequency.size();
-  out->fold_chunks = h->nChunks;
-  out->fold_rows_per_chunk = h->rowsPerChunk;
+  out->fold_chunks = h->nSpectrum % 2 == 0 ? h->nChunks2 : h->nChunks;
+  out->fold_rows_per_chunk = h->nSpectrum % 2 == 0 ? h->rowsPerChunk2 : h->rowsPerChunk;
   return B200DD_OK;
 }
 

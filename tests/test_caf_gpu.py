@@ -134,6 +134,32 @@ def test_batch_split_into_parts_gives_the_same_map(parts, relerr, monkeypatch):
     assert relerr(amb.debug_range_matrix(), Rref)[0] < TOL
 
 
+@pytest.mark.parametrize("log2m,groups,parts", [(10, 2, 1), (10, 4, 1), (11, 2, 1), (11, 3, 1), (11, 4, 1), (12, 2, 1),
+                                                 (12, 3, 1), (12, 4, 1), (10, 2, 2), (10, 3, 3), (11, 2, 100), (10, 8, 1)])
+def test_segment_groups_give_the_same_map(log2m, groups, parts, relerr, monkeypatch):
+    """B200DD_CAF_GROUPS: several warp groups of one CTA transform different segments of a batch and group 0 runs
+    the one inverse FFT (caf_range_grouped_kernel).  Same map and same range matrix as the oracle, alone and
+    combined with the split into parts; more groups than segments / than the kernel supports are clamped."""
+    monkeypatch.setenv("B200DD_CAF_LOG2M", str(log2m))
+    monkeypatch.setenv("B200DD_CAF_GROUPS", str(groups))
+    monkeypatch.setenv("B200DD_CAF_PARTS", str(parts))
+    geom = (-5, 60, -200, 200, 100000, 100000, True)     # nCorr 1666: 2 (M=4096) to 8 (M=1024... 256) segments
+    if log2m == 12:
+        geom = (-5, 60, -20, 20, 100000, 100000, True)   # longer batches so that M = 4096 has several segments
+    x, y = random_iq(geom[5], seed=7)
+    amb, m = _run(geom, x, y)
+    assert amb.geometry.range_fft_len == (1 << log2m)
+    og = O.ambiguity_geometry(*geom)
+    ref, _, _ = O.ambiguity_process(x, y, og)
+    e = relerr(m.data, ref)
+    assert e[0] < TOL and e[1] < TOL, f"log2m={log2m} groups={groups} parts={parts} map {e}"
+    Rref = O.range_matrix(np.asarray(x, np.complex128), np.asarray(y, np.complex128), og)
+    assert relerr(amb.debug_range_matrix(), Rref)[0] < TOL
+    # deterministic: the groups are added in a fixed order
+    _, m2 = _run(geom, x, y)
+    assert np.array_equal(m.data, m2.data)
+
+
 def test_linearity_and_determinism_full_size():
     """Size-independent properties at BASELINE config-3 size (oracle too slow to run in
     seconds): CAF(x, a*y1 + b*y2) = a CAF(x,y1) + b CAF(x,y2), and bitwise repeatability."""
@@ -204,6 +230,7 @@ def test_tma_staged_range_kernel_is_bit_identical(geom, monkeypatch):
     be bit-identical to the direct-load kernel -- odd batch lengths, negative and positive first lags,
     and input buffers that start on an odd float2 (8-byte, not 16-byte aligned) address."""
     import torch
+    monkeypatch.setenv("B200DD_CAF_GROUPS", "1")   # the staged kernel has no segment groups: compare like with like
     x, y = random_iq(geom[5], 31)
     amb = Ambiguity(*geom)
     g = amb.geometry

@@ -38,10 +38,10 @@ def test_cuda_spectrum_vs_reference_golden(name, relerr):
 
 
 @pytest.mark.parametrize("n,bw", [(2000, 2000.0), (2001, 2000.0), (40000, 2000.0), (123457, 2000.0), (50000, 7.0),
-                                  (65536, 9000.0), (30000, 12.5), (8, 8.0), (9, 2.0)])
+                                  (65536, 9000.0), (30000, 12.5), (8, 8.0), (9, 2.0), (131072, 5000.0), (60000, 40000.0)])
 def test_cuda_spectrum_vs_oracle_shapes(n, bw, relerr):
-    """ragged sizes: nfft < n, decimation 1, one column tile / many, odd decimation, more than 6144 bins
-    (the DFT kernel's table then stays in global memory), tiny inputs"""
+    """ragged sizes: nfft < n, decimation 1, one column tile / many, odd decimation, odd and even bin counts (the
+    two fold kernels), more than 12288 bins (the DFT kernel then reads g from global memory), tiny inputs"""
     x, _ = random_iq(n, 31)
     sa = SpectrumAnalyser(n, bw)
     spec, _ = sa.process(x)
@@ -58,15 +58,22 @@ def test_device_float2_path_equals_host_path_on_int16_samples(relerr):
     sa = SpectrumAnalyser(n, bw)
     host, _ = sa.process(sc.x)
     dx = torch.from_numpy(sc.x.astype(np.complex64)).cuda()
-    for _ in range(2):
-        sa.process_device(dx)
-        dev = sa.fetch()
-        assert np.array_equal(dev, host)        # same kernels, same order of operations: bit-identical
+    sa.process_device(dx)
+    dev = sa.fetch()
+    # same samples, but the float2 kernel folds two columns per thread with its own row chunking: equal to rounding
+    assert relerr(dev, host)[0] < 1e-13
+    sa.process_device(dx)
+    assert np.array_equal(sa.fetch(), dev)      # deterministic: every sum has a fixed order
     out = torch.empty(sa.nSpectrum, dtype=torch.complex128, device="cuda")
     st = torch.cuda.Stream()
     sa.process_device(dx, d_spectrum=out, stream=st.cuda_stream)
     st.synchronize()
-    assert np.array_equal(out.cpu().numpy(), host)
+    assert np.array_equal(out.cpu().numpy(), dev)
+    # an input that starts on an odd float2 (8-byte aligned only) takes the one-column kernel: same answer
+    buf = torch.empty(n + 1, dtype=torch.complex64, device="cuda")
+    buf[1:].copy_(dx)
+    sa.process_device(buf[1:])
+    assert relerr(sa.fetch(), host)[0] < 1e-13
     ref, _ = O.spectrum_process(sc.x, n, bw)
     assert relerr(host, ref)[0] < TOL
 
@@ -112,7 +119,7 @@ def test_geometry_limits_and_errors():
     assert lib.b200dd_spectrum_create(1000, 2000.0, -1, C.byref(h)) == capi.ERR_GEOMETRY   # bandwidth > n: the reference divides by zero
     assert lib.b200dd_spectrum_create(1000, 0.0, -1, C.byref(h)) == capi.ERR_GEOMETRY
     assert lib.b200dd_spectrum_create(1000, float("nan"), -1, C.byref(h)) == capi.ERR_GEOMETRY
-    assert lib.b200dd_spectrum_create(100000, 1.0, -1, C.byref(h)) == capi.ERR_GEOMETRY    # 100000 bins > 65536
+    assert lib.b200dd_spectrum_create(100000, 100000.0, -1, C.byref(h)) == capi.ERR_GEOMETRY   # 100000 bins > 65536
     sa = SpectrumAnalyser(4000, 100.0)
     with pytest.raises(capi.B200ddError):
         sa.process(np.zeros(100, dtype=np.complex128))   # fewer than nfft samples
