@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(32 * RED_WARPS) spec_reduce_kernel(const doubl
 // shared-memory table: 745 k bank conflicts per launch on the scattered 16-byte reads, 13.5 us (profiles/
 // r01_summary.md s6); the running product needs no table reads in the loop.  SMEM: g staged in shared memory
 // (nSpec <= 12288; reads are warp-broadcasts), else read through L1.
-constexpr int DFT_RESEED = 32;
+constexpr int DFT_RESEED = 16;  // in terms per chain
+constexpr int DFT_ILP = 4;
 
 template <bool SMEM>
 __global__ void __launch_bounds__(DFT_THREADS) spec_dft_kernel(const double2 *__restrict__ g, const double2 *__restrict__ wtab,
@@ -189,22 +190,35 @@ __global__ void __launch_bounds__(DFT_THREADS) spec_dft_kernel(const double2 *__
   const uint32_t m = blockIdx.x * DFT_OUT + ml;
   double2 acc = make_double2(0.0, 0.0);
   if (m < nSpec) {
-    const uint32_t step = (uint32_t)(((uint64_t)DFT_SLICES * m) % nSpec);
-    uint32_t idx = (uint32_t)(((uint64_t)sl * m) % nSpec);
+    // DFT_ILP independent chains per thread (terms r = sl + 32 c + 32 DFT_ILP j, c < DFT_ILP): one chain is a
+    // 16-clock dependent DMUL -> DFMA recurrence per term, which left the FP64 pipe 23 % busy
+    constexpr uint32_t STRIDE = DFT_SLICES * DFT_ILP;
+    const uint32_t step = (uint32_t)(((uint64_t)STRIDE * m) % nSpec);
     const double2 wstep = __ldg(wtab + step);
-    double2 w = __ldg(wtab + idx);
+    uint32_t idx[DFT_ILP];
+    double2 w[DFT_ILP], a[DFT_ILP];
+#pragma unroll
+    for (int c = 0; c < DFT_ILP; c++) {
+      idx[c] = (uint32_t)(((uint64_t)(sl + DFT_SLICES * c) * m) % nSpec);
+      w[c] = __ldg(wtab + idx[c]);
+      a[c] = make_double2(0.0, 0.0);
+    }
     int since = 0;
-    for (uint32_t r = sl; r < nSpec; r += DFT_SLICES) {
-      zfma(acc, gp[r], w);
-      idx += step;
-      if (idx >= nSpec) idx -= nSpec;
-      if (++since == DFT_RESEED) {
-        since = 0;
-        w = __ldg(wtab + idx);
-      } else {
-        w = make_double2(fma(w.x, wstep.x, -w.y * wstep.y), fma(w.x, wstep.y, w.y * wstep.x));
+    for (uint32_t r0 = sl; r0 < nSpec; r0 += STRIDE) {
+      const bool reseed = ++since == DFT_RESEED;
+      if (reseed) since = 0;
+#pragma unroll
+      for (int c = 0; c < DFT_ILP; c++) {
+        const uint32_t r = r0 + DFT_SLICES * c;
+        if (r < nSpec) zfma(a[c], gp[r], w[c]);
+        idx[c] += step;
+        if (idx[c] >= nSpec) idx[c] -= nSpec;
+        if (reseed) w[c] = __ldg(wtab + idx[c]);
+        else w[c] = make_double2(fma(w[c].x, wstep.x, -w[c].y * wstep.y), fma(w[c].x, wstep.y, w[c].y * wstep.x));
       }
     }
+#pragma unroll
+    for (int c = 0; c < DFT_ILP; c++) { acc.x += a[c].x; acc.y += a[c].y; }  // fixed order
   }
   red[sl][ml] = acc;
   __syncthreads();
@@ -275,14 +289,14 @@ extern "C" {
 int b200dd_spectrum_create(uint32_t n, double bandwidth, int32_t device, b200dd_spectrum **out) {
   if (!out) return arg_fail("b200dd_spectrum_create: null argument");
   *out = nullptr;
-  // SpectrumAnalyser.cpp:15-17.  The reference divides by zero for bandwidth > n and converts an out-of-range
+  // SpectrumAnalyser.cpp:16-18.  The reference divides by zero for bandwidth > n and converts an out-of-range
   // double to uint32_t for bandwidth <= 0 / NaN (both undefined): fenced.
   if (!(bandwidth > 0.0) || n == 0) return geom_fail("b200dd_spectrum_create: bandwidth must be positive and n non-zero");
   const double ratio = (double)n / bandwidth;
   if (!(ratio >= 1.0) || ratio >= 4294967296.0) return geom_fail("b200dd_spectrum_create: n / bandwidth outside [1, 2^32)");
-  const uint32_t decimation = (uint32_t)ratio;       // :15  decimation = n/bandwidth
-  const uint32_t nSpectrum = n / decimation;         // :16
-  const uint32_t nfft = nSpectrum * decimation;      // :17
+  const uint32_t decimation = (uint32_t)ratio;       // :16  decimation = n/bandwidth
+  const uint32_t nSpectrum = n / decimation;         // :17
+  const uint32_t nfft = nSpectrum * decimation;      // :18
   if (nSpectrum > 65536u) return geom_fail("b200dd_spectrum_create: more than 65536 spectrum bins");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {

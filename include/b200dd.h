@@ -40,6 +40,7 @@
  *
  * Environment (all optional; defaults are the measured best on B200, profiles/r01_summary.md):
  *   B200DD_CAF_LOG2M / B200DD_CAF_PARTS      range-correlation FFT length (2^k) / CTAs per batch
+ *   B200DD_CAF_GROUPS                        warp groups per range CTA, each on its own segments (1..4)
  *   B200DD_CAF_TMA=1                         stage IQ segments through shared memory with bulk async copies
  *   B200DD_WH_LOG2M, B200DD_WH_CORR_LOG2M, B200DD_WH_APPLY_LOG2M, B200DD_WH_RADIX   WienerHopf FFT plans
  *   B200DD_WH_SOLVE_SHORT=0                  generic Toeplitz solve kernel also for <= 992 taps
@@ -261,16 +262,16 @@ B200DD_API int b200dd_det_interpolate_host(b200dd_det *h, const double *delay, c
  * SpectrumAnalyser(n, bandwidth) / SpectrumAnalyser::process(IqData *x)
  * (src/process/spectrum/SpectrumAnalyser.h:48-57, SpectrumAnalyser.cpp:9-74): the stage of the reference's
  * process thread that runs on the reference channel right before the clutter filter (src/blah2.cpp:263-265).
- * decimation = n / bandwidth, nSpectrum = n / decimation, nfft = nSpectrum * decimation (:15-17); the result is
+ * decimation = n / bandwidth, nSpectrum = n / decimation, nfft = nSpectrum * decimation (:16-18); the result is
  * every decimation-th bin of the fft-shifted nfft-point spectrum of the first nfft samples (:36-54), which the
  * reference stores with IqData::update_spectrum (:55).  The device kernels never form the nfft-point transform:
  * one HBM-bound folding pass over x and an nSpectrum-point DFT (blah2_b200/csrc/spectrum.cu). */
 typedef struct b200dd_spectrum b200dd_spectrum;
 
 typedef struct {
-  uint32_t decimation;   /* SpectrumAnalyser.cpp:15 */
-  uint32_t n_spectrum;   /* :16, number of complex bins process() produces */
-  uint32_t nfft;         /* :17, samples of x consumed (read, not popped) */
+  uint32_t decimation;   /* SpectrumAnalyser.cpp:16 */
+  uint32_t n_spectrum;   /* :17, number of complex bins process() produces */
+  uint32_t nfft;         /* :18, samples of x consumed (read, not popped) */
   uint32_t n_frequency;  /* entries of the frequency vector the reference's loop (:57-67) produces: its uint32_t
                             counter starts at (2^32 - nSpectrum) / 2, so this is 0 for every realistic size */
   /* implementation facts */
@@ -279,7 +280,7 @@ typedef struct {
 } b200dd_spectrum_geometry;
 
 /* Returns B200DD_ERR_GEOMETRY where the reference is undefined (bandwidth <= 0, NaN, or bandwidth > n, which
- * divides by zero at :16) or for more than 65536 spectrum bins. */
+ * divides by zero at :17) or for more than 65536 spectrum bins. */
 B200DD_API int b200dd_spectrum_create(uint32_t n, double bandwidth, int32_t device, b200dd_spectrum **out);
 B200DD_API void b200dd_spectrum_destroy(b200dd_spectrum *h);
 B200DD_API int b200dd_spectrum_get_geometry(const b200dd_spectrum *h, b200dd_spectrum_geometry *out);

@@ -60,7 +60,7 @@ def next_hamming(value: int) -> int:
 # SpectrumAnalyser  (src/process/spectrum/SpectrumAnalyser.cpp:9-74)
 # --------------------------------------------------------------------------------------
 def spectrum_geometry(n: int, bandwidth: float):
-    """(decimation, nSpectrum, nfft) as the constructor computes them (SpectrumAnalyser.cpp:15-17):
+    """(decimation, nSpectrum, nfft) as the constructor computes them (SpectrumAnalyser.cpp:16-18):
     ``decimation = n/bandwidth`` is a double division truncated into a uint32_t member, the other
     two are uint32_t integer arithmetic."""
     decimation = int(float(n) / float(bandwidth)) & 0xFFFFFFFF

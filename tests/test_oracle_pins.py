@@ -184,7 +184,7 @@ def test_live_wienerhopf_positive_delay_min_uint32_wrap(relerr):
 
 # ---- SpectrumAnalyser (src/process/spectrum/SpectrumAnalyser.cpp) ----------------------
 def test_spectrum_geometry_like_blah2_cpp():
-    # blah2.cpp:198-199: SpectrumAnalyser(nSamples, 2000) -> SpectrumAnalyser.cpp:15-17
+    # blah2.cpp:198-199: SpectrumAnalyser(nSamples, 2000) -> SpectrumAnalyser.cpp:16-18
     assert O.spectrum_geometry(2000000, 2000.0) == (1000, 2000, 2000000)
     assert O.spectrum_geometry(20000000, 2000.0) == (10000, 2000, 20000000)
     assert O.spectrum_geometry(5003, 97.0) == (51, 98, 4998)       # nfft < n
@@ -199,7 +199,7 @@ def test_golden_spectrum(name, relerr):
     spec, freq = O.spectrum_process(x, n, bw)
     assert spec.shape == d["spectrum"].shape
     assert relerr(spec, d["spectrum"])[0] < 1e-13
-    # the reference's uint32_t loop counter leaves the frequency vector EMPTY (SpectrumAnalyser.cpp:34,63)
+    # the reference's uint32_t loop counter leaves the frequency vector EMPTY (SpectrumAnalyser.cpp:34,64)
     assert d["frequency"].shape == (0,) and freq.shape == (0,)
     assert int(d["leftover"]) == n     # process() reads the FIFO, it does not consume it
 
