@@ -4,6 +4,7 @@
 // defined here are the complex128 <-> complex64 conversions of the host entry point.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -63,9 +64,21 @@ struct b200dd_pipeline {
   float2 *d_map = nullptr;
   short4 *d_iq16 = nullptr;  // int16 ingest staging
   bool last_had_filter = false;
+  // CUDA-graph replay of the device chain (b200dd_pipeline_submit_device): one instantiated graph per distinct
+  // (d_x, d_y, d_map) triple, captured from the ordinary enqueue code the SECOND time a triple is seen
+  struct GraphEntry {
+    const void *x = nullptr, *y = nullptr;
+    void *map = nullptr;
+    uint32_t n = 0;
+    cudaGraphExec_t exec = nullptr;
+  };
+  std::vector<GraphEntry> graphs;
+  int graph_mode = 1;  // B200DD_PIPELINE_GRAPH=0 disables
 };
 
 extern "C" {
+
+static void pipeline_drop_graphs(b200dd_pipeline *h);
 
 int b200dd_pipeline_create(const b200dd_pipeline_params *params, b200dd_pipeline **out) {
   if (!params || !out) return arg_fail("b200dd_pipeline_create: null argument");
@@ -73,6 +86,7 @@ int b200dd_pipeline_create(const b200dd_pipeline_params *params, b200dd_pipeline
   b200dd_pipeline *h = new (std::nothrow) b200dd_pipeline();
   if (!h) return arg_fail("b200dd_pipeline_create: out of host memory");
   h->p = *params;
+  if (const char *e = getenv("B200DD_PIPELINE_GRAPH")) h->graph_mode = atoi(e) != 0;
   auto fail = [&](int rc) { b200dd_pipeline_destroy(h); return rc; };
   int dev = params->caf.device;
   if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaGetDevice", __FILE__, __LINE__));
@@ -114,6 +128,7 @@ void b200dd_pipeline_destroy(b200dd_pipeline *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     b200dd_caf_destroy(h->caf);
     b200dd_wh_destroy(h->wh);
+    pipeline_drop_graphs(h);
     b200dd_det_destroy(h->det);
     b200dd_spectrum_destroy(h->spec);
     free_dev(h->d_yf);
@@ -142,12 +157,8 @@ int b200dd_pipeline_get_axes(const b200dd_pipeline *h, int32_t *delay, double *d
 
 void *b200dd_pipeline_stream(b200dd_pipeline *h) { return h ? (void *)h->stream : nullptr; }
 
-int b200dd_pipeline_submit_device(b200dd_pipeline *h, const void *d_x, const void *d_y, uint32_t n, void *d_map,
-                                  void *stream) {
-  if (!h || !d_x || !d_y) return arg_fail("b200dd_pipeline_submit_device: null argument");
-  if (h->wh && n != h->p.caf.n_samples) return arg_fail("b200dd_pipeline_submit_device: the clutter filter needs exactly n_samples");
-  DeviceGuard guard(h->device);
-  void *st = stream ? stream : (void *)h->stream;
+// the kernels of one CPI on device-resident IQ, enqueued on `st` (also what a graph capture records)
+static int pipeline_enqueue_device(b200dd_pipeline *h, const void *d_x, const void *d_y, uint32_t n, void *d_map, void *st) {
   const void *y = d_y;
   int rc;
   if (h->spec) {  // spectrumAnalyser->process(x), blah2.cpp:264, before the filter touches anything
@@ -170,6 +181,65 @@ int b200dd_pipeline_submit_device(b200dd_pipeline *h, const void *d_x, const voi
                                        h->doppler.data(), st);
     if (rc != B200DD_OK) return rc;
   }
+  return B200DD_OK;
+}
+
+
+static void pipeline_drop_graphs(b200dd_pipeline *h) {
+  for (auto &e : h->graphs)
+    if (e.exec) cudaGraphExecDestroy(e.exec);
+  h->graphs.clear();
+}
+
+// A CPI is 13+ kernel launches; with several CPIs in flight (and several ranks sharing one host) the launch path
+// of the single submitting thread becomes the limit.  The chain's arguments only depend on the caller's three
+// device pointers, so the second submit with the same triple is recorded by stream capture (everything below runs
+// on `st`, no allocation, attribute call or host copy after the first eager run) and later submits replay the
+// instantiated graph with ONE cudaGraphLaunch.  B200DD_PIPELINE_GRAPH=0 keeps every submit eager.
+int b200dd_pipeline_submit_device(b200dd_pipeline *h, const void *d_x, const void *d_y, uint32_t n, void *d_map,
+                                  void *stream) {
+  if (!h || !d_x || !d_y) return arg_fail("b200dd_pipeline_submit_device: null argument");
+  if (h->wh && n != h->p.caf.n_samples) return arg_fail("b200dd_pipeline_submit_device: the clutter filter needs exactly n_samples");
+  DeviceGuard guard(h->device);
+  void *st = stream ? stream : (void *)h->stream;
+  if (!h->graph_mode) return pipeline_enqueue_device(h, d_x, d_y, n, d_map, st);
+  b200dd_pipeline::GraphEntry *hit = nullptr;
+  for (auto &e : h->graphs)
+    if (e.x == d_x && e.y == d_y && e.map == d_map && e.n == n) { hit = &e; break; }
+  if (!hit) {  // first sight: eager (sets function attributes, uploads the axes, sizes scratch buffers)
+    if (h->graphs.size() < 64) {
+      b200dd_pipeline::GraphEntry e;
+      e.x = d_x; e.y = d_y; e.map = d_map; e.n = n;
+      h->graphs.push_back(e);
+    }
+    return pipeline_enqueue_device(h, d_x, d_y, n, d_map, st);
+  }
+  if (!hit->exec) {  // second sight: record
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture((cudaStream_t)st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      return pipeline_enqueue_device(h, d_x, d_y, n, d_map, st);
+    }
+    const int rc = pipeline_enqueue_device(h, d_x, d_y, n, d_map, st);
+    const cudaError_t ce = cudaStreamEndCapture((cudaStream_t)st, &graph);
+    if (rc != B200DD_OK || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      h->graph_mode = 0;  // something in the chain is not capturable here: stay eager from now on
+      return rc != B200DD_OK ? rc : pipeline_enqueue_device(h, d_x, d_y, n, d_map, st);
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess || !exec) {
+      cudaGetLastError();
+      h->graph_mode = 0;
+      return pipeline_enqueue_device(h, d_x, d_y, n, d_map, st);
+    }
+    hit->exec = exec;
+  }
+  h->last_had_filter = h->wh != nullptr;
+  B2_CUDA(cudaGraphLaunch(hit->exec, (cudaStream_t)st));
   return B200DD_OK;
 }
 
@@ -294,6 +364,7 @@ int b200dd_pipeline_enable_spectrum(b200dd_pipeline *h, double bandwidth, uint32
   if (!h) return arg_fail("b200dd_pipeline_enable_spectrum: null handle");
   DeviceGuard guard(h->device);
   B2_CUDA(cudaStreamSynchronize(h->stream));
+  pipeline_drop_graphs(h);  // the chain changes
   b200dd_spectrum_destroy(h->spec);
   h->spec = nullptr;
   h->spec_bins = h->spec_nfft = 0;

@@ -69,7 +69,13 @@ def main(steps=24):
         dst2[:N].copy_(hx[0], non_blocking=True); dst2[N:].copy_(hy[0], non_blocking=True)
     torch.cuda.synchronize()
     out["h2d_c128_64MB"] = round((time.perf_counter() - t0) / 10 * 1e3, 4)
-    for npipe in (1, 2, 4, 8):
+    for npipe in (1, 2, 4, 6, 8):
+        os.environ["B200DD_PIPELINE_GRAPH"] = "0"
+        pipes = [Pipeline(**bench.GEOM, clutter=bench.CLUTTER, detection=bench.DET, device=0) for _ in range(npipe)]
+        out[f"device_eager_x{npipe}"] = round(loop(pipes, lambda p, i: p.submit_device(dx, dy), steps), 4)
+        for p in pipes:
+            p.close()
+        os.environ["B200DD_PIPELINE_GRAPH"] = "1"
         pipes = [Pipeline(**bench.GEOM, clutter=bench.CLUTTER, detection=bench.DET, device=0) for _ in range(npipe)]
         g = pipes[0].geometry
         hmaps = [torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex128).pin_memory() for _ in range(npipe)]
