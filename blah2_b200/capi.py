@@ -132,6 +132,7 @@ SIGNATURES = [
     ("b200dd_pipeline_submit_host", C.c_int, [_VP, _VP, _VP, C.c_uint32, _VP]),
     ("b200dd_pipeline_submit_host_rspduo", C.c_int, [_VP, _VP, C.c_uint32, _VP]),
     ("b200dd_pipeline_submit_device", C.c_int, [_VP, _VP, _VP, C.c_uint32, _VP, _VP]),
+    ("b200dd_pipeline_prepare_device", C.c_int, [_VP, _VP, _VP, C.c_uint32, _VP, _VP]),
     ("b200dd_pipeline_fetch", C.c_int, [_VP, C.POINTER(CpiResult), _VP, _VP, _VP, C.c_uint32, _VP]),
     ("b200dd_pipeline_stream", _VP, [_VP]),
     ("b200dd_pipeline_enable_spectrum", C.c_int, [_VP, C.c_double, C.POINTER(C.c_uint32)]),

@@ -444,8 +444,11 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT) caf_doppler_kernel(DopplerArg
     return cmul(r, __ldg(a.chirp + i));
   };
   auto stA = [&](int i, float2 v) { A[pad(i)] = v; };
-#pragma unroll 1
-  for (int b = tid; b < P::M / P::R0; b += P::NT) fft_butterfly<float, P::R0, -1, LOG2M>(b, P::log2S(0), a.tw, ld0, stA);
+  // 16 / R0 butterflies per thread, fully unrolled: all their (column-strided, L2-latency) loads are in flight
+  // together -- with one warp per scheduler at 257 x 300 nothing else hides that latency
+#pragma unroll
+  for (int it = 0; it < P::R / P::R0; it++)
+    fft_butterfly<float, P::R0, -1, LOG2M>(tid + it * P::NT, P::log2S(0), a.tw, ld0, stA);
   __syncthreads();
 #pragma unroll 1
   for (int p = 1; p < P::NP - 1; p++) {

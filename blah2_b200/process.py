@@ -493,6 +493,12 @@ class Pipeline:
         capi.check(self._lib.b200dd_pipeline_submit_device(self._h, capi.ptr(d_x), capi.ptr(d_y), int(n),
                                                            capi.ptr(d_map), capi.ptr(stream) if stream else None))
 
+    def prepare_device(self, d_x, d_y, d_map=None, stream=None):
+        """Plan creation for submit_device on this buffer triple (records the CUDA graph of the chain now)."""
+        n = d_x.numel() if hasattr(d_x, "numel") else self.n_samples
+        capi.check(self._lib.b200dd_pipeline_prepare_device(self._h, capi.ptr(d_x), capi.ptr(d_y), int(n),
+                                                            capi.ptr(d_map), capi.ptr(stream) if stream else None))
+
     def fetch(self, stream=None):
         res = capi.CpiResult()
         capi.check(self._lib.b200dd_pipeline_fetch(self._h, C.byref(res), capi.ptr(self._od), capi.ptr(self._of),

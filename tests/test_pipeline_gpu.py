@@ -156,3 +156,28 @@ def test_graph_replay_of_the_device_chain_is_bit_identical(monkeypatch):
     assert r["skipped"]
     m2, r2 = run(eager, 0, em)
     assert r2["skipped"] and np.array_equal(m, m2)
+
+
+def test_prepare_device_records_the_graph_up_front(monkeypatch):
+    """b200dd_pipeline_prepare_device = plan creation: afterwards the FIRST submit of the triple is already a replay and
+    gives the eager result bit for bit; with B200DD_PIPELINE_GRAPH=0 it is a no-op."""
+    import torch
+    d, geom, det, sc = _chain_fixture()
+    clutter = tuple(int(v) for v in d["clutter"])
+    dx = torch.from_numpy(sc.x.astype(np.complex64)).cuda()
+    dy = torch.from_numpy(sc.y.astype(np.complex64)).cuda()
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B200DD_PIPELINE_GRAPH", mode)
+        pipe = Pipeline(*geom[:6], roundHamming=True, clutter=clutter, detection=det, spectrum_bandwidth=2000.0)
+        dmap = torch.zeros((pipe.geometry.n_doppler_bins, pipe.geometry.n_delay_bins), dtype=torch.complex64, device="cuda")
+        scratch = dx.clone()
+        pipe.prepare_device(scratch, dy, dmap)      # runs on whatever the buffers hold now ...
+        scratch.copy_(dx)                           # (same values here; the replay reads the buffers when it runs)
+        dmap.zero_()
+        pipe.submit_device(scratch, dy, dmap)
+        r = pipe.fetch()
+        outs[mode] = (dmap.cpu().numpy().copy(), r["noisePower"], r["detections"].delay.copy(), pipe.fetch_spectrum())
+    assert np.abs(outs["0"][0]).max() > 0
+    assert np.array_equal(outs["0"][0], outs["1"][0]) and outs["0"][1] == outs["1"][1]
+    assert np.array_equal(outs["0"][2], outs["1"][2]) and np.array_equal(outs["0"][3], outs["1"][3])
