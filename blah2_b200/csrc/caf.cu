@@ -436,19 +436,43 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT) caf_doppler_kernel(DopplerArg
   const int col = a.col0 + blockIdx.x;
   const float2 zero = make_float2(0.f, 0.f);
   const size_t plane = (size_t)a.nDop * a.nDel;
-  auto ld0 = [&](int i) {
-    if (i >= a.nDop) return zero;
-    const float2 *p = a.R + (size_t)i * a.nDel + col;
-    float2 r = __ldg(p);
-    for (int q = 1; q < a.nParts; q++) r = cadd(r, __ldg(p + q * plane));  // fixed order: deterministic
-    return cmul(r, __ldg(a.chirp + i));
-  };
   auto stA = [&](int i, float2 v) { A[pad(i)] = v; };
-  // 16 / R0 butterflies per thread, fully unrolled: all their (column-strided, L2-latency) loads are in flight
-  // together -- with one warp per scheduler at 257 x 300 nothing else hides that latency
+  // Pass 0.  A thread owns 16 / R0 butterflies = 16 inputs R[i][col] (column-strided: one L2 sector each).  All 16
+  // loads (and the 16 chirp values) are issued before anything is consumed: with one warp per scheduler at
+  // 257 x 300 nothing else hides that latency (the butterfly-by-butterfly version waited for L2 four times).
+  constexpr int NB0 = P::R / P::R0;
+  constexpr int LS0 = P::log2S(0);
+  float2 pre[NB0][P::R0], ch[NB0][P::R0];
 #pragma unroll
-  for (int it = 0; it < P::R / P::R0; it++)
-    fft_butterfly<float, P::R0, -1, LOG2M>(tid + it * P::NT, P::log2S(0), a.tw, ld0, stA);
+  for (int it = 0; it < NB0; it++) {
+    const int b = tid + it * P::NT;
+    const int base = (b >> LS0) * (P::R0 << LS0) + (b & ((1 << LS0) - 1));
+#pragma unroll
+    for (int k = 0; k < P::R0; k++) {
+      const int i = base + (k << LS0);
+      const int ic = min(i, a.nDop - 1);  // unconditional load on a valid row, masked below
+      pre[it][k] = __ldg(a.R + (size_t)ic * a.nDel + col);
+      ch[it][k] = __ldg(a.chirp + ic);
+    }
+  }
+  for (int q = 1; q < a.nParts; q++) {  // fixed order: deterministic
+#pragma unroll
+    for (int it = 0; it < NB0; it++) {
+      const int b = tid + it * P::NT;
+      const int base = (b >> LS0) * (P::R0 << LS0) + (b & ((1 << LS0) - 1));
+#pragma unroll
+      for (int k = 0; k < P::R0; k++) {
+        const int ic = min(base + (k << LS0), a.nDop - 1);
+        pre[it][k] = cadd(pre[it][k], __ldg(a.R + q * plane + (size_t)ic * a.nDel + col));
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < NB0; it++) {
+    const int b = tid + it * P::NT;
+    auto ldp = [&](int i) { return i < a.nDop ? cmul(pre[it][(i >> LS0) & (P::R0 - 1)], ch[it][(i >> LS0) & (P::R0 - 1)]) : zero; };
+    fft_butterfly<float, P::R0, -1, LOG2M>(b, LS0, a.tw, ldp, stA);
+  }
   __syncthreads();
 #pragma unroll 1
   for (int p = 1; p < P::NP - 1; p++) {
@@ -470,18 +494,28 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT) caf_doppler_kernel(DopplerArg
   const float scale = 1.0f / (float)P::M;
   const int shift = a.nDop / 2 + 1;
   auto ldA = [&](int i) { return A[pad(i)]; };
-  auto stO = [&](int m, float2 val) {
-    if (m < a.nDop) {
-      float2 d = cmul(val, __ldg(a.chirp + m));
-      int k = m - shift;
-      if (k < 0) k += a.nDop;
-      a.out[(size_t)k * a.ldOut + blockIdx.x] = make_float2(d.x * scale, d.y * scale);
-    }
-  };
-  constexpr int S0 = 1 << P::log2S(0);
-#pragma unroll 1
-  for (int b = tid; b < P::M / P::R0; b += P::NT) {
-    if ((b & (S0 - 1)) < a.nDop) fft_butterfly<float, P::R0, +1, LOG2M>(b, P::log2S(0), a.tw, ldA, stO);
+  // final inverse pass: the chirp value of every output this thread will write is fetched up front (same reason
+  // as pass 0), butterflies whose outputs all lie beyond nDop are skipped
+  float2 cho[NB0][P::R0];
+#pragma unroll
+  for (int it = 0; it < NB0; it++) {
+    const int b = tid + it * P::NT;
+    const int base = (b >> LS0) * (P::R0 << LS0) + (b & ((1 << LS0) - 1));
+#pragma unroll
+    for (int q = 0; q < P::R0; q++) cho[it][q] = __ldg(a.chirp + min(base + (q << LS0), a.nDop - 1));
+  }
+#pragma unroll
+  for (int it = 0; it < NB0; it++) {
+    const int b = tid + it * P::NT;
+    auto stO = [&](int m, float2 val) {
+      if (m < a.nDop) {
+        float2 d = cmul(val, cho[it][(m >> LS0) & (P::R0 - 1)]);
+        int k = m - shift;
+        if (k < 0) k += a.nDop;
+        a.out[(size_t)k * a.ldOut + blockIdx.x] = make_float2(d.x * scale, d.y * scale);
+      }
+    };
+    if ((b & ((1 << LS0) - 1)) < a.nDop) fft_butterfly<float, P::R0, +1, LOG2M>(b, LS0, a.tw, ldA, stO);
   }
 }
 
