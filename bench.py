@@ -477,6 +477,14 @@ def main():
                                              "ambiguity_processing": round(stage_ms[1], 1),
                                              "detector": round(stage_ms[2], 2)},
                                 "host_cores": os.cpu_count(), "n_detections": n_det}
+        try:  # the reference's SpectrumAnalyser on the same reference channel (blah2.cpp:263-265), for the `spectrum` block
+            from oracle import refpath as R
+            if R.available():
+                t0 = time.perf_counter()
+                R.spectrum_process(sc.x, N, 2000.0)
+                line["cpu_baseline"]["spectrum_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
+        except Exception:
+            pass
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
