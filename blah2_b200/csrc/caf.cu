@@ -442,36 +442,47 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT) caf_doppler_kernel(DopplerArg
   // 257 x 300 nothing else hides that latency (the butterfly-by-butterfly version waited for L2 four times).
   constexpr int NB0 = P::R / P::R0;
   constexpr int LS0 = P::log2S(0);
-  float2 pre[NB0][P::R0], ch[NB0][P::R0];
-#pragma unroll
-  for (int it = 0; it < NB0; it++) {
-    const int b = tid + it * P::NT;
-    const int base = (b >> LS0) * (P::R0 << LS0) + (b & ((1 << LS0) - 1));
-#pragma unroll
-    for (int k = 0; k < P::R0; k++) {
-      const int i = base + (k << LS0);
-      const int ic = min(i, a.nDop - 1);  // unconditional load on a valid row, masked below
-      pre[it][k] = __ldg(a.R + (size_t)ic * a.nDel + col);
-      ch[it][k] = __ldg(a.chirp + ic);
-    }
-  }
-  for (int q = 1; q < a.nParts; q++) {  // fixed order: deterministic
+  if constexpr (NB0 > 1) {
+    float2 pre[NB0][P::R0], ch[NB0][P::R0];
 #pragma unroll
     for (int it = 0; it < NB0; it++) {
       const int b = tid + it * P::NT;
       const int base = (b >> LS0) * (P::R0 << LS0) + (b & ((1 << LS0) - 1));
 #pragma unroll
       for (int k = 0; k < P::R0; k++) {
-        const int ic = min(base + (k << LS0), a.nDop - 1);
-        pre[it][k] = cadd(pre[it][k], __ldg(a.R + q * plane + (size_t)ic * a.nDel + col));
+        const int i = base + (k << LS0);
+        const int ic = min(i, a.nDop - 1);  // unconditional load on a valid row, masked below
+        pre[it][k] = __ldg(a.R + (size_t)ic * a.nDel + col);
+        ch[it][k] = __ldg(a.chirp + ic);
       }
     }
-  }
+    for (int q = 1; q < a.nParts; q++) {  // fixed order: deterministic
 #pragma unroll
-  for (int it = 0; it < NB0; it++) {
-    const int b = tid + it * P::NT;
-    auto ldp = [&](int i) { return i < a.nDop ? cmul(pre[it][(i >> LS0) & (P::R0 - 1)], ch[it][(i >> LS0) & (P::R0 - 1)]) : zero; };
-    fft_butterfly<float, P::R0, -1, LOG2M>(b, LS0, a.tw, ldp, stA);
+      for (int it = 0; it < NB0; it++) {
+        const int b = tid + it * P::NT;
+        const int base = (b >> LS0) * (P::R0 << LS0) + (b & ((1 << LS0) - 1));
+#pragma unroll
+        for (int k = 0; k < P::R0; k++) {
+          const int ic = min(base + (k << LS0), a.nDop - 1);
+          pre[it][k] = cadd(pre[it][k], __ldg(a.R + q * plane + (size_t)ic * a.nDel + col));
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NB0; it++) {
+      const int b = tid + it * P::NT;
+      auto ldp = [&](int i) { return i < a.nDop ? cmul(pre[it][(i >> LS0) & (P::R0 - 1)], ch[it][(i >> LS0) & (P::R0 - 1)]) : zero; };
+      fft_butterfly<float, P::R0, -1, LOG2M>(b, LS0, a.tw, ldp, stA);
+    }
+  } else {  // one radix-16 butterfly per thread: its 16 loads are independent already (measured: preloading costs 9 % here)
+    auto ld0 = [&](int i) {
+      if (i >= a.nDop) return zero;
+      const float2 *p = a.R + (size_t)i * a.nDel + col;
+      float2 r = __ldg(p);
+      for (int q = 1; q < a.nParts; q++) r = cadd(r, __ldg(p + q * plane));  // fixed order: deterministic
+      return cmul(r, __ldg(a.chirp + i));
+    };
+    fft_butterfly<float, P::R0, -1, LOG2M>(tid, LS0, a.tw, ld0, stA);
   }
   __syncthreads();
 #pragma unroll 1
@@ -496,26 +507,38 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT) caf_doppler_kernel(DopplerArg
   auto ldA = [&](int i) { return A[pad(i)]; };
   // final inverse pass: the chirp value of every output this thread will write is fetched up front (same reason
   // as pass 0), butterflies whose outputs all lie beyond nDop are skipped
-  float2 cho[NB0][P::R0];
+  if constexpr (NB0 > 1) {
+    float2 cho[NB0][P::R0];
 #pragma unroll
-  for (int it = 0; it < NB0; it++) {
-    const int b = tid + it * P::NT;
-    const int base = (b >> LS0) * (P::R0 << LS0) + (b & ((1 << LS0) - 1));
+    for (int it = 0; it < NB0; it++) {
+      const int b = tid + it * P::NT;
+      const int base = (b >> LS0) * (P::R0 << LS0) + (b & ((1 << LS0) - 1));
 #pragma unroll
-    for (int q = 0; q < P::R0; q++) cho[it][q] = __ldg(a.chirp + min(base + (q << LS0), a.nDop - 1));
-  }
+      for (int q = 0; q < P::R0; q++) cho[it][q] = __ldg(a.chirp + min(base + (q << LS0), a.nDop - 1));
+    }
 #pragma unroll
-  for (int it = 0; it < NB0; it++) {
-    const int b = tid + it * P::NT;
+    for (int it = 0; it < NB0; it++) {
+      const int b = tid + it * P::NT;
+      auto stO = [&](int m, float2 val) {
+        if (m < a.nDop) {
+          float2 d = cmul(val, cho[it][(m >> LS0) & (P::R0 - 1)]);
+          int k = m - shift;
+          if (k < 0) k += a.nDop;
+          a.out[(size_t)k * a.ldOut + blockIdx.x] = make_float2(d.x * scale, d.y * scale);
+        }
+      };
+      if ((b & ((1 << LS0) - 1)) < a.nDop) fft_butterfly<float, P::R0, +1, LOG2M>(b, LS0, a.tw, ldA, stO);
+    }
+  } else {
     auto stO = [&](int m, float2 val) {
       if (m < a.nDop) {
-        float2 d = cmul(val, cho[it][(m >> LS0) & (P::R0 - 1)]);
+        float2 d = cmul(val, __ldg(a.chirp + m));
         int k = m - shift;
         if (k < 0) k += a.nDop;
         a.out[(size_t)k * a.ldOut + blockIdx.x] = make_float2(d.x * scale, d.y * scale);
       }
     };
-    if ((b & ((1 << LS0) - 1)) < a.nDop) fft_butterfly<float, P::R0, +1, LOG2M>(b, LS0, a.tw, ldA, stO);
+    if ((tid & ((1 << LS0) - 1)) < a.nDop) fft_butterfly<float, P::R0, +1, LOG2M>(tid, LS0, a.tw, ldA, stO);
   }
 }
 

@@ -226,7 +226,7 @@ int b200dd_pipeline_submit_device(b200dd_pipeline *h, const void *d_x, const voi
       if (graph) cudaGraphDestroy(graph);
       cudaGetLastError();
       h->graph_mode = 0;  // something in the chain is not capturable here: stay eager from now on
-      return rc != B200DD_OK ? rc : pipeline_enqueue_device(h, d_x, d_y, n, d_map, st);
+      return pipeline_enqueue_device(h, d_x, d_y, n, d_map, st);  // (a genuine error shows up again here)
     }
     cudaGraphExec_t exec = nullptr;
     const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);

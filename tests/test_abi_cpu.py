@@ -40,9 +40,12 @@ def test_host_only_entry_points():
 def test_compute_fails_loudly_without_gpu():
     if capi.device_count() > 0:
         pytest.skip("a GPU is present")
-    from blah2_b200.process import Ambiguity, WienerHopf, CfarDetector1D
+    from blah2_b200.process import Ambiguity, WienerHopf, CfarDetector1D, SpectrumAnalyser
     with pytest.raises(capi.B200ddError) as e:
         Ambiguity(-10, 300, -300, 300, 2000000, 1000000)
+    assert e.value.code == capi.ERR_CUDA
+    with pytest.raises(capi.B200ddError) as e:
+        SpectrumAnalyser(2000000, 2000.0)
     assert e.value.code == capi.ERR_CUDA
     with pytest.raises(capi.B200ddError):
         WienerHopf(-10, 400, 100000)
@@ -59,6 +62,12 @@ def test_argument_validation_without_gpu():
     assert lib.b200dd_wh_create(0, 0, 1000, -1, C.byref(h)) == capi.ERR_GEOMETRY     # zero taps
     assert lib.b200dd_wh_create(0, 5000, 100000, -1, C.byref(h)) == capi.ERR_GEOMETRY  # too many taps
     assert b"taps" in lib.b200dd_last_error()
+    # SpectrumAnalyser: where the reference divides by zero (bandwidth > n, SpectrumAnalyser.cpp:17) or converts an
+    # out-of-range double (bandwidth <= 0 / NaN, :16) the ABI answers ERR_GEOMETRY before touching a device
+    assert lib.b200dd_spectrum_create(1000, 2000.0, -1, C.byref(h)) == capi.ERR_GEOMETRY
+    assert lib.b200dd_spectrum_create(1000, -5.0, -1, C.byref(h)) == capi.ERR_GEOMETRY
+    assert lib.b200dd_spectrum_create(1000, float("nan"), -1, C.byref(h)) == capi.ERR_GEOMETRY
+    assert lib.b200dd_spectrum_create(1000, 100.0, -1, None) == capi.ERR_ARG
 
 
 def test_product_never_imports_the_oracle():
