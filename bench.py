@@ -47,13 +47,15 @@ WORKLOAD = ("cfg2: WienerHopf(410 taps)+Ambiguity(300 delay x 257 Doppler)+set_m
 KERNELS_PER_STEP = 4 + 2 + 2 + 3 + 1  # wh(corr,solve,wspec,apply) caf(range,doppler) metrics(2) cfar(flag,scan,emit) tail(centroid+interp)
 
 
-def ncu_traffic(kernel="caf_range_kernel"):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
+def ncu_traffic(kernel="caf_range_", capture="cfg2"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the range kernel (caf_range_kernel or
+    caf_range_grouped_kernel, whichever the plan uses) in the config-2 capture of the committed ncu --set full
     extract (profiles/r01z_kernels.json), or None."""
     p = os.path.join(ROOT, "profiles", "r01z_kernels.json")
     try:
-        for k in json.load(open(p))["kernels"]:
-            if kernel in k["name"]:
+        ks = json.load(open(p))["kernels"]
+        for k in ks:
+            if kernel in k["name"] and capture in str(k.get("capture", capture)):
                 return int(k["dram_bytes_read"] + k["dram_bytes_write"])
     except Exception:
         pass
@@ -439,7 +441,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "cpis_per_step_per_gpu": 1, "parallelism": f"independent CPIs x{world}",
                    "l2": f"{NB} distinct CPI input sets rotated ({NB * 32} MB > L2)", "cpis_in_flight": NPIPE,
-                   "range_fft": f"M={g.range_fft_len} x{g.range_segments} segments, hop {g.range_hop}",
+                   "range_fft": f"M={g.range_fft_len} x{g.range_segments} segments, hop {g.range_hop}, "
+                                f"{g.range_groups} warp group(s) x {g.range_parts} part(s) per batch",
                    "doppler_fft": f"Bluestein M2={g.doppler_fft_len}"},
         "e2e": {"value": round(e2e_value, 2), "unit": "Msamples/s", "h2d_bytes_per_step": 2 * 16 * N,
                 "d2h_bytes_per_step": 16 * cells + 3 * 8 * int(r_e2e["detections"].get_nDetections()) + 32,
@@ -452,7 +455,7 @@ def main():
                              "n_detections": int(r_i16["detections"].get_nDetections())},
         "gpu_launches": KERNELS_PER_STEP * args.steps,
         "clocks": clocks,
-        "roofline": {"kernel": "caf_range_kernel", "bound": "hbm", "achieved": round(ach_range, 1), "peak": peak,
+        "roofline": {"kernel": "caf_range_grouped_kernel" if g.range_groups > 1 else "caf_range_kernel", "bound": "hbm", "achieved": round(ach_range, 1), "peak": peak,
                      "unit": "GB/s", "frac": round(ach_range / peak, 4), "traffic": ncu_traffic(), "peak_source": peak_src,
                      "algorithmic_bytes": bytes_range, "kernel_ms": round(kms["range"], 5),
                      "caf_total": {"ms": round(kms["range"] + kms["doppler"], 5),

@@ -42,7 +42,7 @@ class CafGeometry(C.Structure):
     _fields_ = [("n_delay_bins", C.c_uint32), ("n_doppler_bins", C.c_uint32), ("n_corr", C.c_uint32),
                 ("nfft", C.c_uint32), ("n_used", C.c_uint32), ("cpi", C.c_double), ("doppler_middle", C.c_double),
                 ("range_fft_len", C.c_uint32), ("range_segments", C.c_uint32), ("range_hop", C.c_uint32),
-                ("doppler_fft_len", C.c_uint32), ("range_parts", C.c_uint32)]
+                ("doppler_fft_len", C.c_uint32), ("range_parts", C.c_uint32), ("range_groups", C.c_uint32)]
 
 
 class DetParams(C.Structure):

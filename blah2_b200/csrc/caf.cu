@@ -993,6 +993,7 @@ int b200dd_caf_get_geometry(const b200dd_caf *h, b200dd_caf_geometry *out) {
   out->range_segments = (uint32_t)h->nSeg;
   out->range_hop = (uint32_t)h->L;
   out->range_parts = (uint32_t)h->nParts;
+  out->range_groups = (uint32_t)h->nGroups;
   out->doppler_fft_len = 1u << h->log2m2;
   return B200DD_OK;
 }

@@ -110,7 +110,8 @@ typedef struct {
   uint32_t range_segments;  /* segments per batch */
   uint32_t range_hop;       /* new samples per segment */
   uint32_t doppler_fft_len; /* Bluestein length M2 */
-  uint32_t range_parts;     /* CTAs per batch (segment groups summed by the Doppler kernel) */
+  uint32_t range_parts;     /* CTAs per batch (partial range matrices summed by the Doppler kernel) */
+  uint32_t range_groups;    /* warp groups per range CTA, each transforming its own segments of the batch */
 } b200dd_caf_geometry;
 
 B200DD_API int b200dd_caf_create(const b200dd_caf_params *params, b200dd_caf **out);
