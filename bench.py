@@ -233,6 +233,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the device chain as CUDA graphs (prepare_device)")
     ap.add_argument("--streams", type=int, default=6, help="CPIs in flight per GPU (independent pipelines on their own streams)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -297,11 +298,13 @@ def main():
             pipes[p].submit_device(xs[i % NB], ys[i % NB], dmaps[p], streams[p].cuda_stream)
 
     # ---- device-resident throughput: a stream of independent CPIs, NPIPE in flight ----
-    # plan creation (untimed, before the warm-up steps): the CUDA graph of the chain for every (input set, pipeline)
-    # pair the loop below will submit
-    for i in range(NB * NPIPE):   # submit(i) uses (i % NB, i % NPIPE): the pattern repeats after lcm(NB, NPIPE) steps
-        p = i % NPIPE
-        pipes[p].prepare_device(xs[i % NB], ys[i % NB], dmaps[p], streams[p].cuda_stream)
+    # --graph: plan creation (untimed, before the warm-up steps) = the CUDA graph of the chain for every (input set,
+    # pipeline) pair the loop below submits.  Off by default: with 50 CPIs enqueued ahead eager launches measured 3 %
+    # faster than graph replay (profiles/r01_summary.md s6)
+    if args.graph:
+        for i in range(NB * NPIPE):   # submit(i) uses (i % NB, i % NPIPE): the pattern repeats after lcm(NB, NPIPE) steps
+            p = i % NPIPE
+            pipes[p].prepare_device(xs[i % NB], ys[i % NB], dmaps[p], streams[p].cuda_stream)
     for i in range(args.warmup):
         submit(i)
     for p in range(NPIPE):
@@ -440,7 +443,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (CAF) / f64 (WienerHopf, detection)",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "cpis_per_step_per_gpu": 1, "parallelism": f"independent CPIs x{world}",
-                   "l2": f"{NB} distinct CPI input sets rotated ({NB * 32} MB > L2)", "cpis_in_flight": NPIPE,
+                   "l2": f"{NB} distinct CPI input sets rotated ({NB * 32} MB > L2)", "cpis_in_flight": NPIPE, "submission": "cuda graph replay" if args.graph else "eager launches",
                    "range_fft": f"M={g.range_fft_len} x{g.range_segments} segments, hop {g.range_hop}, "
                                 f"{g.range_groups} warp group(s) x {g.range_parts} part(s) per batch",
                    "doppler_fft": f"Bluestein M2={g.doppler_fft_len}"},

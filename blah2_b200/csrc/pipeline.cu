@@ -73,7 +73,9 @@ struct b200dd_pipeline {
     cudaGraphExec_t exec = nullptr;
   };
   std::vector<GraphEntry> graphs;
-  int graph_mode = 1;  // B200DD_PIPELINE_GRAPH=0 disables
+  // 2 (default): replay only triples recorded by b200dd_pipeline_prepare_device; 1 (B200DD_PIPELINE_GRAPH=1): also
+  // record any triple on its second use; 0 (B200DD_PIPELINE_GRAPH=0): every submit eager, prepare is a no-op
+  int graph_mode = 2;
 };
 
 extern "C" {
@@ -86,7 +88,7 @@ int b200dd_pipeline_create(const b200dd_pipeline_params *params, b200dd_pipeline
   b200dd_pipeline *h = new (std::nothrow) b200dd_pipeline();
   if (!h) return arg_fail("b200dd_pipeline_create: out of host memory");
   h->p = *params;
-  if (const char *e = getenv("B200DD_PIPELINE_GRAPH")) h->graph_mode = atoi(e) != 0;
+  if (const char *e = getenv("B200DD_PIPELINE_GRAPH")) h->graph_mode = atoi(e) != 0 ? 1 : 0;
   auto fail = [&](int rc) { b200dd_pipeline_destroy(h); return rc; };
   int dev = params->caf.device;
   if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaGetDevice", __FILE__, __LINE__));
@@ -191,11 +193,12 @@ static void pipeline_drop_graphs(b200dd_pipeline *h) {
   h->graphs.clear();
 }
 
-// A CPI is 13+ kernel launches; with several CPIs in flight (and several ranks sharing one host) the launch path
-// of the single submitting thread becomes the limit.  The chain's arguments only depend on the caller's three
-// device pointers, so the second submit with the same triple is recorded by stream capture (everything below runs
-// on `st`, no allocation, attribute call or host copy after the first eager run) and later submits replay the
-// instantiated graph with ONE cudaGraphLaunch.  B200DD_PIPELINE_GRAPH=0 keeps every submit eager.
+// A CPI is 12+ kernel launches on the single submitting thread.  The chain's arguments only depend on the caller's
+// three device pointers, so a triple can be recorded by stream capture (everything below runs on `st`; no
+// allocation, attribute call or host copy after the first eager run) and replayed with ONE cudaGraphLaunch.
+// Measured (profiles/r01_summary.md s6): in a submit -> fetch -> submit loop replay is 7-20 % faster per CPI (1-8
+// pipelines); in bench.py's deep queue (50 CPIs enqueued ahead on 6 streams) it is 3 % SLOWER than eager launches,
+// so replay is opt-in per triple (b200dd_pipeline_prepare_device), or for every triple with B200DD_PIPELINE_GRAPH=1.
 int b200dd_pipeline_submit_device(b200dd_pipeline *h, const void *d_x, const void *d_y, uint32_t n, void *d_map,
                                   void *stream) {
   if (!h || !d_x || !d_y) return arg_fail("b200dd_pipeline_submit_device: null argument");
@@ -207,7 +210,7 @@ int b200dd_pipeline_submit_device(b200dd_pipeline *h, const void *d_x, const voi
   for (auto &e : h->graphs)
     if (e.x == d_x && e.y == d_y && e.map == d_map && e.n == n) { hit = &e; break; }
   if (!hit) {  // first sight: eager (sets function attributes, uploads the axes, sizes scratch buffers)
-    if (h->graphs.size() < 64) {
+    if (h->graph_mode == 1 && h->graphs.size() < 64) {
       b200dd_pipeline::GraphEntry e;
       e.x = d_x; e.y = d_y; e.map = d_map; e.n = n;
       h->graphs.push_back(e);
@@ -249,14 +252,18 @@ int b200dd_pipeline_prepare_device(b200dd_pipeline *h, const void *d_x, const vo
   if (!h->graph_mode) return B200DD_OK;
   DeviceGuard guard(h->device);
   void *st = stream ? stream : (void *)h->stream;
-  for (int pass = 0; pass < 2; pass++) {  // first sight runs the chain eagerly, second sight records it
+  const int mode = h->graph_mode;
+  h->graph_mode = 1;  // record on second sight, for the two submits below
+  int rc = B200DD_OK;
+  for (int pass = 0; pass < 2 && rc == B200DD_OK; pass++) {  // first sight runs the chain eagerly, second sight records it
     bool ready = false;
     for (auto &e : h->graphs)
       if (e.x == d_x && e.y == d_y && e.map == d_map && e.n == n && e.exec) ready = true;
     if (ready) break;
-    const int rc = b200dd_pipeline_submit_device(h, d_x, d_y, n, d_map, st);
-    if (rc != B200DD_OK) return rc;
+    rc = b200dd_pipeline_submit_device(h, d_x, d_y, n, d_map, st);
   }
+  if (h->graph_mode != 0) h->graph_mode = mode;  // (0 = the chain turned out not to be capturable: stay eager)
+  if (rc != B200DD_OK) return rc;
   B2_CUDA(cudaStreamSynchronize((cudaStream_t)st));
   return B200DD_OK;
 }

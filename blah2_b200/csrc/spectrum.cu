@@ -21,6 +21,7 @@
 #include "common.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <type_traits>
 #include <vector>
@@ -85,9 +86,10 @@ __global__ void __launch_bounds__(FOLD_THREADS) spec_fold_kernel(const TIN *__re
 // load is 512 contiguous bytes and FOLD_UNROLL x 16 bytes are in flight per thread -- what it takes to keep HBM busy
 // with 8 CTAs of 4 warps per SM (the 8-byte version stops at 60 % of the DRAM peak, profiles/r01_summary.md s6).
 // Same sums in the same order as the scalar kernel: results are bit-identical.
-__global__ void __launch_bounds__(FOLD_THREADS, 6) spec_fold2_kernel(const float2 *__restrict__ x, const double2 *__restrict__ t1,
-                                                                  double2 *__restrict__ part, uint32_t nSpec, uint32_t dec,
-                                                                  uint32_t rowsPerChunk) {
+template <int U, int MINB>
+__global__ void __launch_bounds__(FOLD_THREADS, MINB) spec_fold2_kernel(const float2 *__restrict__ x, const double2 *__restrict__ t1,
+                                                                     double2 *__restrict__ part, uint32_t nSpec, uint32_t dec,
+                                                                     uint32_t rowsPerChunk) {
   const uint32_t r = 2u * (blockIdx.x * FOLD_THREADS + threadIdx.x);
   if (r >= nSpec) return;  // nSpec is even: r + 1 < nSpec as well
   const uint32_t q0 = blockIdx.y * rowsPerChunk;
@@ -96,25 +98,25 @@ __global__ void __launch_bounds__(FOLD_THREADS, 6) spec_fold2_kernel(const float
   const float4 *p = reinterpret_cast<const float4 *>(x + (size_t)q0 * nSpec + r);
   const size_t rowStride = nSpec / 2;  // in float4
   uint32_t q = q0;
-  for (; q + FOLD_UNROLL <= q1; q += FOLD_UNROLL) {
-    float4 v[FOLD_UNROLL];
+  for (; q + U <= q1; q += U) {
+    float4 v[U];
 #pragma unroll
-    for (int u = 0; u < FOLD_UNROLL; u++) v[u] = __ldg(p + (size_t)u * rowStride);
+    for (int u = 0; u < U; u++) v[u] = __ldg(p + (size_t)u * rowStride);
 #pragma unroll
-    for (int u = 0; u < FOLD_UNROLL; u++) {
+    for (int u = 0; u < U; u++) {
       const double2 w = __ldg(t1 + q + u);
       zfma(acc0, make_double2((double)v[u].x, (double)v[u].y), w);
       zfma(acc1, make_double2((double)v[u].z, (double)v[u].w), w);
     }
-    p += (size_t)FOLD_UNROLL * rowStride;
+    p += (size_t)U * rowStride;
   }
   if (q < q1) {
-    float4 v[FOLD_UNROLL];
+    float4 v[U];
 #pragma unroll
-    for (int u = 0; u < FOLD_UNROLL; u++)
+    for (int u = 0; u < U; u++)
       if (q + u < q1) v[u] = __ldg(p + (size_t)u * rowStride);
 #pragma unroll
-    for (int u = 0; u < FOLD_UNROLL; u++)
+    for (int u = 0; u < U; u++)
       if (q + u < q1) {
         const double2 w = __ldg(t1 + q + u);
         zfma(acc0, make_double2((double)v[u].x, (double)v[u].y), w);
@@ -259,8 +261,9 @@ template <class TIN> int run_spectrum(b200dd_spectrum *h, const TIN *d_x, double
     vec2 = h->nSpectrum % 2 == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0;
   if (vec2) {
     const dim3 gridF((h->nSpectrum / 2 + FOLD_THREADS - 1) / FOLD_THREADS, h->nChunks2);
-    spec_fold2_kernel<<<gridF, FOLD_THREADS, 0, st>>>((const float2 *)d_x, h->d_t1, h->d_part, h->nSpectrum, h->decimation,
-                                                     h->rowsPerChunk2);
+    // 8 rows in flight per thread, 6 CTAs per SM: measured best (16 x 4: 37.4 us, 4 x 10: 35.4 us, this: 32.9 us at 2e7)
+    spec_fold2_kernel<FOLD_UNROLL, 6><<<gridF, FOLD_THREADS, 0, st>>>((const float2 *)d_x, h->d_t1, h->d_part, h->nSpectrum,
+                                                                      h->decimation, h->rowsPerChunk2);
   } else {
     const dim3 gridF((h->nSpectrum + FOLD_THREADS - 1) / FOLD_THREADS, h->nChunks);
     spec_fold_kernel<TIN><<<gridF, FOLD_THREADS, 0, st>>>(d_x, h->d_t1, h->d_part, h->nSpectrum, h->decimation, h->rowsPerChunk);
@@ -336,11 +339,12 @@ int b200dd_spectrum_create(uint32_t n, double bandwidth, int32_t device, b200dd_
   h->rowsPerChunk = rows;
   h->nChunks = (decimation + rows - 1) / rows;
   {
+    const uint32_t perSm = 6u;  // resident CTAs per SM of spec_fold2_kernel (80 registers)
     const uint32_t colTiles2 = (nSpectrum / 2 + FOLD_THREADS - 1) / FOLD_THREADS;
-    uint32_t want2 = (148u * 6u + (colTiles2 ? colTiles2 : 1) - 1) / (colTiles2 ? colTiles2 : 1);  // 6 resident CTAs per SM (80 registers)
+    uint32_t want2 = (148u * perSm + (colTiles2 ? colTiles2 : 1) - 1) / (colTiles2 ? colTiles2 : 1);
     if (want2 > 256) want2 = 256;
     uint32_t rows2 = (decimation + want2 - 1) / want2;
-    if (rows2 < (uint32_t)FOLD_UNROLL) rows2 = FOLD_UNROLL;
+    if (rows2 < 8u) rows2 = 8u;
     h->rowsPerChunk2 = rows2;
     h->nChunks2 = (decimation + rows2 - 1) / rows2;
   }

@@ -45,7 +45,8 @@
  *   B200DD_WH_LOG2M, B200DD_WH_CORR_LOG2M, B200DD_WH_APPLY_LOG2M, B200DD_WH_RADIX   WienerHopf FFT plans
  *   B200DD_WH_SOLVE_SHORT=0                  generic Toeplitz solve kernel also for <= 992 taps
  *   B200DD_WH_REUSE=1                        filter stage reuses the correlation stage's window spectra
- *   B200DD_PIPELINE_GRAPH=0                  b200dd_pipeline_submit_device launches every kernel itself (no CUDA graph)
+ *   B200DD_PIPELINE_GRAPH=1 / 0              CUDA-graph replay of the device chain for every buffer triple / never
+ *                                            (default: only triples given to b200dd_pipeline_prepare_device)
  * None of them changes results beyond the rounding of a different FFT factorisation.
  */
 #ifndef B200DD_H
@@ -364,11 +365,12 @@ B200DD_API int b200dd_pipeline_submit_host_rspduo(b200dd_pipeline *h, const int1
  * (nullable) receives the float2 map.  Results stay on the device until b200dd_pipeline_fetch. */
 B200DD_API int b200dd_pipeline_submit_device(b200dd_pipeline *h, const void *d_x, const void *d_y, uint32_t n,
                                              void *d_map, void *stream);
-/* Plan creation for the device path: b200dd_pipeline_submit_device replays a CUDA graph of the whole chain once a
- * (d_x, d_y, d_map) triple has been seen twice (first use eager, second use recorded; B200DD_PIPELINE_GRAPH=0 keeps
- * every submit eager).  This call does both steps now -- it runs the chain on the buffers' current contents, records
- * and instantiates the graph and synchronises the stream -- so that later submits of the triple are one
- * cudaGraphLaunch each.  Optional; results are identical either way. */
+/* Plan creation for the device path (optional): records the whole chain for this (d_x, d_y, d_map) triple as a CUDA
+ * graph -- it runs the chain once on the buffers' current contents, captures and instantiates it and synchronises
+ * the stream -- after which b200dd_pipeline_submit_device on the same triple is ONE cudaGraphLaunch.  Results are
+ * identical either way.  Worth it for submit -> fetch -> submit loops over a fixed ring of buffers (7-20 % per CPI);
+ * with many CPIs enqueued ahead eager launches measured 3 % faster, hence opt-in.  B200DD_PIPELINE_GRAPH=1 records
+ * every triple on its second use without this call, B200DD_PIPELINE_GRAPH=0 turns replay off altogether. */
 B200DD_API int b200dd_pipeline_prepare_device(b200dd_pipeline *h, const void *d_x, const void *d_y, uint32_t n,
                                               void *d_map, void *stream);
 B200DD_API int b200dd_pipeline_fetch(b200dd_pipeline *h, b200dd_cpi_result *result, double *o_delay,

@@ -115,8 +115,8 @@ def test_rspduo_int16_ingest_matches_complex128_entry(relerr):
 
 
 def test_graph_replay_of_the_device_chain_is_bit_identical(monkeypatch):
-    """b200dd_pipeline_submit_device records the chain for a (d_x, d_y, d_map) triple on its second use and replays
-    the CUDA graph afterwards: eager (B200DD_PIPELINE_GRAPH=0), first, recorded and replayed submissions must give
+    """With B200DD_PIPELINE_GRAPH=1 b200dd_pipeline_submit_device records the chain for a (d_x, d_y, d_map) triple on
+    its second use and replays the CUDA graph afterwards: eager (B200DD_PIPELINE_GRAPH=0), first, recorded and replayed submissions must give
     bit-identical maps, detections and metrics -- also when two input sets alternate, when the CONTENT of a buffer
     changes between replays, and for a CPI whose filter fails (status word read after the replay)."""
     import torch
@@ -160,15 +160,20 @@ def test_graph_replay_of_the_device_chain_is_bit_identical(monkeypatch):
 
 def test_prepare_device_records_the_graph_up_front(monkeypatch):
     """b200dd_pipeline_prepare_device = plan creation: afterwards the FIRST submit of the triple is already a replay and
-    gives the eager result bit for bit; with B200DD_PIPELINE_GRAPH=0 it is a no-op."""
+    gives the eager result bit for bit -- in the default mode (replay only for prepared triples) and with
+    B200DD_PIPELINE_GRAPH=1; with B200DD_PIPELINE_GRAPH=0 it is a no-op.  In the default mode a triple that was never
+    prepared stays eager however often it is submitted."""
     import torch
     d, geom, det, sc = _chain_fixture()
     clutter = tuple(int(v) for v in d["clutter"])
     dx = torch.from_numpy(sc.x.astype(np.complex64)).cuda()
     dy = torch.from_numpy(sc.y.astype(np.complex64)).cuda()
     outs = {}
-    for mode in ("0", "1"):
-        monkeypatch.setenv("B200DD_PIPELINE_GRAPH", mode)
+    for mode in ("0", "1", None):
+        if mode is None:
+            monkeypatch.delenv("B200DD_PIPELINE_GRAPH", raising=False)
+        else:
+            monkeypatch.setenv("B200DD_PIPELINE_GRAPH", mode)
         pipe = Pipeline(*geom[:6], roundHamming=True, clutter=clutter, detection=det, spectrum_bandwidth=2000.0)
         dmap = torch.zeros((pipe.geometry.n_doppler_bins, pipe.geometry.n_delay_bins), dtype=torch.complex64, device="cuda")
         scratch = dx.clone()
@@ -178,6 +183,13 @@ def test_prepare_device_records_the_graph_up_front(monkeypatch):
         pipe.submit_device(scratch, dy, dmap)
         r = pipe.fetch()
         outs[mode] = (dmap.cpu().numpy().copy(), r["noisePower"], r["detections"].delay.copy(), pipe.fetch_spectrum())
+        if mode is None:                            # an unprepared triple: eager, three times over
+            other = torch.zeros_like(dmap)
+            for _ in range(3):
+                pipe.submit_device(dx, dy, other)
+                pipe.fetch()
+            assert np.array_equal(other.cpu().numpy(), outs[mode][0])
     assert np.abs(outs["0"][0]).max() > 0
-    assert np.array_equal(outs["0"][0], outs["1"][0]) and outs["0"][1] == outs["1"][1]
-    assert np.array_equal(outs["0"][2], outs["1"][2]) and np.array_equal(outs["0"][3], outs["1"][3])
+    for mode in ("1", None):
+        assert np.array_equal(outs["0"][0], outs[mode][0]) and outs["0"][1] == outs[mode][1]
+        assert np.array_equal(outs["0"][2], outs[mode][2]) and np.array_equal(outs["0"][3], outs[mode][3])

@@ -75,7 +75,7 @@ def main(steps=24):
         out[f"device_eager_x{npipe}"] = round(loop(pipes, lambda p, i: p.submit_device(dx, dy), steps), 4)
         for p in pipes:
             p.close()
-        os.environ["B200DD_PIPELINE_GRAPH"] = "1"
+        os.environ["B200DD_PIPELINE_GRAPH"] = "1"   # record every triple on its second use (the warm-up of loop())
         pipes = [Pipeline(**bench.GEOM, clutter=bench.CLUTTER, detection=bench.DET, device=0) for _ in range(npipe)]
         g = pipes[0].geometry
         hmaps = [torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex128).pin_memory() for _ in range(npipe)]
