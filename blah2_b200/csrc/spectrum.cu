@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(32 * RED_WARPS) spec_reduce_kernel(const doubl
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t r = blockIdx.x * 32 + lane;
   double2 acc = make_double2(0.0, 0.0);
+  double2 ph = make_double2(1.0, 0.0);
+  if (w == 0 && r < nSpec) ph = __ldg(t2 + r);  // issued with the partial sums: one memory round trip, not two
   if (r < nSpec) {
     uint32_t c = w;
     for (; c + 3 * RED_WARPS < nChunks; c += 4 * RED_WARPS) {
@@ -160,7 +162,6 @@ __global__ void __launch_bounds__(32 * RED_WARPS) spec_reduce_kernel(const doubl
     double2 t = s[0][lane];
 #pragma unroll
     for (int k = 1; k < RED_WARPS; k++) { t.x += s[k][lane].x; t.y += s[k][lane].y; }
-    const double2 ph = __ldg(t2 + r);
     g[r] = make_double2(t.x * ph.x - t.y * ph.y, t.x * ph.y + t.y * ph.x);
   }
 }
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(32 * RED_WARPS) spec_reduce_kernel(const doubl
 // shared-memory table: 745 k bank conflicts per launch on the scattered 16-byte reads, 13.5 us (profiles/
 // r01_summary.md s6); the running product needs no table reads in the loop.  SMEM: g staged in shared memory
 // (nSpec <= 12288; reads are warp-broadcasts), else read through L1.
-constexpr int DFT_RESEED = 16;  // in terms per chain
+constexpr int DFT_RESEED = 64;  // in terms per chain (no re-seed at all below 8192 bins)
 constexpr int DFT_ILP = 4;
 
 template <bool SMEM>
@@ -181,6 +182,23 @@ __global__ void __launch_bounds__(DFT_THREADS) spec_dft_kernel(const double2 *__
                                                                double2 *__restrict__ out, uint32_t nSpec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double2 red[DFT_SLICES][DFT_OUT];
+  const int ml = threadIdx.x % DFT_OUT, sl = threadIdx.x / DFT_OUT;
+  const uint32_t m = blockIdx.x * DFT_OUT + ml;
+  const uint32_t mm = m < nSpec ? m : 0;  // out-of-range outputs compute bin 0 and drop it
+  // DFT_ILP independent chains per thread (terms r = sl + 32 c + 32 DFT_ILP j, c < DFT_ILP): one chain is a
+  // 16-clock dependent DMUL -> DFMA recurrence per term.  The phase seeds are requested BEFORE g is staged so
+  // that both memory round trips overlap (the kernel is a few round trips long, not compute-bound).
+  constexpr uint32_t STRIDE = DFT_SLICES * DFT_ILP;
+  const uint32_t step = (uint32_t)(((uint64_t)STRIDE * mm) % nSpec);
+  const double2 wstep = __ldg(wtab + step);
+  uint32_t idx[DFT_ILP];
+  double2 w[DFT_ILP], a[DFT_ILP];
+#pragma unroll
+  for (int c = 0; c < DFT_ILP; c++) {
+    idx[c] = (uint32_t)(((uint64_t)(sl + DFT_SLICES * c) * mm) % nSpec);
+    w[c] = __ldg(wtab + idx[c]);
+    a[c] = make_double2(0.0, 0.0);
+  }
   const double2 *gp = g;
   if constexpr (SMEM) {
     double2 *sg = reinterpret_cast<double2 *>(smem_raw);
@@ -188,26 +206,11 @@ __global__ void __launch_bounds__(DFT_THREADS) spec_dft_kernel(const double2 *__
     __syncthreads();
     gp = sg;
   }
-  const int ml = threadIdx.x % DFT_OUT, sl = threadIdx.x / DFT_OUT;
-  const uint32_t m = blockIdx.x * DFT_OUT + ml;
   double2 acc = make_double2(0.0, 0.0);
-  if (m < nSpec) {
-    // DFT_ILP independent chains per thread (terms r = sl + 32 c + 32 DFT_ILP j, c < DFT_ILP): one chain is a
-    // 16-clock dependent DMUL -> DFMA recurrence per term, which left the FP64 pipe 23 % busy
-    constexpr uint32_t STRIDE = DFT_SLICES * DFT_ILP;
-    const uint32_t step = (uint32_t)(((uint64_t)STRIDE * m) % nSpec);
-    const double2 wstep = __ldg(wtab + step);
-    uint32_t idx[DFT_ILP];
-    double2 w[DFT_ILP], a[DFT_ILP];
-#pragma unroll
-    for (int c = 0; c < DFT_ILP; c++) {
-      idx[c] = (uint32_t)(((uint64_t)(sl + DFT_SLICES * c) * m) % nSpec);
-      w[c] = __ldg(wtab + idx[c]);
-      a[c] = make_double2(0.0, 0.0);
-    }
+  {
     int since = 0;
     for (uint32_t r0 = sl; r0 < nSpec; r0 += STRIDE) {
-      const bool reseed = ++since == DFT_RESEED;
+      const bool reseed = ++since == DFT_RESEED && r0 + STRIDE < nSpec;
       if (reseed) since = 0;
 #pragma unroll
       for (int c = 0; c < DFT_ILP; c++) {
