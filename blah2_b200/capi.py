@@ -75,6 +75,7 @@ SIGNATURES = [
     ("b200dd_device_name", C.c_int, [C.c_int, C.c_char_p, C.c_int]),
     ("b200dd_next_hamming", C.c_uint32, [C.c_uint32]),
     ("b200dd_caf_create", C.c_int, [C.POINTER(CafParams), C.POINTER(_VP)]),
+    ("b200dd_caf_plan", C.c_int, [C.POINTER(CafParams), C.POINTER(CafGeometry), _VP, C.c_uint32, _VP, C.c_uint32]),
     ("b200dd_caf_destroy", None, [_VP]),
     ("b200dd_caf_get_geometry", C.c_int, [_VP, C.POINTER(CafGeometry)]),
     ("b200dd_caf_get_axes", C.c_int, [_VP, _VP, _VP]),
@@ -113,6 +114,7 @@ SIGNATURES = [
     ("b200dd_det_interpolate_host", C.c_int, [_VP, _VP, _VP, _VP, C.c_uint32, _VP, C.c_uint32, C.c_uint32, _VP, _VP,
                                               C.c_double, _VP, _VP, _VP, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("b200dd_spectrum_create", C.c_int, [C.c_uint32, C.c_double, C.c_int32, C.POINTER(_VP)]),
+    ("b200dd_spectrum_plan", C.c_int, [C.c_uint32, C.c_double, C.POINTER(SpectrumGeometry), _VP, C.c_uint32]),
     ("b200dd_spectrum_destroy", None, [_VP]),
     ("b200dd_spectrum_get_geometry", C.c_int, [_VP, C.POINTER(SpectrumGeometry)]),
     ("b200dd_spectrum_get_frequency", C.c_int, [_VP, _VP, C.c_uint32]),
@@ -179,6 +181,29 @@ def ptr(a):
     if hasattr(a, "data_ptr"):
         return C.c_void_p(a.data_ptr())
     raise TypeError(type(a))
+
+
+def caf_plan(delayMin, delayMax, dopplerMin, dopplerMax, fs, n, roundHamming=False, device=-1):
+    """Host-only: (CafGeometry, delay axis, doppler axis) as b200dd_caf_create would set them up."""
+    lib = load()
+    p = CafParams(int(delayMin), int(delayMax), int(dopplerMin), int(dopplerMax), int(fs), int(n),
+                  int(bool(roundHamming)), int(device))
+    g = CafGeometry()
+    check(lib.b200dd_caf_plan(C.byref(p), C.byref(g), None, 0, None, 0))
+    delay = np.empty(g.n_delay_bins, dtype=np.int32)
+    doppler = np.empty(g.n_doppler_bins, dtype=np.float64)
+    check(lib.b200dd_caf_plan(C.byref(p), C.byref(g), ptr(delay), delay.shape[0], ptr(doppler), doppler.shape[0]))
+    return g, delay, doppler
+
+
+def spectrum_plan(n, bandwidth):
+    """Host-only: (SpectrumGeometry, frequency vector) as b200dd_spectrum_create would set them up."""
+    lib = load()
+    g = SpectrumGeometry()
+    check(lib.b200dd_spectrum_plan(int(n), float(bandwidth), C.byref(g), None, 0))
+    f = np.empty(g.n_frequency, dtype=np.float64)
+    check(lib.b200dd_spectrum_plan(int(n), float(bandwidth), C.byref(g), ptr(f), f.shape[0]))
+    return g, f
 
 
 def device_count() -> int:

@@ -430,7 +430,7 @@ struct DopplerArgs {
 template <int LOG2M>
 __global__ void __launch_bounds__(Plan<LOG2M>::NT) caf_doppler_kernel(DopplerArgs a) {
   using P = Plan<LOG2M>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float2 *A = reinterpret_cast<float2 *>(smem_raw);
   const int tid = threadIdx.x;
   const int col = a.col0 + blockIdx.x;
@@ -557,7 +557,7 @@ __global__ void caf_sum_parts_kernel(const float2 *__restrict__ parts, int nPart
 template <int LOG2M>
 __global__ void __launch_bounds__(Plan<LOG2M>::NT) fft_forward_kernel(const float2 *in, float2 *out, const float2 *tw) {
   using P = Plan<LOG2M>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float2 *A = reinterpret_cast<float2 *>(smem_raw);
   const int tid = threadIdx.x;
   auto ld0 = [&](int i) { return in[i]; };
@@ -915,35 +915,57 @@ extern "C" {
 
 uint32_t b200dd_next_hamming(uint32_t value) { return next_hamming_host(value); }
 
-int b200dd_caf_create(const b200dd_caf_params *params, b200dd_caf **out) {
-  if (!params || !out) return arg_fail("b200dd_caf_create: null argument");
-  *out = nullptr;
+// host half of b200dd_caf_create: argument checks, the Ambiguity constructor's geometry (Ambiguity.cpp:11-66) and the
+// kernel plan.  Needs no device (the SM count falls back to 148), which is what b200dd_caf_plan exposes.
+static int caf_host_plan(const b200dd_caf_params *params, b200dd_caf *h) {
   if (params->fs == 0 || params->n_samples == 0) return arg_fail("b200dd_caf_create: fs and n_samples must be > 0");
   if (params->delay_max < params->delay_min) return geom_fail("b200dd_caf_create: delay_max < delay_min");
-  b200dd_caf *h = new (std::nothrow) b200dd_caf();
-  if (!h) return arg_fail("b200dd_caf_create: out of host memory");
   h->params = *params;
   compute_geometry(*params, h->g);
   const HostGeom &g = h->g;
-  auto fail = [&](int rc) { b200dd_caf_destroy(h); return rc; };
-  if (g.nDop == 0 || g.nCorr == 0 || g.nDel == 0) return fail(geom_fail("b200dd_caf_create: empty geometry"));
+  if (g.nDop == 0 || g.nCorr == 0 || g.nDel == 0) return geom_fail("b200dd_caf_create: empty geometry");
   if ((uint64_t)g.nDop * g.nCorr > params->n_samples)
-    return fail(geom_fail("b200dd_caf_create: nDopplerBins overflowed uint16_t in the reference formula"));
+    return geom_fail("b200dd_caf_create: nDopplerBins overflowed uint16_t in the reference formula");
   // the reference only reads defined memory for -nDel <= delayMin <= 1 (SURVEY.md s8 footnote c);
   // we compute lag delayMin + j directly and accept any window that fits the FFT plan.
-  if (g.nDop > 8192) return fail(geom_fail("b200dd_caf_create: more than 8192 Doppler bins unsupported"));
+  if (g.nDop > 8192) return geom_fail("b200dd_caf_create: more than 8192 Doppler bins unsupported");
   {
     int d0 = params->device;
-    if (d0 < 0) cudaGetDevice(&d0);
+    if (d0 < 0 && cudaGetDevice(&d0) != cudaSuccess) d0 = 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, d0) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
     cudaGetLastError();
   }
   plan_range(h);
-  if (h->log2m == 0) return fail(geom_fail("b200dd_caf_create: nDelayBins too large for the range FFT (max ~7168)"));
+  if (h->log2m == 0) return geom_fail("b200dd_caf_create: nDelayBins too large for the range FFT (max ~7168)");
   int l2 = 8;
   while ((1 << l2) < 2 * (int)g.nDop - 1) l2++;
   h->log2m2 = l2;
+  return B200DD_OK;
+}
+
+int b200dd_caf_plan(const b200dd_caf_params *params, b200dd_caf_geometry *out, int32_t *delay, uint32_t cap_delay,
+                    double *doppler, uint32_t cap_doppler) {
+  if (!params || !out) return arg_fail("b200dd_caf_plan: null argument");
+  b200dd_caf *h = new (std::nothrow) b200dd_caf();
+  if (!h) return arg_fail("b200dd_caf_plan: out of host memory");
+  int rc = caf_host_plan(params, h);
+  if (rc == B200DD_OK) rc = b200dd_caf_get_geometry(h, out);
+  if (rc == B200DD_OK && ((delay && cap_delay < h->g.nDel) || (doppler && cap_doppler < h->g.nDop)))
+    rc = arg_fail("b200dd_caf_plan: axis capacity too small");
+  if (rc == B200DD_OK) rc = b200dd_caf_get_axes(h, delay, doppler);
+  delete h;  // nothing was created on a device
+  return rc;
+}
+
+int b200dd_caf_create(const b200dd_caf_params *params, b200dd_caf **out) {
+  if (!params || !out) return arg_fail("b200dd_caf_create: null argument");
+  *out = nullptr;
+  b200dd_caf *h = new (std::nothrow) b200dd_caf();
+  if (!h) return arg_fail("b200dd_caf_create: out of host memory");
+  auto fail = [&](int rc) { b200dd_caf_destroy(h); return rc; };
+  int rc = caf_host_plan(params, h);
+  if (rc != B200DD_OK) return fail(rc);
   int dev = params->device;
   if (dev < 0) {
     if (cudaGetDevice(&dev) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaGetDevice", __FILE__, __LINE__));
@@ -951,7 +973,7 @@ int b200dd_caf_create(const b200dd_caf_params *params, b200dd_caf **out) {
   h->device = dev;
   DeviceGuard guard(dev);
   if (!guard.ok) return fail(cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__));
-  int rc = caf_setup_device(h);
+  rc = caf_setup_device(h);
   if (rc != B200DD_OK) return fail(rc);
   *out = h;
   return B200DD_OK;

@@ -292,11 +292,11 @@ template <class TIN> int run_spectrum(b200dd_spectrum *h, const TIN *d_x, double
 
 extern "C" {
 
-int b200dd_spectrum_create(uint32_t n, double bandwidth, int32_t device, b200dd_spectrum **out) {
-  if (!out) return arg_fail("b200dd_spectrum_create: null argument");
-  *out = nullptr;
-  // SpectrumAnalyser.cpp:16-18.  The reference divides by zero for bandwidth > n and converts an out-of-range
-  // double to uint32_t for bandwidth <= 0 / NaN (both undefined): fenced.
+// host half of b200dd_spectrum_create: the constructor's geometry (SpectrumAnalyser.cpp:16-18), the frequency vector
+// its process() would publish (:57-67) and the chunking of the folding pass.  Needs no device.
+static int spectrum_host_plan(uint32_t n, double bandwidth, b200dd_spectrum *h) {
+  // The reference divides by zero for bandwidth > n (:17) and converts an out-of-range double to uint32_t for
+  // bandwidth <= 0 / NaN (:16) (both undefined): fenced.
   if (!(bandwidth > 0.0) || n == 0) return geom_fail("b200dd_spectrum_create: bandwidth must be positive and n non-zero");
   const double ratio = (double)n / bandwidth;
   if (!(ratio >= 1.0) || ratio >= 4294967296.0) return geom_fail("b200dd_spectrum_create: n / bandwidth outside [1, 2^32)");
@@ -304,20 +304,6 @@ int b200dd_spectrum_create(uint32_t n, double bandwidth, int32_t device, b200dd_
   const uint32_t nSpectrum = n / decimation;         // :17
   const uint32_t nfft = nSpectrum * decimation;      // :18
   if (nSpectrum > 65536u) return geom_fail("b200dd_spectrum_create: more than 65536 spectrum bins");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    cudaGetLastError();
-    set_last_error("b200dd_spectrum_create: no CUDA device (there is no CPU fallback)");
-    return B200DD_ERR_CUDA;
-  }
-  b200dd_spectrum *h = new (std::nothrow) b200dd_spectrum();
-  if (!h) return arg_fail("b200dd_spectrum_create: out of host memory");
-  auto fail = [&](int rc) { b200dd_spectrum_destroy(h); return rc; };
-  int dev = device;
-  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaGetDevice", __FILE__, __LINE__));
-  h->device = dev;
-  DeviceGuard guard(dev);
-  if (!guard.ok) return fail(cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__));
   h->n = n;
   h->bandwidth = bandwidth;
   h->decimation = decimation;
@@ -351,6 +337,43 @@ int b200dd_spectrum_create(uint32_t n, double bandwidth, int32_t device, b200dd_
     h->rowsPerChunk2 = rows2;
     h->nChunks2 = (decimation + rows2 - 1) / rows2;
   }
+  return B200DD_OK;
+}
+
+int b200dd_spectrum_plan(uint32_t n, double bandwidth, b200dd_spectrum_geometry *out, double *frequency, uint32_t cap) {
+  if (!out) return arg_fail("b200dd_spectrum_plan: null argument");
+  b200dd_spectrum *h = new (std::nothrow) b200dd_spectrum();
+  if (!h) return arg_fail("b200dd_spectrum_plan: out of host memory");
+  int rc = spectrum_host_plan(n, bandwidth, h);
+  if (rc == B200DD_OK) rc = b200dd_spectrum_get_geometry(h, out);
+  if (rc == B200DD_OK && frequency) rc = b200dd_spectrum_get_frequency(h, frequency, cap);
+  delete h;  // nothing was created on a device
+  return rc;
+}
+
+int b200dd_spectrum_create(uint32_t n, double bandwidth, int32_t device, b200dd_spectrum **out) {
+  if (!out) return arg_fail("b200dd_spectrum_create: null argument");
+  *out = nullptr;
+  b200dd_spectrum *h = new (std::nothrow) b200dd_spectrum();
+  if (!h) return arg_fail("b200dd_spectrum_create: out of host memory");
+  {
+    const int rc0 = spectrum_host_plan(n, bandwidth, h);
+    if (rc0 != B200DD_OK) { delete h; return rc0; }
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    delete h;
+    set_last_error("b200dd_spectrum_create: no CUDA device (there is no CPU fallback)");
+    return B200DD_ERR_CUDA;
+  }
+  auto fail = [&](int rc) { b200dd_spectrum_destroy(h); return rc; };
+  int dev = device;
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaGetDevice", __FILE__, __LINE__));
+  h->device = dev;
+  DeviceGuard guard(dev);
+  if (!guard.ok) return fail(cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__));
+  const uint32_t decimation = h->decimation, nSpectrum = h->nSpectrum, nfft = h->nfft;
   // phase tables (long double on the host, exact integer residues)
   const uint64_t k0 = (uint64_t)(nfft / 2) + 1;  // :46 int(nfft / 2) + 1
   std::vector<double2> t1(decimation), t2(nSpectrum), w(nSpectrum);

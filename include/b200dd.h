@@ -116,6 +116,12 @@ typedef struct {
 } b200dd_caf_geometry;
 
 B200DD_API int b200dd_caf_create(const b200dd_caf_params *params, b200dd_caf **out);
+/* The host half of b200dd_caf_create on its own -- the Ambiguity constructor's arithmetic (Ambiguity.cpp:11-66: bin
+ * counts, nCorr, cpi, nfft, both axes) and the kernel plan -- without touching a device (params->device is only used
+ * to look up the SM count; 148 is assumed when there is none).  delay / doppler are nullable; capacities in elements.
+ * This is what lets the CPU test-suite check the PRODUCT's geometry code against the reference's golden values. */
+B200DD_API int b200dd_caf_plan(const b200dd_caf_params *params, b200dd_caf_geometry *out, int32_t *delay,
+                               uint32_t cap_delay, double *doppler, uint32_t cap_doppler);
 B200DD_API void b200dd_caf_destroy(b200dd_caf *h);
 B200DD_API int b200dd_caf_get_geometry(const b200dd_caf *h, b200dd_caf_geometry *out);
 /* Map axes as the Ambiguity constructor builds them (Ambiguity.cpp:46-59):
@@ -285,6 +291,10 @@ typedef struct {
 /* Returns B200DD_ERR_GEOMETRY where the reference is undefined (bandwidth <= 0, NaN, or bandwidth > n, which
  * divides by zero at :17) or for more than 65536 spectrum bins. */
 B200DD_API int b200dd_spectrum_create(uint32_t n, double bandwidth, int32_t device, b200dd_spectrum **out);
+/* The host half of b200dd_spectrum_create on its own (no device needed): geometry and, when `frequency` is not NULL,
+ * the n_frequency values of the frequency vector. */
+B200DD_API int b200dd_spectrum_plan(uint32_t n, double bandwidth, b200dd_spectrum_geometry *out, double *frequency,
+                                    uint32_t cap);
 B200DD_API void b200dd_spectrum_destroy(b200dd_spectrum *h);
 B200DD_API int b200dd_spectrum_get_geometry(const b200dd_spectrum *h, b200dd_spectrum_geometry *out);
 /* The vector SpectrumAnalyser::process hands to IqData::update_frequency (n_frequency doubles, kHz). */
