@@ -256,10 +256,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly ONE line, the JSON: keep the real stdout aside and point file descriptor 1 at stderr, so
+    # that anything a library prints there (NCCL's "NCCL version ..." banner, which it writes at WARN level too)
+    # lands on stderr instead
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -491,7 +494,7 @@ def main():
                 line["cpu_baseline"]["spectrum_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
         except Exception:
             pass
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
