@@ -542,11 +542,21 @@ int run_chain(b200dd_det *h, int last_stage, const TMAP *d_map, uint32_t nDop, u
 }
 
 int fetch_results(b200dd_det *h, int buf, int count_slot, double *o_delay, double *o_doppler, double *o_snr, uint32_t cap,
-                  uint32_t *n_out, cudaStream_t st) {
-  uint32_t n = 0;
-  B2_CUDA(cudaMemcpyAsync(&n, h->d_n + count_slot, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                  uint32_t *n_out, cudaStream_t st, bool chain_from_cfar = false) {
+  // count_slot < 0: the chain ran set_metrics only (no detection stage): nothing to copy, but the caller's
+  // metrics copy is on this stream, so synchronise all the same
+  uint32_t counts[4] = {0, 0, 0, 0};
+  if (count_slot >= 0) B2_CUDA(cudaMemcpyAsync(counts, h->d_n, sizeof(counts), cudaMemcpyDeviceToHost, st));
   B2_CUDA(cudaStreamSynchronize(st));
+  const uint32_t n = count_slot >= 0 ? counts[count_slot] : 0;
   if (n_out) *n_out = n;
+  // The lists hold at most h->cap entries.  If CFAR itself found more than that, every later stage worked on a
+  // truncated list: the result is wrong even when the final count fits, so report it.
+  if (chain_from_cfar && counts[0] > h->cap) {
+    if (n_out) *n_out = 0;
+    set_last_error("more CFAR detections than the handle's list capacity (2^18): detection list invalid");
+    return B200DD_ERR_CAPACITY;
+  }
   uint32_t have = n < h->cap ? n : h->cap;
   uint32_t take = have < cap ? have : cap;
   if (take) {
@@ -677,13 +687,13 @@ int b200dd_det_process_device(b200dd_det *h, int last_stage, const void *d_map, 
   int buf = 0, slot = 0;
   rc = run_chain<float2>(h, last_stage, (const float2 *)d_map, n_dop, n_del, delay, doppler, noise_power, nullptr, st, &buf, &slot);
   if (rc != B200DD_OK) return rc;
-  return fetch_results(h, buf, slot, o_delay, o_doppler, o_snr, cap, n_out, st);
+  return fetch_results(h, buf, slot, o_delay, o_doppler, o_snr, cap, n_out, st, true);
 }
 
 int b200dd_det_chain_device_async(b200dd_det *h, int last_stage, const void *d_map, uint32_t n_dop, uint32_t n_del,
                                   const int32_t *delay, const double *doppler, void *stream) {
   if (!h || !d_map || !delay || !doppler) return arg_fail("b200dd_det_chain_device_async: null argument");
-  if (last_stage < B200DD_DET_CFAR || last_stage > B200DD_DET_INTERPOLATE) return arg_fail("b200dd_det_chain_device_async: bad stage");
+  if (last_stage < 0 || last_stage > B200DD_DET_INTERPOLATE) return arg_fail("b200dd_det_chain_device_async: bad stage");
   int rc = check_dims(h, n_dop, n_del);
   if (rc != B200DD_OK) return rc;
   DeviceGuard guard(h->device);
@@ -695,6 +705,11 @@ int b200dd_det_chain_device_async(b200dd_det *h, int last_stage, const void *d_m
   B2_LAUNCH_CHECK();
   metrics_final_kernel<<<1, kBlock, 0, st>>>(h->d_part, h->d_part + h->nPart, grid, (double)cells, h->d_metrics);
   B2_LAUNCH_CHECK();
+  if (last_stage == 0) {  // Map::set_metrics only (blah2.cpp:279 runs it whether or not detection is enabled)
+    h->chain_buf = 0;
+    h->chain_slot = -1;
+    return B200DD_OK;
+  }
   return run_chain<float2>(h, last_stage, (const float2 *)d_map, n_dop, n_del, delay, doppler, 0.0, h->d_metrics, st,
                            &h->chain_buf, &h->chain_slot);
 }
@@ -706,7 +721,7 @@ int b200dd_det_chain_fetch(b200dd_det *h, double *metrics, double *o_delay, doub
   DeviceGuard guard(h->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   if (metrics) B2_CUDA(cudaMemcpyAsync(metrics, h->d_metrics, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
-  return fetch_results(h, h->chain_buf, h->chain_slot, o_delay, o_doppler, o_snr, cap, n_out, st);
+  return fetch_results(h, h->chain_buf, h->chain_slot, o_delay, o_doppler, o_snr, cap, n_out, st, true);
 }
 
 int b200dd_det_process_host(b200dd_det *h, int last_stage, const double *map, uint32_t n_dop, uint32_t n_del,
@@ -728,7 +743,7 @@ int b200dd_det_process_host(b200dd_det *h, int last_stage, const double *map, ui
   int buf = 0, slot = 0;
   rc = run_chain<double2>(h, last_stage, h->d_mapd, n_dop, n_del, delay, doppler, noise_power, nullptr, st, &buf, &slot);
   if (rc != B200DD_OK) return rc;
-  return fetch_results(h, buf, slot, o_delay, o_doppler, o_snr, cap, n_out, st);
+  return fetch_results(h, buf, slot, o_delay, o_doppler, o_snr, cap, n_out, st, true);
 }
 
 int b200dd_det_centroid_host(b200dd_det *h, const double *delay, const double *doppler, const double *snr, uint32_t n,

@@ -177,13 +177,10 @@ static int pipeline_enqueue_device(b200dd_pipeline *h, const void *d_x, const vo
   float2 *map = d_map ? (float2 *)d_map : h->d_map;
   rc = b200dd_caf_process_device(h->caf, d_x, y, n, map, st);
   if (rc != B200DD_OK) return rc;
+  // Map::set_metrics runs after every Ambiguity::process, detection or not (blah2.cpp:278-279): stage 0 = metrics only
   const int last = h->p.detection_enable ? B200DD_DET_INTERPOLATE : 0;
-  if (last) {
-    rc = b200dd_det_chain_device_async(h->det, last, map, h->g.n_doppler_bins, h->g.n_delay_bins, h->delay.data(),
+  return b200dd_det_chain_device_async(h->det, last, map, h->g.n_doppler_bins, h->g.n_delay_bins, h->delay.data(),
                                        h->doppler.data(), st);
-    if (rc != B200DD_OK) return rc;
-  }
-  return B200DD_OK;
 }
 
 
@@ -277,22 +274,21 @@ int b200dd_pipeline_fetch(b200dd_pipeline *h, b200dd_cpi_result *result, double 
   result->n_detections = 0;
   result->noise_power = 0.0;
   result->max_power = 0.0;
-  int rc = B200DD_OK;
-  if (h->p.detection_enable) {
-    double metrics[2] = {0.0, 0.0};
-    uint32_t n = 0;
-    rc = b200dd_det_chain_fetch(h->det, metrics, o_delay, o_doppler, o_snr, cap, &n, st);
-    result->n_detections = n;
-    result->noise_power = metrics[0];
-    result->max_power = metrics[1];
-  } else {
-    B2_CUDA(cudaStreamSynchronize((cudaStream_t)st));
+  int fs = 0;
+  if (h->last_had_filter) B2_CUDA(cudaMemcpyAsync(&fs, b200dd_wh_device_status(h->wh), sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)st));
+  double metrics[2] = {0.0, 0.0};
+  uint32_t n = 0;
+  const int rc = b200dd_det_chain_fetch(h->det, metrics, o_delay, o_doppler, o_snr, cap, &n, st);  // synchronises st
+  if (fs != 0) {
+    // The reference skips the whole CPI when the Cholesky solve fails: `if (!filter->process(x, y)) continue;`
+    // (blah2.cpp:270-273) -- no map, no metrics, no detections are published.  The kernels downstream of the
+    // failed solve have run on the unfiltered channel; their results are discarded here.
+    result->filter_status = B200DD_FILTER_FAILED;
+    return B200DD_OK;
   }
-  if (h->last_had_filter) {
-    int s = 0;
-    B2_CUDA(cudaMemcpy(&s, b200dd_wh_device_status(h->wh), sizeof(int), cudaMemcpyDeviceToHost));
-    if (s != 0) result->filter_status = B200DD_FILTER_FAILED;
-  }
+  result->n_detections = n;
+  result->noise_power = metrics[0];
+  result->max_power = metrics[1];
   return rc;
 }
 
@@ -336,11 +332,9 @@ int b200dd_pipeline_submit_host(b200dd_pipeline *h, const double *x, const doubl
   B2_LAUNCH_CHECK();
   rc = b200dd_caf_process_device(h->caf, h->d_xf, h->d_yf2, need, h->d_map, st);
   if (rc != B200DD_OK) return rc;
-  if (h->p.detection_enable) {
-    rc = b200dd_det_chain_device_async(h->det, B200DD_DET_INTERPOLATE, h->d_map, h->g.n_doppler_bins,
-                                       h->g.n_delay_bins, h->delay.data(), h->doppler.data(), st);
-    if (rc != B200DD_OK) return rc;
-  }
+  rc = b200dd_det_chain_device_async(h->det, h->p.detection_enable ? B200DD_DET_INTERPOLATE : 0, h->d_map,
+                                     h->g.n_doppler_bins, h->g.n_delay_bins, h->delay.data(), h->doppler.data(), st);
+  if (rc != B200DD_OK) return rc;
   if (map_out) {
     const uint32_t cells = h->g.n_doppler_bins * h->g.n_delay_bins;
     pl_widen_kernel<<<grid_for(cells), 256, 0, st>>>(h->d_map, h->d_mapd, cells);

@@ -30,6 +30,7 @@
 // (WienerHopf.cpp:67) exactly, including its behaviour for delayMin > 0.
 #include "common.cuh"
 #include "fft_core.cuh"
+#include "fft_dit.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -79,9 +80,9 @@ template <class TIN> __device__ __forceinline__ double2 ld_iq(const TIN *p, uint
   return make_double2((double)v.x, (double)v.y);
 }
 
-// resident CTAs per SM the register allocator leaves room for (<= 128 registers per thread)
-template <int LOG2M, int LR> constexpr int wh_min_ctas() {
-  return 512 / Plan<LOG2M, LR>::NT > 8 ? 8 : (512 / Plan<LOG2M, LR>::NT < 1 ? 1 : 512 / Plan<LOG2M, LR>::NT);
+// resident CTAs per SM of the filter kernel (<= 128 registers per thread, one FFT buffer each)
+template <int LOG2M> constexpr int wh_min_ctas() {
+  return 512 / dit::Plan3<LOG2M>::NT > 8 ? 8 : (512 / dit::Plan3<LOG2M>::NT < 1 ? 1 : 512 / dit::Plan3<LOG2M>::NT);
 }
 
 struct CorrArgs {
@@ -92,49 +93,55 @@ struct CorrArgs {
   uint32_t N;
   XsMap xs;
   int nBins, L, nSegTotal, segPerCta;
-  double2 *xw_out;    // [nSeg][R][NT] spectra of the reference windows, kept for the filter stage (or null)
 };
 
-// forward FFT of M points from a loader, result in registers (position order of fft_core.cuh)
-template <int LOG2M, int LR, class LD>
-__device__ __forceinline__ void fwd_fft_regs(double2 *A, const double2 *tw, int tid, LD ld, double2 (&v)[1 << LR]) {
-  using P = Plan<LOG2M, LR>;
-  auto stA = [&](int i, double2 val) { A[padr<LR>(i)] = val; };
-#pragma unroll 1
-  for (int b = tid; b < P::M / P::R0; b += P::NT) fft_butterfly<double, P::R0, -1, LOG2M>(b, P::log2S(0), tw, ld, stA);
-  __syncthreads();
-#pragma unroll 1
-  for (int p = 1; p < P::NP - 1; p++) {
-    smem_pass<double, LOG2M, -1, LR>(A, tw, p, tid);
-    __syncthreads();
+// One M-point window of a channel for the DIT transform (fft_dit.cuh): thread tid owns the window elements
+// m = tid + NT k, k < 16 (consecutive lanes -> consecutive samples).  The loads are issued early into `raw`
+// (unconditional, on clamped indices, so that all 16 are in flight together) and converted / masked when the
+// transform starts: element m is valid while m < lim.  MAPX applies the reference's index map of the shifted
+// reference channel; indices are circular over N (WienerHopf.cpp:76-108).
+template <int NT, bool MAPX, class TIN>
+__device__ __forceinline__ void win_issue(TIN (&raw)[16], const TIN *__restrict__ p, const XsMap &xs, uint32_t N, uint32_t n0,
+                                          int lim, int tid) {
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const int m = min(tid + NT * k, lim - 1);
+    uint32_t i = n0 + (uint32_t)m;
+    i = i >= N ? i - N : i;
+    raw[k] = p[MAPX ? xs(i) : i];
   }
-  fwd_last_to_regs<double, LOG2M, LR>(A, tid, v);
 }
-
-// inverse FFT from registers; the final pass hands natural-order outputs to st(m, value)
-template <int LOG2M, int LR, class ST>
-__device__ __forceinline__ void inv_fft_from_regs(double2 *A, const double2 *tw, int tid, const double2 (&z)[1 << LR],
-                                                  int keep, ST st) {
-  using P = Plan<LOG2M, LR>;
-  inv_first_from_regs<double, LOG2M, LR>(A, tid, z);
-  __syncthreads();
-#pragma unroll 1
-  for (int p = P::NP - 2; p >= 1; p--) {
-    smem_pass<double, LOG2M, +1, LR>(A, tw, p, tid);
-    __syncthreads();
-  }
-  auto ldA = [&](int i) { return A[padr<LR>(i)]; };
-  constexpr int S0 = 1 << P::log2S(0);
-#pragma unroll 1
-  for (int b = tid; b < P::M / P::R0; b += P::NT) {
-    if ((b & (S0 - 1)) < keep) fft_butterfly<double, P::R0, +1, LOG2M>(b, P::log2S(0), tw, ldA, st);
+template <int NT, class TIN> __device__ __forceinline__ void win_convert(double2 (&v)[16], const TIN (&raw)[16], int lim, int tid) {
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const bool ok = tid + NT * k < lim;
+    v[k] = make_double2(ok ? (double)raw[k].x : 0.0, ok ? (double)raw[k].y : 0.0);
   }
 }
 
-template <int LOG2M, int LR, class TIN>
-__global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, 1) wh_corr_kernel(CorrArgs a) {
-  using P = Plan<LOG2M, LR>;
-  constexpr int R = P::R;
+// v (the thread's 16 window elements) -> its 16 spectrum values X[tid + NT q], left in v[brev16(q)].
+// Three CTA barriers; the caller adds one before the buffer is written again.
+template <int LOG2M, int DIR> __device__ __forceinline__ void dit_transform(double2 *A, const double2 *__restrict__ tw, int tid, double2 (&v)[16]) {
+  dit::pass0_store<double, LOG2M, DIR>(A, tid, v);
+  __syncthreads();
+  dit::pass1_load<double, LOG2M>(A, tid, v);
+  dit::pass1_compute<double, LOG2M, DIR>(tw, tid, v);
+  dit::pass1_store<double, LOG2M>(A, tid, v);
+  __syncthreads();
+  dit::pass2_load<double, LOG2M>(A, tid, v);
+  dit::pass2_compute<double, LOG2M, DIR>(tw, tid, v);
+}
+
+// K3.  One CTA per SM walks segPerCta segments of L new samples.  Per segment three forward transforms of
+// M = L + nBins - 1 points: P = the segment zero-padded, W = the reference window, V = the surveillance window;
+// cross-spectra W conj(P) and V conj(P) are accumulated over the CTA's segments (shared memory, each thread
+// its own 16 bins), one inverse transform per correlation at the end.  The global loads of transform t + 1 are
+// issued before transform t's shared-memory passes (register prefetch: with one CTA of 8 warps per SM nothing
+// else hides their latency).
+template <int LOG2M, class TIN>
+__global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_corr_kernel(CorrArgs a) {
+  using P = dit::Plan3<LOG2M>;
+  constexpr int NT = P::NT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *A = reinterpret_cast<double2 *>(smem_raw);
   double2 *Za = A + P::MP;
@@ -144,92 +151,72 @@ __global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, 1) wh_corr_kernel(CorrArg
   const TIN *__restrict__ y = reinterpret_cast<const TIN *>(a.y);
   const double2 zero = make_double2(0.0, 0.0);
 #pragma unroll
-  for (int r = 0; r < R; r++) {
-    Za[r * P::NT + tid] = zero;
-    Zb[r * P::NT + tid] = zero;
+  for (int q = 0; q < 16; q++) {
+    Za[q * NT + tid] = zero;
+    Zb[q * NT + tid] = zero;
   }
   const int s0 = blockIdx.x * a.segPerCta;
   const int s1 = min(s0 + a.segPerCta, a.nSegTotal);
   const XsMap xs = a.xs;
+  const uint32_t N = a.N;
+  auto seg_len = [&](int s) { return (int)min((uint32_t)a.L, N - (uint32_t)s * (uint32_t)a.L); };
+  TIN raw[16];
+  if (s0 < s1) win_issue<NT, true>(raw, x, xs, N, (uint32_t)s0 * (uint32_t)a.L, seg_len(s0), tid);
   for (int s = s0; s < s1; s++) {
     const uint32_t n0 = (uint32_t)s * (uint32_t)a.L;
-    const int len = (int)min((uint32_t)a.L, a.N - n0);
+    const int len = seg_len(s);
     const int wlen = len + a.nBins - 1;
-    // branch-free loaders: every load is unconditional on a valid index (so the 16 loads of a
-    // butterfly are issued back to back) and masked afterwards
-    auto ldxp = [&](int m) {
-      const double2 v = ld_iq(x, xs(n0 + (uint32_t)min(m, len - 1)));
-      return m < len ? v : zero;
-    };
-    auto ldxw = [&](int m) {
-      uint32_t i = n0 + (uint32_t)m;
-      i = i >= a.N ? i - a.N : i;  // circular correlation over N (WienerHopf.cpp:76-108)
-      const double2 v = ld_iq(x, xs(i));
-      return m < wlen ? v : zero;
-    };
-    auto ldyw = [&](int m) {
-      uint32_t i = n0 + (uint32_t)m;
-      i = i >= a.N ? i - a.N : i;
-      const double2 v = ld_iq(y, i);
-      return m < wlen ? v : zero;
-    };
-    // hint the NEXT segment's x and y windows into L2 (one 128-byte line per thread and array): this CTA is
-    // alone on its SM, so nothing else hides the DRAM latency of the pass-0 loads (25 % of the stall samples
-    // sat on their first use: profiles/r01_summary.md)
-    if (s + 1 < s1) {
-      constexpr uint32_t per_line = 128 / sizeof(TIN);
-      for (uint32_t e = (uint32_t)tid * per_line; e < (uint32_t)P::M; e += (uint32_t)P::NT * per_line) {
-        uint32_t i = n0 + (uint32_t)a.L + e;
-        i = i >= a.N ? i - a.N : i;
-        if (i < a.N) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(y + i));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(x + xs(i)));
-        }
-      }
-    }
-    double2 vxp[R], v[R];
-    fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldxp, vxp);
+    double2 vxp[16], v[16];
+    // P: the padded segment
+    win_convert<NT>(vxp, raw, len, tid);
+    win_issue<NT, true>(raw, x, xs, N, n0, wlen, tid);  // the same samples again + the next nBins-1: L1/L2 hits
+    dit_transform<LOG2M, -1>(A, a.tw, tid, vxp);
     __syncthreads();
-    fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldxw, v);
-    // The window x[sL .. sL+M) is exactly the overlap-save window the FIR stage needs for the outputs
-    // [sL + nBins-1, (s+1)L + nBins-1): keep its spectrum so that stage does not transform x again.
-    if (a.xw_out) {
-      double2 *dst = a.xw_out + (size_t)s * P::M + tid;
+    // W: the reference window; a-spectrum += W conj(P)
+    win_convert<NT>(v, raw, wlen, tid);
+    win_issue<NT, false>(raw, y, xs, N, n0, wlen, tid);
+    dit_transform<LOG2M, -1>(A, a.tw, tid, v);
 #pragma unroll
-      for (int r = 0; r < R; r++) dst[r * P::NT] = v[r];
-    }
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      double2 acc = Za[r * P::NT + tid];
-      cfmac(acc, v[r], vxp[r]);
-      Za[r * P::NT + tid] = acc;
+    for (int q = 0; q < 16; q++) {
+      double2 acc = Za[q * NT + tid];
+      cfmac(acc, v[brev<16>(q)], vxp[brev<16>(q)]);
+      Za[q * NT + tid] = acc;
     }
     __syncthreads();
-    fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldyw, v);
+    // V: the surveillance window; b-spectrum += V conj(P)
+    win_convert<NT>(v, raw, wlen, tid);
+    if (s + 1 < s1) win_issue<NT, true>(raw, x, xs, N, n0 + (uint32_t)a.L, seg_len(s + 1), tid);
+    dit_transform<LOG2M, -1>(A, a.tw, tid, v);
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-      double2 acc = Zb[r * P::NT + tid];
-      cfmac(acc, v[r], vxp[r]);
-      Zb[r * P::NT + tid] = acc;
+    for (int q = 0; q < 16; q++) {
+      double2 acc = Zb[q * NT + tid];
+      cfmac(acc, v[brev<16>(q)], vxp[brev<16>(q)]);
+      Zb[q * NT + tid] = acc;
     }
     __syncthreads();
   }
   const double scale = 1.0 / (double)P::M;
   double2 *pa = a.partial + (size_t)blockIdx.x * 2 * a.nBins;
   double2 *pb = pa + a.nBins;
-  double2 z[R];
+  double2 z[16];
 #pragma unroll
-  for (int r = 0; r < R; r++) z[r] = Za[r * P::NT + tid];
+  for (int q = 0; q < 16; q++) z[q] = Za[q * NT + tid];
   // IFFT gives ra[k] = sum xs[n+k] conj(xs[n]);  a[k] = conj(ra[k])  (WienerHopf.cpp:82-84)
-  inv_fft_from_regs<LOG2M, LR>(A, a.tw, tid, z, a.nBins, [&](int m, double2 val) {
-    if (m < a.nBins) pa[m] = make_double2(val.x * scale, -val.y * scale);
-  });
+  dit_transform<LOG2M, +1>(A, a.tw, tid, z);
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    const int m = tid + NT * q;
+    if (m < a.nBins) pa[m] = make_double2(z[brev<16>(q)].x * scale, -z[brev<16>(q)].y * scale);
+  }
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < R; r++) z[r] = Zb[r * P::NT + tid];
-  inv_fft_from_regs<LOG2M, LR>(A, a.tw, tid, z, a.nBins, [&](int m, double2 val) {
-    if (m < a.nBins) pb[m] = make_double2(val.x * scale, val.y * scale);
-  });
+  for (int q = 0; q < 16; q++) z[q] = Zb[q * NT + tid];
+  dit_transform<LOG2M, +1>(A, a.tw, tid, z);
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    const int m = tid + NT * q;
+    if (m < a.nBins) pb[m] = make_double2(z[brev<16>(q)].x * scale, z[brev<16>(q)].y * scale);
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -640,22 +627,26 @@ template <int MAXT> __global__ void __launch_bounds__(MAXT, 1) wh_solve_short_ke
 }
 
 // ---------------------------------------------------------------------------------
-// spectrum of the zero-padded weights (position order), once per CPI
+// spectrum of the zero-padded weights, once per CPI: what[q NT + tid] = W^[tid + NT q] (the order in which the
+// filter kernel's threads hold their spectra: coalesced 16-byte loads)
 // ---------------------------------------------------------------------------------
-template <int LOG2M, int LR>
-__global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, 1) wh_wspec_kernel(const double2 *w, int nBins, double2 *what,
+template <int LOG2M>
+__global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_wspec_kernel(const double2 *w, int nBins, double2 *what,
                                                                         const double2 *tw) {
-  using P = Plan<LOG2M, LR>;
-  constexpr int R = P::R;
+  using P = dit::Plan3<LOG2M>;
+  constexpr int NT = P::NT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *A = reinterpret_cast<double2 *>(smem_raw);
   const int tid = threadIdx.x;
-  double2 v[R];
-  fwd_fft_regs<LOG2M, LR>(A, tw, tid, [&](int i) { return i < nBins ? w[i] : make_double2(0.0, 0.0); }, v);
+  double2 v[16];
 #pragma unroll
-  // register-major layout [r][tid]: the filter kernel's 16 loads per thread are then coalesced (consecutive
-  // lanes read consecutive 16-byte elements) instead of 32 scattered sectors per instruction (-16 % on K5)
-  for (int r = 0; r < R; r++) what[r * P::NT + tid] = v[r];
+  for (int k = 0; k < 16; k++) {
+    const int m = tid + NT * k;
+    v[k] = m < nBins ? w[m] : make_double2(0.0, 0.0);
+  }
+  dit_transform<LOG2M, -1>(A, tw, tid, v);
+#pragma unroll
+  for (int q = 0; q < 16; q++) what[q * NT + tid] = v[brev<16>(q)];
 }
 
 struct ApplyArgs {
@@ -668,7 +659,6 @@ struct ApplyArgs {
   uint32_t N;
   XsMap xs;
   int nBins, Lout;
-  const double2 *xw;  // window spectra written by the correlation stage (same FFT plan), or null
 };
 
 template <class TOUT> __device__ __forceinline__ void st_iq(TOUT *p, uint32_t i, double2 v);
@@ -677,94 +667,76 @@ template <> __device__ __forceinline__ void st_iq<float2>(float2 *p, uint32_t i,
 }
 template <> __device__ __forceinline__ void st_iq<double2>(double2 *p, uint32_t i, double2 v) { p[i] = v; }
 
-// one CTA per block of Lout outputs: window of M = Lout + nBins - 1 shifted-reference samples
-template <int LOG2M, int LR, class TIN>
-__global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, wh_min_ctas<LOG2M, LR>()) wh_apply_kernel(ApplyArgs a) {
-  using P = Plan<LOG2M, LR>;
-  constexpr int R = P::R;
+// K5.  One CTA per block of Lout outputs: overlap-save with the window of M = Lout + nBins - 1 shifted-reference
+// samples that ends at the block's last output; forward transform, multiply by the weight spectrum, inverse
+// transform, y' = y - conv / M.  y and y_out may be the same buffer (each element is read, then written, by the
+// same thread), hence no __restrict__ on them.
+template <int LOG2M, class TIN>
+__global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, wh_min_ctas<LOG2M>()) wh_apply_kernel(ApplyArgs a) {
+  using P = dit::Plan3<LOG2M>;
+  constexpr int NT = P::NT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *A = reinterpret_cast<double2 *>(smem_raw);
   const int tid = threadIdx.x;
   const TIN *__restrict__ x = reinterpret_cast<const TIN *>(a.x);
-  const TIN *__restrict__ y = reinterpret_cast<const TIN *>(a.y);
-  TIN *__restrict__ yo = reinterpret_cast<TIN *>(a.y_out);
-  // Output blocks.  Without kept spectra: block b = [b Lout, (b+1) Lout).  With them the blocks are shifted by
-  // the filter history so that block s+1 owns exactly the outputs of the correlation stage's window s, and
-  // block 0 produces the first nBins-1 outputs (zero history) with a transform of its own.
+  const TIN *y = reinterpret_cast<const TIN *>(a.y);
+  TIN *yo = reinterpret_cast<TIN *>(a.y_out);
   const int hist = a.nBins - 1;
-  const bool kept = a.xw != nullptr && blockIdx.x > 0;
-  uint32_t i0;
-  int nOut;
-  if (a.xw == nullptr) {
-    i0 = (uint32_t)blockIdx.x * (uint32_t)a.Lout;
-    nOut = (int)min((uint32_t)a.Lout, a.N - i0);
-  } else if (blockIdx.x == 0) {
-    i0 = 0;
-    nOut = (int)min((uint32_t)hist, a.N);
-  } else {
-    const uint64_t start = (uint64_t)(blockIdx.x - 1) * (uint64_t)a.Lout + (uint64_t)hist;
-    i0 = (uint32_t)min(start, (uint64_t)a.N);
-    nOut = (int)min((uint32_t)a.Lout, a.N - i0);
-  }
+  const uint32_t i0 = (uint32_t)blockIdx.x * (uint32_t)a.Lout;
+  const int nOut = (int)min((uint32_t)a.Lout, a.N - i0);
   if (nOut <= 0) return;
   if (*a.status != 0) {  // failed solve: surveillance channel passes through untouched
-    for (int m = tid; m < nOut; m += P::NT) st_iq<TIN>(yo, i0 + m, ld_iq(y, i0 + m));
+    for (int m = tid; m < nOut; m += NT) st_iq<TIN>(yo, i0 + m, ld_iq(y, i0 + m));
     return;
   }
-  const double2 zero = make_double2(0.0, 0.0);
-  // window element m <-> shifted-reference index i0 - hist + m (zero history before sample 0);
-  // branch-free: load from a clamped valid index, mask afterwards
+  // window element m <-> shifted-reference index i0 - hist + m (zero history before sample 0: the reference's
+  // LINEAR convolution, WienerHopf.cpp:125-153); branch-free: load from a clamped valid index, mask afterwards
   const XsMap xs = a.xs;
-  auto ldw = [&](int m) {
-    const int64_t i = (int64_t)i0 - hist + m;
-    const int64_t ic = i < 0 ? 0 : (i >= (int64_t)a.N ? (int64_t)a.N - 1 : i);
-    const double2 v = ld_iq(x, xs((uint32_t)ic));
-    return (i >= 0 && i < (int64_t)a.N && m < hist + nOut) ? v : zero;
-  };
-  double2 v[R];
-  if (kept) {
-    const double2 *src = a.xw + (size_t)(blockIdx.x - 1) * P::M + tid;
+  double2 v[16];
+  {
+    TIN raw[16];
 #pragma unroll
-    for (int r = 0; r < R; r++) v[r] = src[r * P::NT];
-  } else {
-    fwd_fft_regs<LOG2M, LR>(A, a.tw, tid, ldw, v);
+    for (int k = 0; k < 16; k++) {
+      const int64_t i = (int64_t)i0 - hist + (tid + NT * k);
+      const int64_t ic = i < 0 ? 0 : (i >= (int64_t)a.N ? (int64_t)a.N - 1 : i);
+      raw[k] = x[xs((uint32_t)ic)];
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const int m = tid + NT * k;
+      const int64_t i = (int64_t)i0 - hist + m;
+      const bool ok = i >= 0 && i < (int64_t)a.N && m < hist + nOut;
+      v[k] = make_double2(ok ? (double)raw[k].x : 0.0, ok ? (double)raw[k].y : 0.0);
+    }
   }
+  dit_transform<LOG2M, -1>(A, a.tw, tid, v);
+  double2 z[16];
 #pragma unroll
-  for (int r = 0; r < R; r++) v[r] = cmul(v[r], a.what[r * P::NT + tid]);
+  for (int q = 0; q < 16; q++) z[q] = cmul(v[brev<16>(q)], __ldg(a.what + q * NT + tid));
   __syncthreads();
-  const double scale = 1.0 / (double)P::M;
-  // conv[m] valid for m >= hist; output i = i0 + m - hist.  The final inverse pass is written out here so
-  // that the epilogue can issue all surveillance-channel loads of a butterfly back to back before the
-  // first store (y_out may alias y, so the compiler would otherwise keep load -> store order and
-  // serialise 16 global-load latencies per thread: profiles/r01_summary.md).
-  inv_first_from_regs<double, LOG2M, LR>(A, tid, v);
-  __syncthreads();
-#pragma unroll 1
-  for (int p = P::NP - 2; p >= 1; p--) {
-    smem_pass<double, LOG2M, +1, LR>(A, a.tw, p, tid);
-    __syncthreads();
-  }
-  auto ldA = [&](int i) { return A[padr<LR>(i)]; };
-  constexpr int R0 = P::R0;
-  constexpr int L2S0 = P::log2S(0);
-#pragma unroll 1
-  for (int b = tid; b < P::M / R0; b += P::NT) {
-    double2 c[R0];
-    const int base = fft_butterfly_core<double, R0, +1, LOG2M>(b, L2S0, a.tw, ldA, c);
-    TIN yy[R0];
+  // the surveillance samples of the epilogue are requested before the inverse transform's shared-memory passes
+  // (float2 input only: sixteen double2 would not fit beside the transform's registers)
+  constexpr bool kPrefetchY = sizeof(TIN) == sizeof(float2);
+  TIN yy[16];
+  auto load_y = [&]() {
 #pragma unroll
-    for (int q = 0; q < R0; q++) {
-      const int o = base + (q << L2S0) - hist;
+    for (int q = 0; q < 16; q++) {
+      const int o = tid + NT * q - hist;
       const int oc = o < 0 ? 0 : (o >= nOut ? nOut - 1 : o);
       yy[q] = y[i0 + oc];  // unconditional, clamped: batched loads
     }
+  };
+  if constexpr (kPrefetchY) load_y();
+  dit_transform<LOG2M, +1>(A, a.tw, tid, z);
+  if constexpr (!kPrefetchY) load_y();
+  const double scale = 1.0 / (double)P::M;
+  // conv[m] valid for m >= hist; output i = i0 + m - hist
 #pragma unroll
-    for (int q = 0; q < R0; q++) {
-      const int o = base + (q << L2S0) - hist;
-      if (o >= 0 && o < nOut) {
-        const double2 cv = c[brev<R0>(q)];
-        st_iq<TIN>(yo, i0 + o, make_double2((double)yy[q].x - cv.x * scale, (double)yy[q].y - cv.y * scale));
-      }
+  for (int q = 0; q < 16; q++) {
+    const int o = tid + NT * q - hist;
+    if (o >= 0 && o < nOut) {
+      const double2 cv = z[brev<16>(q)];
+      st_iq<TIN>(yo, i0 + o, make_double2((double)yy[q].x - cv.x * scale, (double)yy[q].y - cv.y * scale));
     }
   }
 }
@@ -788,56 +760,52 @@ struct b200dd_wh {
   int device = 0;
   cudaStream_t stream = nullptr;
   int log2m_c = 12, log2m_a = 12;  // FFT lengths of the correlation / filter stages
-  int lr = 4;                      // log2 of the base radix of the FP64 FFTs (B200DD_WH_RADIX = 8 | 16)
   int L = 0, nSeg = 0, segPerCta = 1, gridCorr = 1;  // correlation stage
   int Lout = 0, gridApply = 1;                       // filter stage
   double2 *d_tw_c = nullptr, *d_tw_a = nullptr, *d_partial = nullptr, *d_a = nullptr, *d_b = nullptr, *d_w = nullptr, *d_what = nullptr;
   int *d_status = nullptr;
   double2 *d_xd = nullptr, *d_yd = nullptr;  // host path staging (complex128)
-  double2 *d_xw = nullptr;                   // [nSeg][M] reference-window spectra kept between the two FFT stages
   int num_sms = 148;
+  bool solve_short = true;  // B200DD_WH_SOLVE_SHORT, read once at create
   bool attr_corr_f32 = false, attr_corr_f64 = false, attr_apply_f32 = false, attr_apply_f64 = false, attr_solve = false;
 };
 
 namespace {
 
-template <int LOG2M, int LR> size_t corr_smem() { return (size_t)(Plan<LOG2M, LR>::MP + 2 * Plan<LOG2M, LR>::M) * sizeof(double2); }
-template <int LOG2M, int LR> size_t fft_smem() { return (size_t)Plan<LOG2M, LR>::MP * sizeof(double2); }
+template <int LOG2M> size_t corr_smem() { return (size_t)(dit::Plan3<LOG2M>::MP + 2 * dit::Plan3<LOG2M>::M) * sizeof(double2); }
+template <int LOG2M> size_t fft_smem() { return (size_t)dit::Plan3<LOG2M>::MP * sizeof(double2); }
 
 template <class TIN> constexpr bool is_f32() { return sizeof(TIN) == sizeof(float2); }
 
-// correlation stage with its own FFT length (smaller M -> two CTAs per SM fit beside the accumulators)
-template <int LOG2M, int LR, class TIN> int wh_launch_corr(b200dd_wh *h, const void *x, const void *y, cudaStream_t st) {
-  using P = Plan<LOG2M, LR>;
+template <int LOG2M, class TIN> int wh_launch_corr(b200dd_wh *h, const void *x, const void *y, cudaStream_t st) {
+  using P = dit::Plan3<LOG2M>;
   bool &done = is_f32<TIN>() ? h->attr_corr_f32 : h->attr_corr_f64;
   if (!done) {
-    B2_CUDA(cudaFuncSetAttribute(wh_corr_kernel<LOG2M, LR, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_smem<LOG2M, LR>()));
+    B2_CUDA(cudaFuncSetAttribute(wh_corr_kernel<LOG2M, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)corr_smem<LOG2M>()));
     done = true;
   }
   CorrArgs ca;
   ca.x = x; ca.y = y; ca.partial = h->d_partial; ca.tw = h->d_tw_c; ca.N = h->N; ca.xs = make_xs_map(h->N, h->delayMin);
   ca.nBins = h->nBins; ca.L = h->L; ca.nSegTotal = h->nSeg; ca.segPerCta = h->segPerCta;
-  ca.xw_out = h->d_xw;
-  wh_corr_kernel<LOG2M, LR, TIN><<<h->gridCorr, P::NT, corr_smem<LOG2M, LR>(), st>>>(ca);
+  wh_corr_kernel<LOG2M, TIN><<<h->gridCorr, P::NT, corr_smem<LOG2M>(), st>>>(ca);
   B2_LAUNCH_CHECK();
   return B200DD_OK;
 }
 
-template <int LOG2M, int LR, class TIN> int wh_launch_apply(b200dd_wh *h, const void *x, const void *y, void *y_out, cudaStream_t st) {
-  using P = Plan<LOG2M, LR>;
+template <int LOG2M, class TIN> int wh_launch_apply(b200dd_wh *h, const void *x, const void *y, void *y_out, cudaStream_t st) {
+  using P = dit::Plan3<LOG2M>;
   bool &done = is_f32<TIN>() ? h->attr_apply_f32 : h->attr_apply_f64;
   if (!done) {
-    B2_CUDA(cudaFuncSetAttribute(wh_apply_kernel<LOG2M, LR, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M, LR>()));
-    B2_CUDA(cudaFuncSetAttribute(wh_wspec_kernel<LOG2M, LR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M, LR>()));
+    B2_CUDA(cudaFuncSetAttribute(wh_apply_kernel<LOG2M, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M>()));
+    B2_CUDA(cudaFuncSetAttribute(wh_wspec_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M>()));
     done = true;
   }
-  wh_wspec_kernel<LOG2M, LR><<<1, P::NT, fft_smem<LOG2M, LR>(), st>>>(h->d_w, h->nBins, h->d_what, h->d_tw_a);
+  wh_wspec_kernel<LOG2M><<<1, P::NT, fft_smem<LOG2M>(), st>>>(h->d_w, h->nBins, h->d_what, h->d_tw_a);
   B2_LAUNCH_CHECK();
   ApplyArgs aa;
   aa.x = x; aa.y = y; aa.y_out = y_out; aa.what = h->d_what; aa.tw = h->d_tw_a; aa.status = h->d_status;
   aa.N = h->N; aa.xs = make_xs_map(h->N, h->delayMin); aa.nBins = h->nBins; aa.Lout = h->Lout;
-  aa.xw = h->d_xw;
-  wh_apply_kernel<LOG2M, LR, TIN><<<h->d_xw ? h->nSeg + 1 : h->gridApply, P::NT, fft_smem<LOG2M, LR>(), st>>>(aa);
+  wh_apply_kernel<LOG2M, TIN><<<h->gridApply, P::NT, fft_smem<LOG2M>(), st>>>(aa);
   B2_LAUNCH_CHECK();
   return B200DD_OK;
 }
@@ -856,9 +824,7 @@ int wh_launch_solve(b200dd_wh *h, cudaStream_t st) {
   sa.partial = h->d_partial; sa.nPartial = h->gridCorr; sa.nBins = h->nBins;
   sa.a_out = h->d_a; sa.b_out = h->d_b; sa.w_out = h->d_w; sa.status = h->d_status;
   const int threads = ((h->nBins + 31) / 32) * 32;
-  const char *senv = getenv("B200DD_WH_SOLVE_SHORT");  // read per call: the parity tests toggle it
-  const int split_env = senv ? atoi(senv) : 1;
-  if (split_env && threads + 32 <= 1024) {  // includes the reference's configuration (410 taps)
+  if (h->solve_short && threads + 32 <= 1024) {  // includes the reference's configuration (410 taps)
     if (threads + 32 <= 512) wh_solve_short_kernel<512><<<1, threads + 32, solve_smem, st>>>(sa);
     else wh_solve_short_kernel<1024><<<1, threads + 32, solve_smem, st>>>(sa);
   } else if (h->nBins <= 1024) {
@@ -875,10 +841,10 @@ template <class TIN> int wh_dispatch(b200dd_wh *h, const void *x, const void *y,
   int rc = B200DD_ERR_GEOMETRY;
   if (ev) B2_CUDA(cudaEventRecord(ev[0], st));
   switch (h->log2m_c) {
-    case 9: rc = h->lr == 3 ? wh_launch_corr<9, 3, TIN>(h, x, y, st) : wh_launch_corr<9, 4, TIN>(h, x, y, st); break;
-    case 10: rc = h->lr == 3 ? wh_launch_corr<10, 3, TIN>(h, x, y, st) : wh_launch_corr<10, 4, TIN>(h, x, y, st); break;
-    case 11: rc = h->lr == 3 ? wh_launch_corr<11, 3, TIN>(h, x, y, st) : wh_launch_corr<11, 4, TIN>(h, x, y, st); break;
-    case 12: rc = h->lr == 3 ? wh_launch_corr<12, 3, TIN>(h, x, y, st) : wh_launch_corr<12, 4, TIN>(h, x, y, st); break;
+    case 9: rc = wh_launch_corr<9, TIN>(h, x, y, st); break;
+    case 10: rc = wh_launch_corr<10, TIN>(h, x, y, st); break;
+    case 11: rc = wh_launch_corr<11, TIN>(h, x, y, st); break;
+    case 12: rc = wh_launch_corr<12, TIN>(h, x, y, st); break;
   }
   if (rc != B200DD_OK) return rc == B200DD_ERR_GEOMETRY ? geom_fail("WienerHopf FFT length out of range") : rc;
   if (ev) B2_CUDA(cudaEventRecord(ev[1], st));
@@ -887,10 +853,10 @@ template <class TIN> int wh_dispatch(b200dd_wh *h, const void *x, const void *y,
   if (ev) B2_CUDA(cudaEventRecord(ev[2], st));
   rc = B200DD_ERR_GEOMETRY;
   switch (h->log2m_a) {
-    case 9: rc = h->lr == 3 ? wh_launch_apply<9, 3, TIN>(h, x, y, y_out, st) : wh_launch_apply<9, 4, TIN>(h, x, y, y_out, st); break;
-    case 10: rc = h->lr == 3 ? wh_launch_apply<10, 3, TIN>(h, x, y, y_out, st) : wh_launch_apply<10, 4, TIN>(h, x, y, y_out, st); break;
-    case 11: rc = h->lr == 3 ? wh_launch_apply<11, 3, TIN>(h, x, y, y_out, st) : wh_launch_apply<11, 4, TIN>(h, x, y, y_out, st); break;
-    case 12: rc = h->lr == 3 ? wh_launch_apply<12, 3, TIN>(h, x, y, y_out, st) : wh_launch_apply<12, 4, TIN>(h, x, y, y_out, st); break;
+    case 9: rc = wh_launch_apply<9, TIN>(h, x, y, y_out, st); break;
+    case 10: rc = wh_launch_apply<10, TIN>(h, x, y, y_out, st); break;
+    case 11: rc = wh_launch_apply<11, TIN>(h, x, y, y_out, st); break;
+    case 12: rc = wh_launch_apply<12, TIN>(h, x, y, y_out, st); break;
   }
   if (rc != B200DD_OK) return rc == B200DD_ERR_GEOMETRY ? geom_fail("WienerHopf FFT length out of range") : rc;
   if (ev) B2_CUDA(cudaEventRecord(ev[3], st));
@@ -917,7 +883,7 @@ int wh_pick_log2m(const b200dd_wh *h, const char *env1, const char *env2) {
 }
 
 void wh_plan(b200dd_wh *h) {
-  if (const char *e = getenv("B200DD_WH_RADIX")) h->lr = atoi(e) == 8 ? 3 : 4;
+  if (const char *e = getenv("B200DD_WH_SOLVE_SHORT")) h->solve_short = atoi(e) != 0;
   h->log2m_c = wh_pick_log2m(h, "B200DD_WH_LOG2M", "B200DD_WH_CORR_LOG2M");
   h->log2m_a = wh_pick_log2m(h, "B200DD_WH_LOG2M", "B200DD_WH_APPLY_LOG2M");
   if (!h->log2m_c || !h->log2m_a) return;
@@ -982,13 +948,6 @@ int b200dd_wh_create(int32_t delay_min, int32_t delay_max, uint32_t n_samples, i
     B2_CUDA(cudaMalloc(&h->d_what, sizeof(double2) * M));
     B2_CUDA(cudaMalloc(&h->d_status, sizeof(int)));
     B2_CUDA(cudaMemset(h->d_status, 0, sizeof(int)));
-    // B200DD_WH_REUSE=1 (needs the same FFT plan in both stages): keep the reference-window spectra of the
-    // correlation stage for the filter stage (16 M bytes per segment; skipped above 1 GB).  Measured on B200
-    // it saves 8 us in the filter kernel and costs as much elsewhere (70 MB of extra traffic per CPI through
-    // L2 while four CPIs are in flight: profiles/r01_summary.md), so it is opt-in.
-    const char *re = getenv("B200DD_WH_REUSE");
-    const size_t xw_bytes = sizeof(double2) * (size_t)h->nSeg * (size_t)Mc;
-    if (h->log2m_c == h->log2m_a && re && atoi(re) == 1 && xw_bytes <= ((size_t)1 << 30)) B2_CUDA(cudaMalloc(&h->d_xw, xw_bytes));
     return B200DD_OK;
   };
   int rc = body();
@@ -1011,7 +970,6 @@ void b200dd_wh_destroy(b200dd_wh *h) {
     free_dev(h->d_what);
     free_dev(h->d_status);
     free_dev(h->d_xd);
-    free_dev(h->d_xw);
     free_dev(h->d_yd);
     if (h->stream) cudaStreamDestroy(h->stream);
   }

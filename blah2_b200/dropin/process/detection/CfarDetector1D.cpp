@@ -35,7 +35,9 @@ std::unique_ptr<Detection> CfarDetector1D::process(Map<std::complex<double>> *x)
   const int rc = b200dd_det_process_host(handle, B200DD_DET_CFAR, reinterpret_cast<const double *>(m.cells.data()),
                                          m.nDop, m.nDel, m.delay.data(), m.doppler.data(), x->noisePower, d.data(),
                                          f.data(), s.data(), cap, &n);
-  if (rc != B200DD_OK && rc != B200DD_ERR_CAPACITY)
+  // B200DD_ERR_CAPACITY: more detections than the device lists hold (min(cells, 2^18)) -- the list would be
+  // truncated, which the reference never does, so that is an error here too
+  if (rc != B200DD_OK)
     throw std::runtime_error(std::string("CfarDetector1D::process: ") + b200dd_last_error());
   if (n > cap) n = cap;
   return b200dd_dropin::to_detection(d, f, s, n);

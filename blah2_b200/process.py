@@ -454,10 +454,12 @@ class Pipeline:
         return out
 
     def _result(self, res, want_map_arr=None):
-        k = min(res.n_detections, self.cap)
+        skipped = res.filter_status != capi.OK
+        # a failed clutter-filter solve skips the CPI (blah2.cpp:270-273): no detections, no metrics, no map product
+        k = 0 if skipped else min(res.n_detections, self.cap)
         det = Detection(self._od[:k].copy(), self._of[:k].copy(), self._os[:k].copy())
-        return dict(skipped=res.filter_status != capi.OK, noisePower=res.noise_power, maxPower=res.max_power,
-                    detections=det, map=want_map_arr)
+        return dict(skipped=skipped, noisePower=res.noise_power, maxPower=res.max_power,
+                    detections=det, map=None if skipped else want_map_arr)
 
     def process(self, x, y, want_map=True, map_out=None):
         """Host path: complex128 arrays (pinned torch tensors / numpy).  Synchronous."""

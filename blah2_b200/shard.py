@@ -77,6 +77,11 @@ def caf_single_cpi_sharded(amb, d_x_local: torch.Tensor, d_y_local: torch.Tensor
     b0, nb = block_range(n_dop, rank, world)
     assert d_x_local.numel() == nb * n_corr and d_y_local.numel() == nb * n_corr, "local IQ must hold exactly the rank's batches"
     dev = d_x_local.device
+    # The torch operations around the two kernels (copies, collectives, transposes) run on torch's CURRENT stream;
+    # the kernels must be ordered with them, so without an explicit stream they go onto that one -- never onto the
+    # handle's private non-blocking stream.  An explicit stream must be current while this runs.
+    if stream is None and dev.type == "cuda":
+        stream = torch.cuda.current_stream(dev)
     s_ptr = stream.cuda_stream if stream is not None and hasattr(stream, "cuda_stream") else stream
     R_local = torch.empty((nb, n_del), dtype=torch.complex64, device=dev)
     amb.range_device(d_x_local, d_y_local, b0, nb, R_local, s_ptr)

@@ -42,9 +42,8 @@
  *   B200DD_CAF_LOG2M / B200DD_CAF_PARTS      range-correlation FFT length (2^k) / CTAs per batch
  *   B200DD_CAF_GROUPS                        warp groups per range CTA, each on its own segments (1..4)
  *   B200DD_CAF_TMA=1                         stage IQ segments through shared memory with bulk async copies
- *   B200DD_WH_LOG2M, B200DD_WH_CORR_LOG2M, B200DD_WH_APPLY_LOG2M, B200DD_WH_RADIX   WienerHopf FFT plans
+ *   B200DD_WH_LOG2M, B200DD_WH_CORR_LOG2M, B200DD_WH_APPLY_LOG2M   WienerHopf FFT plans
  *   B200DD_WH_SOLVE_SHORT=0                  generic Toeplitz solve kernel also for <= 992 taps
- *   B200DD_WH_REUSE=1                        filter stage reuses the correlation stage's window spectra
  *   B200DD_PIPELINE_GRAPH=1 / 0              CUDA-graph replay of the device chain for every buffer triple / never
  *                                            (default: only triples given to b200dd_pipeline_prepare_device)
  * None of them changes results beyond the rounding of a different FFT factorisation.
@@ -245,7 +244,10 @@ B200DD_API int b200dd_det_process_device(b200dd_det *h, int last_stage, const vo
 
 /* Fully asynchronous variant for device-resident streams of CPIs: Map::set_metrics is evaluated
  * on the device first (blah2.cpp:279) and its noisePower feeds the detector without a host round
- * trip; nothing is copied back until b200dd_det_chain_fetch (which synchronises the stream). */
+ * trip; nothing is copied back until b200dd_det_chain_fetch (which synchronises the stream).
+ * last_stage = 0 runs Map::set_metrics only (detection disabled: the fetch then reports 0 detections).
+ * A CFAR stage that finds more detections than the handle's list capacity (min(cells, 2^18)) makes the
+ * fetch return B200DD_ERR_CAPACITY: the later stages saw a truncated list. */
 B200DD_API int b200dd_det_chain_device_async(b200dd_det *h, int last_stage, const void *d_map, uint32_t n_dop,
                                              uint32_t n_del, const int32_t *delay, const double *doppler,
                                              void *stream);
@@ -340,7 +342,8 @@ typedef struct {
 } b200dd_pipeline_params;
 
 typedef struct {
-  int32_t filter_status;   /* B200DD_OK, or B200DD_FILTER_FAILED: CPI skipped like blah2.cpp:270-273 */
+  int32_t filter_status;   /* B200DD_OK, or B200DD_FILTER_FAILED: the CPI is skipped like blah2.cpp:270-273 --
+                              n_detections, noise_power and max_power are then 0 and the map buffer is not a product */
   uint32_t n_detections;
   double noise_power;      /* Map::noisePower */
   double max_power;        /* Map::maxPower   */

@@ -41,3 +41,16 @@ def test_cta_fft_core_host_simulation(tmp_path):
                     os.path.join(ROOT, "tests", "native", "fft_sim.cu")], check=True, capture_output=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "FFT_SIM OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="no nvcc")
+def test_cta_fft_dit_core_host_simulation(tmp_path):
+    """blah2_b200/csrc/fft_dit.cuh (the fused-butterfly decimation-in-time core of the WienerHopf kernels) executed
+    on the CPU: forward against a long-double DFT and forward -> inverse through the register hand-off, M = 512..4096,
+    float and double."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "fft_dit_sim")
+    subprocess.run([nvcc, "-std=c++17", "-O1", "-Wno-deprecated-gpu-targets", "-o", exe,
+                    os.path.join(ROOT, "tests", "native", "fft_dit_sim.cu")], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "FFT_DIT_SIM OK" in r.stdout, r.stdout + r.stderr

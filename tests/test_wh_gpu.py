@@ -124,10 +124,10 @@ def test_linearity_in_y_for_fixed_weights_property():
     assert np.linalg.norm(yf - y) < 0.05 * np.linalg.norm(y)
 
 
-@pytest.mark.parametrize("radix,log2m", [(8, 9), (8, 10), (8, 11), (8, 12), (16, 9), (16, 10), (16, 11), (16, 12)])
-def test_every_fft_plan_gives_the_same_filter(radix, log2m, relerr, monkeypatch):
-    """Base radix 8 / 16 and every FFT length of the FP64 kernels (B200DD_WH_RADIX, B200DD_WH_LOG2M)."""
-    monkeypatch.setenv("B200DD_WH_RADIX", str(radix))
+@pytest.mark.parametrize("log2m", [9, 10, 11, 12])
+def test_every_fft_plan_gives_the_same_filter(log2m, relerr, monkeypatch):
+    """Every FFT length of the FP64 kernels (B200DD_WH_LOG2M): middle radix 2, 4, 8, 16 of the DIT plan."""
+    radix = 16
     monkeypatch.setenv("B200DD_WH_LOG2M", str(log2m))
     n, dm, dM = 50021, -5, 70
     sc = _scene(n, 13)
@@ -155,31 +155,3 @@ def test_both_solve_kernels_give_the_same_weights(case, relerr, monkeypatch):
     assert relerr(ws["1"], ws["0"])[0] < 1e-11
 
 
-@pytest.mark.parametrize("case", [(5000, -3, 20, 1), (20011, -10, 40, 2), (100000, 2, 60, 5), (200000, -10, 400, 4),
-                                  (300000, -10, 1200, 6)])
-def test_kept_window_spectra_give_the_same_filter_output(case, relerr, monkeypatch):
-    """With B200DD_WH_REUSE=1 the correlation stage keeps the spectra of its reference windows and the filter
-    stage multiplies them by the weight spectrum instead of transforming x again (output blocks shifted by
-    the filter history, first nBins-1 outputs from a block of their own).  The default is the two-transform
-    path; both must agree to rounding, on the host (complex128) and device (complex64) paths."""
-    import torch
-    n, dm, dM, seed = case
-    sc = _scene(n, seed)
-    ys, yd = {}, {}
-    for mode in ("1", "0"):
-        monkeypatch.setenv("B200DD_WH_REUSE", mode)
-        wh = WienerHopf(dm, dM, n)
-        ok, ys[mode] = wh.process(sc.x, sc.y)
-        assert ok
-        dx = torch.from_numpy(sc.x.astype(np.complex64)).cuda()
-        dy = torch.from_numpy(sc.y.astype(np.complex64)).cuda()
-        out = torch.empty_like(dy)
-        torch.cuda.synchronize()
-        wh.process_device(dx, dy, out)
-        torch.cuda.synchronize()
-        yd[mode] = out.cpu().numpy()
-    e = relerr(ys["1"], ys["0"])
-    assert e[0] < 1e-12 and e[1] < 1e-12, e
-    assert relerr(yd["1"], yd["0"])[0] < 1e-6   # complex64 output rounding
-    ok_ref, y_ref = O.wienerhopf_process(sc.x, sc.y, dm, dM)
-    assert relerr(ys["1"], y_ref)[0] < 1e-9
