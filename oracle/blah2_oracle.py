@@ -29,10 +29,44 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
+import os
+
 try:  # scipy is present in the image; keep the import local to the solve
     import scipy.linalg as _sla
 except Exception:  # pragma: no cover
     _sla = None
+try:
+    import scipy.fft as _sfft
+except Exception:  # pragma: no cover
+    _sfft = None
+
+
+class _FFT:
+    """The DFTs of this file.  Default: numpy's pocketfft on one thread.  BLAH2_ORACLE_WORKERS=k (k = -1: every
+    core) switches to scipy.fft -- the same pocketfft algorithm -- with k worker threads, for the full-size
+    BASELINE configurations (2e7 .. 8e7 samples) the GPU tests check live; results agree to ~1e-16."""
+
+    @staticmethod
+    def _workers():
+        try:
+            return int(os.environ.get("BLAH2_ORACLE_WORKERS", "0"))
+        except ValueError:
+            return 0
+
+    def fft(self, a, n=None, axis=-1):
+        w = self._workers()
+        if w and _sfft is not None:
+            return _sfft.fft(a, n=n, axis=axis, workers=w)
+        return np.fft.fft(a, n=n, axis=axis)
+
+    def ifft(self, a, n=None, axis=-1):
+        w = self._workers()
+        if w and _sfft is not None:
+            return _sfft.ifft(a, n=n, axis=axis, workers=w)
+        return np.fft.ifft(a, n=n, axis=axis)
+
+
+_fft = _FFT()
 
 
 # --------------------------------------------------------------------------------------
@@ -87,7 +121,7 @@ def spectrum_process(x: np.ndarray, n: int, bandwidth: float):
     samples (:36-40), ``fftshift[i] = X[(i + int(nfft/2) + 1) % nfft]`` (:43-47), every decimation-th
     entry kept (:50-54).  Returns (spectrum, frequency); x is read, not consumed (get_data copies, :35)."""
     decimation, nSpectrum, nfft = spectrum_geometry(n, bandwidth)
-    X = np.fft.fft(np.asarray(x, dtype=np.complex128)[:nfft])
+    X = _fft.fft(np.asarray(x, dtype=np.complex128)[:nfft])
     i = np.arange(0, nfft, decimation, dtype=np.int64)
     return X[(i + nfft // 2 + 1) % nfft], spectrum_frequency(n, bandwidth)
 
@@ -180,10 +214,10 @@ def range_matrix(x: np.ndarray, y: np.ndarray, g: Geometry, chunk: int = 64) -> 
     # dataCorr[nDel + delayMin + j]  with dataCorr = [z[nfft-nDel .. nfft-1], z[0 .. nDel]]
     idx = np.where(lags >= 0, lags, nfft + lags)
     for s in range(0, nD, chunk):
-        X = np.fft.fft(xb[s : s + chunk], n=nfft, axis=1)
-        Y = np.fft.fft(yb[s : s + chunk], n=nfft, axis=1)
+        X = _fft.fft(xb[s : s + chunk], n=nfft, axis=1)
+        Y = _fft.fft(yb[s : s + chunk], n=nfft, axis=1)
         Z = (Y * np.conj(X)) / float(nfft)
-        z = np.fft.ifft(Z, axis=1) * nfft  # FFTW backward is unnormalised
+        z = _fft.ifft(Z, axis=1) * nfft  # FFTW backward is unnormalised
         R[s : s + chunk] = z[:, idx]
     return R
 
@@ -192,7 +226,7 @@ def doppler_transform(R: np.ndarray, g: Geometry) -> np.ndarray:
     """A5 -- Ambiguity.cpp:152-169: forward DFT of length nDop down every delay column,
     then out[k] = D[(k + nDop/2 + 1) % nDop] (an fftshift for odd nDop)."""
     nD = g.nDopplerBins
-    D = np.fft.fft(R, axis=0)
+    D = _fft.fft(R, axis=0)
     k = (np.arange(nD) + nD // 2 + 1) % nD
     return D[k, :]
 
@@ -252,13 +286,13 @@ def wienerhopf_weights(x: np.ndarray, y: np.ndarray, delayMin: int, delayMax: in
     t = (np.arange(N, dtype=np.int64) - int(delayMin)) % (1 << 32)
     xs = x[((t % N) + N) % N]
     ys = y
-    X = np.fft.fft(xs)  # :72
-    Y = np.fft.fft(ys)  # :73
+    X = _fft.fft(xs)  # :72
+    Y = _fft.fft(ys)  # :73
     # :76-84  a[k] = conj(IFFT_unnorm(|X|^2)[k]) / N
-    dataA = np.fft.ifft(X * np.conj(X)) * N
+    dataA = _fft.ifft(X * np.conj(X)) * N
     a = np.conj(dataA[:nBins]) / float(N)
     # :100-108  b[k] = IFFT_unnorm(Y conj X)[k] / N
-    dataB = np.fft.ifft(Y * np.conj(X)) * N
+    dataB = _fft.ifft(Y * np.conj(X)) * N
     b = dataB[:nBins] / float(N)
     # :85-97  A = toeplitz(a) (no conjugation), then conj where i > j
     ii, jj = np.meshgrid(np.arange(nBins), np.arange(nBins), indexing="ij")
@@ -285,7 +319,7 @@ def wienerhopf_apply(xs: np.ndarray, y: np.ndarray, w: np.ndarray) -> np.ndarray
     nBins = w.shape[0]
     L = N + nBins + 1
     Lf = next_hamming(L)
-    F = np.fft.ifft(np.fft.fft(xs, n=Lf) * np.fft.fft(w, n=Lf))
+    F = _fft.ifft(_fft.fft(xs, n=Lf) * _fft.fft(w, n=Lf))
     return np.asarray(y, dtype=np.complex128) - F[:N]
 
 

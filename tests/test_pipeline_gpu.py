@@ -97,6 +97,46 @@ def test_pipeline_filter_failure_is_reported():
     assert out["skipped"]
 
 
+def test_failed_solve_skips_the_cpi_like_the_reference():
+    """`if (!filter->process(x, y)) continue;` (blah2.cpp:270-273): with a reference channel whose autocorrelation
+    matrix is not positive definite (all zeros) the CPI is skipped -- no detections, no metrics, no map product --
+    on the host, int16 and device entry points, although detection is enabled and the surveillance channel is
+    full of strong 'targets'."""
+    import torch
+    n = 8192
+    det = dict(pfa=1e-3, nGuard=1, nTrain=4, minDelay=0, minDoppler=0.0, nCentroid=2)
+    pipe = Pipeline(-3, 20, -50, 50, 10000, n, clutter=(-2, 10), detection=det)
+    rng = np.random.default_rng(5)
+    y = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 100.0
+    y[::97] += 1e5
+    ok_ref, _ = O.wienerhopf_process(np.zeros(n, complex), y, -2, 10)
+    assert not ok_ref
+    out = pipe.process(np.zeros(n, complex), y)
+    assert out["skipped"] and out["detections"].get_nDetections() == 0
+    assert out["noisePower"] == 0.0 and out["maxPower"] == 0.0 and out["map"] is None
+    dx = torch.zeros(n, dtype=torch.complex64, device="cuda")
+    dy = torch.from_numpy(y.astype(np.complex64)).cuda()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        pipe.submit_device(dx, dy, None, s.cuda_stream)
+        dev = pipe.fetch(s.cuda_stream)
+    assert dev["skipped"] and dev["detections"].get_nDetections() == 0 and dev["noisePower"] == 0.0
+    # the next good CPI on the same handle is processed normally
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 100.0
+    good = pipe.process(x, 0.5 * x + y * 1e-3)
+    assert not good["skipped"] and good["noisePower"] != 0.0
+
+
+def test_set_metrics_runs_without_detection(relerr):
+    """Map::set_metrics follows every Ambiguity::process (blah2.cpp:278-279), detection enabled or not."""
+    geom = (-3, 20, -50, 50, 10000, 4000)
+    x, y = random_iq(geom[5], 3)
+    out = Pipeline(*geom, roundHamming=False).process(x, y)
+    noise, mx = O.set_metrics(out["map"])
+    assert abs(out["noisePower"] - noise) < 1e-3 and abs(out["maxPower"] - mx) < 1e-3
+    assert out["detections"].get_nDetections() == 0
+
+
 def test_rspduo_int16_ingest_matches_complex128_entry(relerr):
     """N1: the replay layout (int16 I1 Q1 I2 Q2) de-interleaved on the device gives the same CPI result
     as handing over complex128 buffers."""
