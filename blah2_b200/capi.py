@@ -139,6 +139,19 @@ SIGNATURES = [
     ("b200dd_pipeline_stream", _VP, [_VP]),
     ("b200dd_pipeline_enable_spectrum", C.c_int, [_VP, C.c_double, C.POINTER(C.c_uint32)]),
     ("b200dd_pipeline_fetch_spectrum", C.c_int, [_VP, _VP, C.c_uint32]),
+    ("b200dd_comm_get_unique_id", C.c_int, [_VP]),
+    ("b200dd_comm_create", C.c_int, [C.c_int32, C.c_int32, _VP, C.c_int32, C.POINTER(_VP)]),
+    ("b200dd_comm_destroy", None, [_VP]),
+    ("b200dd_comm_rank", C.c_int32, [_VP]),
+    ("b200dd_comm_world", C.c_int32, [_VP]),
+    ("b200dd_comm_stream", _VP, [_VP]),
+    ("b200dd_comm_gather_async", C.c_int, [_VP, _VP, _VP, C.c_size_t, C.c_int32, _VP]),
+    ("b200dd_comm_gatherv_async", C.c_int, [_VP, _VP, C.c_size_t, _VP, _VP, _VP, C.c_int32, _VP]),
+    ("b200dd_comm_allgatherv_async", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    ("b200dd_comm_allreduce_f64_async", C.c_int, [_VP, _VP, C.c_size_t, _VP]),
+    ("b200dd_comm_shift_right_async", C.c_int, [_VP, _VP, _VP, C.c_size_t, _VP]),
+    ("b200dd_comm_join", C.c_int, [_VP, _VP]),
+    ("b200dd_comm_sync", C.c_int, [_VP]),
 ]
 
 _lib = None

@@ -51,6 +51,7 @@
 #ifndef B200DD_H
 #define B200DD_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -397,6 +398,44 @@ B200DD_API void *b200dd_pipeline_stream(b200dd_pipeline *h);
  * synchronises the pipeline's stream itself). */
 B200DD_API int b200dd_pipeline_enable_spectrum(b200dd_pipeline *h, double bandwidth, uint32_t *n_spectrum);
 B200DD_API int b200dd_pipeline_fetch_spectrum(b200dd_pipeline *h, double *spectrum_out, uint32_t cap);
+
+/* ------------------------------------------------------------------------------------------------
+ * Inter-GPU exchanges (one process per GPU, NCCL over NVLink / NVSwitch).  The reference has no
+ * distributed code; these serve the two shardings of SURVEY.md s8(e): independent CPIs round-robin
+ * over the GPUs (the only communication: gather of finished maps to one rank) and one large CPI split
+ * over the GPUs (all-gather of the range matrix, gather of the delay-column tiles; for the clutter filter
+ * an all-reduce of the partial correlations and a halo from the left neighbour).
+ * NCCL is resolved with dlopen("libnccl.so.2") at the first call: libb200dd.so has no link-time dependency on it.
+ * Every *_async call orders the communicator's own stream after what is enqueued so far on `after` (a CUDA
+ * stream, nullable), enqueues the exchange there and returns; b200dd_comm_join makes a compute stream wait for
+ * everything enqueued on the communicator so far.  All ranks must issue the same sequence of calls.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b200dd_comm b200dd_comm;
+#define B200DD_COMM_ID_BYTES 128
+
+/* rank 0 creates the 128-byte id and hands it to the other ranks by any host-side means */
+B200DD_API int b200dd_comm_get_unique_id(uint8_t *id128);
+B200DD_API int b200dd_comm_create(int32_t rank, int32_t world, const uint8_t *id128, int32_t device, b200dd_comm **out);
+B200DD_API void b200dd_comm_destroy(b200dd_comm *c);
+B200DD_API int32_t b200dd_comm_rank(const b200dd_comm *c);
+B200DD_API int32_t b200dd_comm_world(const b200dd_comm *c);
+B200DD_API void *b200dd_comm_stream(b200dd_comm *c);
+
+/* every rank contributes `bytes` from d_send; rank dst receives rank r's block at d_recv + r * bytes
+ * (d_recv may be NULL elsewhere) */
+B200DD_API int b200dd_comm_gather_async(b200dd_comm *c, const void *d_send, void *d_recv, size_t bytes, int32_t dst,
+                                        void *after);
+/* blocks of different sizes: rank r's send_bytes must equal bytes[r]; block r lands at d_recv + offsets[r] */
+B200DD_API int b200dd_comm_gatherv_async(b200dd_comm *c, const void *d_send, size_t send_bytes, void *d_recv,
+                                         const size_t *bytes, const size_t *offsets, int32_t dst, void *after);
+B200DD_API int b200dd_comm_allgatherv_async(b200dd_comm *c, const void *d_send, void *d_recv, const size_t *bytes,
+                                            const size_t *offsets, void *after);
+/* in-place sum of `count` doubles over the ranks */
+B200DD_API int b200dd_comm_allreduce_f64_async(b200dd_comm *c, void *d_buf, size_t count, void *after);
+/* rank r sends `bytes` to rank r + 1 and receives as many from rank r - 1 (no wrap-around) */
+B200DD_API int b200dd_comm_shift_right_async(b200dd_comm *c, const void *d_send, void *d_recv, size_t bytes, void *after);
+B200DD_API int b200dd_comm_join(b200dd_comm *c, void *stream);
+B200DD_API int b200dd_comm_sync(b200dd_comm *c);
 
 #ifdef __cplusplus
 }
