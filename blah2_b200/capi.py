@@ -152,6 +152,8 @@ SIGNATURES = [
     ("b200dd_comm_shift_right_async", C.c_int, [_VP, _VP, _VP, C.c_size_t, _VP]),
     ("b200dd_comm_join", C.c_int, [_VP, _VP]),
     ("b200dd_comm_sync", C.c_int, [_VP]),
+    ("b200dd_ubench_fp64_tflops", C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
+    ("b200dd_bind_host_to_device", C.c_int, [C.c_int32, C.c_char_p, C.c_int32]),
 ]
 
 _lib = None

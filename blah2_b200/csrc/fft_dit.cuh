@@ -217,19 +217,32 @@ template <class T, int LOG2M> B2_HD void pass1_load(const cpx<T> *s, int tid, cp
     for (int k = 0; k < RM; k++) v[j * RM + k] = s[lay1(hi, k, lo)];
   }
 }
-template <class T, int LOG2M, int DIR> B2_HD void pass1_compute(const cpx<T> *__restrict__ tw, int tid, cpx<T> (&v)[16]) {
+// table value of thread tid's middle-pass twiddle base, exp(-2 pi i lo / (16 RM)) with lo = tid & 15 (NT is a
+// multiple of 16, so all of a thread's middle-pass butterflies share it), and of its last-pass base exp(-2 pi i tid / M):
+// the same two numbers for EVERY transform of a kernel -- load them once (a dependent global load in front of each
+// pass cost the first kernels built on this core 10-12 % of their stall samples, profiles/r02_summary.md)
+template <class T, int LOG2M> B2_HD cpx<T> pass1_twiddle(const cpx<T> *__restrict__ tw, int tid) {
+  using P = Plan3<LOG2M>;
+  return tw[(tid & 15) * (P::M / (16 * P::RM))];
+}
+template <class T, int LOG2M> B2_HD cpx<T> pass2_twiddle(const cpx<T> *__restrict__ tw, int tid) { return tw[tid]; }
+
+template <class T, int LOG2M, int DIR> B2_HD void pass1_compute(cpx<T> tabv, cpx<T> (&v)[16]) {
   using P = Plan3<LOG2M>;
   constexpr int RM = P::RM;
+  static_assert(P::NT % 16 == 0, "one middle-pass twiddle base per thread");
 #pragma unroll
   for (int j = 0; j < P::BPT; j++) {
-    const int lo = (tid + P::NT * j) & 15;
     cpx<T> u[RM];
 #pragma unroll
     for (int k = 0; k < RM; k++) u[k] = v[j * RM + k];
-    dft_tw<T, DIR, RM>(u, tw[lo * (P::M / (16 * RM))]);
+    dft_tw<T, DIR, RM>(u, tabv);
 #pragma unroll
     for (int k = 0; k < RM; k++) v[j * RM + k] = u[k];
   }
+}
+template <class T, int LOG2M, int DIR> B2_HD void pass1_compute(const cpx<T> *__restrict__ tw, int tid, cpx<T> (&v)[16]) {
+  pass1_compute<T, LOG2M, DIR>(pass1_twiddle<T, LOG2M>(tw, tid), v);
 }
 template <class T, int LOG2M> B2_HD void pass1_store(cpx<T> *s, int tid, const cpx<T> (&v)[16]) {
   using P = Plan3<LOG2M>;
@@ -248,6 +261,7 @@ template <class T, int LOG2M> B2_HD void pass2_load(const cpx<T> *s, int tid, cp
 #pragma unroll
   for (int k = 0; k < 16; k++) v[k] = s[lay1(k, tid >> 4, tid & 15)];
 }
+template <class T, int LOG2M, int DIR> B2_HD void pass2_compute(cpx<T> tabv, cpx<T> (&v)[16]) { dft_tw<T, DIR, 16>(v, tabv); }
 template <class T, int LOG2M, int DIR> B2_HD void pass2_compute(const cpx<T> *__restrict__ tw, int tid, cpx<T> (&v)[16]) {
   dft_tw<T, DIR, 16>(v, tw[tid]);
 }

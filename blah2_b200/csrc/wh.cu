@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "fft_core.cuh"
 #include "fft_dit.cuh"
+#include "tma_stage.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -95,105 +96,188 @@ struct CorrArgs {
   int nBins, L, nSegTotal, segPerCta;
 };
 
-// One M-point window of a channel for the DIT transform (fft_dit.cuh): thread tid owns the window elements
-// m = tid + NT k, k < 16 (consecutive lanes -> consecutive samples).  The loads are issued early into `raw`
-// (unconditional, on clamped indices, so that all 16 are in flight together) and converted / masked when the
-// transform starts: element m is valid while m < lim.  MAPX applies the reference's index map of the shifted
-// reference channel; indices are circular over N (WienerHopf.cpp:76-108).
-template <int NT, bool MAPX, class TIN>
-__device__ __forceinline__ void win_issue(TIN (&raw)[16], const TIN *__restrict__ p, const XsMap &xs, uint32_t N, uint32_t n0,
-                                          int lim, int tid) {
-#pragma unroll
-  for (int k = 0; k < 16; k++) {
-    const int m = min(tid + NT * k, lim - 1);
-    uint32_t i = n0 + (uint32_t)m;
-    i = i >= N ? i - N : i;
-    raw[k] = p[MAPX ? xs(i) : i];
-  }
-}
-template <int NT, class TIN> __device__ __forceinline__ void win_convert(double2 (&v)[16], const TIN (&raw)[16], int lim, int tid) {
-#pragma unroll
-  for (int k = 0; k < 16; k++) {
-    const bool ok = tid + NT * k < lim;
-    v[k] = make_double2(ok ? (double)raw[k].x : 0.0, ok ? (double)raw[k].y : 0.0);
-  }
+// twiddle bases of a thread, loaded once per kernel (fft_dit.cuh pass1_twiddle / pass2_twiddle)
+struct TwPair { double2 t1, t2; };
+template <int LOG2M> __device__ __forceinline__ TwPair load_twiddles(const double2 *__restrict__ tw, int tid) {
+  TwPair t;
+  t.t1 = dit::pass1_twiddle<double, LOG2M>(tw, tid);
+  t.t2 = dit::pass2_twiddle<double, LOG2M>(tw, tid);
+  return t;
 }
 
-// v (the thread's 16 window elements) -> its 16 spectrum values X[tid + NT q], left in v[brev16(q)].
-// Three CTA barriers; the caller adds one before the buffer is written again.
-template <int LOG2M, int DIR> __device__ __forceinline__ void dit_transform(double2 *A, const double2 *__restrict__ tw, int tid, double2 (&v)[16]) {
+// v (the thread's 16 window elements m = tid + NT k) -> its 16 spectrum values X[tid + NT q], left in v[brev16(q)].
+// Two CTA barriers inside; the caller adds one before the buffer is written again.  AFTER_STORE runs between the
+// first barrier and the middle pass: every thread has consumed its inputs by then, so that is where the NEXT
+// window's staging copy is started.
+template <int LOG2M, int DIR, class F>
+__device__ __forceinline__ void dit_transform(double2 *A, const TwPair &tw, int tid, double2 (&v)[16], F after_store) {
   dit::pass0_store<double, LOG2M, DIR>(A, tid, v);
   __syncthreads();
+  after_store();
   dit::pass1_load<double, LOG2M>(A, tid, v);
-  dit::pass1_compute<double, LOG2M, DIR>(tw, tid, v);
+  dit::pass1_compute<double, LOG2M, DIR>(tw.t1, v);
   dit::pass1_store<double, LOG2M>(A, tid, v);
   __syncthreads();
   dit::pass2_load<double, LOG2M>(A, tid, v);
-  dit::pass2_compute<double, LOG2M, DIR>(tw, tid, v);
+  dit::pass2_compute<double, LOG2M, DIR>(tw.t2, v);
 }
+template <int LOG2M, int DIR> __device__ __forceinline__ void dit_transform(double2 *A, const TwPair &tw, int tid, double2 (&v)[16]) {
+  dit_transform<LOG2M, DIR>(A, tw, tid, v, [] {});
+}
+// Variant for kernels at the 128-register bound (two CTAs per SM): the two twiddle bases are requested at the top of
+// the transform -- the twiddle-free first pass covers their latency -- instead of living in registers across the
+// whole kernel.
+template <int LOG2M, int DIR, class F>
+__device__ __forceinline__ void dit_transform_ld(double2 *A, const double2 *__restrict__ twtab, int tid, double2 (&v)[16], F after_store) {
+  const double2 *p1 = twtab + (tid & 15) * (dit::Plan3<LOG2M>::M / (16 * dit::Plan3<LOG2M>::RM)), *p2 = twtab + tid;
+  TwPair tw;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(tw.t1.x), "=d"(tw.t1.y) : "l"(p1));
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(tw.t2.x), "=d"(tw.t2.y) : "l"(p2));
+  dit_transform<LOG2M, DIR>(A, tw, tid, v, after_store);
+}
+
+// One window of a channel: `lim` valid elements starting at circular index `start` of p (element m lives at
+// p[(start + m) mod N]), zero beyond.  When the window is one contiguous run of float2 it is staged by TMA
+// (tma_stage.cuh); otherwise (circular wrap, double2 input, the reference's index quirk for delayMin > 0) its
+// elements are loaded directly at the point of use.
+template <class TIN> struct WinDesc {
+  const TIN *p;
+  uint32_t start, N;
+  int lim;
+  bool contiguous;
+};
+
+// staged elements per window: k < 15 of the 16 per thread (15 NT float2 + 2 alignment slots fit beside the FFT
+// buffer and the two accumulators in 227 KB at M = 4096; element k = 15 travels through one prefetch register)
+template <int LOG2M> struct CorrStage { static constexpr int kElems = 15 * dit::Plan3<LOG2M>::NT; };
 
 // K3.  One CTA per SM walks segPerCta segments of L new samples.  Per segment three forward transforms of
 // M = L + nBins - 1 points: P = the segment zero-padded, W = the reference window, V = the surveillance window;
-// cross-spectra W conj(P) and V conj(P) are accumulated over the CTA's segments (shared memory, each thread
-// its own 16 bins), one inverse transform per correlation at the end.  The global loads of transform t + 1 are
-// issued before transform t's shared-memory passes (register prefetch: with one CTA of 8 warps per SM nothing
-// else hides their latency).
+// cross-spectra W conj(P) and V conj(P) are accumulated over the CTA's segments (shared memory, each thread its
+// own 16 bins), one inverse transform per correlation at the end.  float2 input: the next window is staged into
+// shared memory by a TMA bulk copy while the current one is transformed.
 template <int LOG2M, class TIN>
 __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_corr_kernel(CorrArgs a) {
   using P = dit::Plan3<LOG2M>;
   constexpr int NT = P::NT;
+  constexpr bool kStage = sizeof(TIN) == sizeof(float2);
+  constexpr int CAP = CorrStage<LOG2M>::kElems;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *A = reinterpret_cast<double2 *>(smem_raw);
   double2 *Za = A + P::MP;
   double2 *Zb = Za + P::M;
+  float2 *S = reinterpret_cast<float2 *>(Zb + P::M);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(S + CAP + 2);
   const int tid = threadIdx.x;
   const TIN *__restrict__ x = reinterpret_cast<const TIN *>(a.x);
   const TIN *__restrict__ y = reinterpret_cast<const TIN *>(a.y);
   const double2 zero = make_double2(0.0, 0.0);
+  const TwPair tw = load_twiddles<LOG2M>(a.tw, tid);
 #pragma unroll
   for (int q = 0; q < 16; q++) {
     Za[q * NT + tid] = zero;
     Zb[q * NT + tid] = zero;
   }
+  if constexpr (kStage) {
+    if (tid == 0) tma::mbar_init(mbar, 1);
+  }
+  __syncthreads();
   const int s0 = blockIdx.x * a.segPerCta;
   const int s1 = min(s0 + a.segPerCta, a.nSegTotal);
   const XsMap xs = a.xs;
   const uint32_t N = a.N;
-  auto seg_len = [&](int s) { return (int)min((uint32_t)a.L, N - (uint32_t)s * (uint32_t)a.L); };
-  TIN raw[16];
-  if (s0 < s1) win_issue<NT, true>(raw, x, xs, N, (uint32_t)s0 * (uint32_t)a.L, seg_len(s0), tid);
+  // window t (0: P, 1: W, 2: V) of segment s
+  auto describe = [&](int s, int t) {
+    WinDesc<TIN> d;
+    const uint32_t n0 = (uint32_t)s * (uint32_t)a.L;
+    const int len = (int)min((uint32_t)a.L, N - n0);
+    d.N = N;
+    d.lim = t == 0 ? len : len + a.nBins - 1;
+    if (t < 2) {
+      d.p = x;
+      d.start = xs(n0);
+      // the shifted reference is a pure rotation of x only for delayMin <= 0 (thr == 0)
+      d.contiguous = xs.thr == 0 && (uint64_t)d.start + (uint64_t)d.lim <= (uint64_t)N;
+    } else {
+      d.p = y;
+      d.start = n0;
+      d.contiguous = (uint64_t)n0 + (uint64_t)d.lim <= (uint64_t)N;
+    }
+    return d;
+  };
+  // element m of window d, t < 2 through the reference's index map when the window is not a plain run
+  auto direct = [&](const WinDesc<TIN> &d, int t, uint32_t n0, int m) {
+    uint32_t i = n0 + (uint32_t)min(m, d.lim - 1);
+    i = i >= N ? i - N : i;
+    return d.p[t < 2 ? xs(i) : i];
+  };
+  auto stage_window = [&](const WinDesc<TIN> &d) {
+    tma::Window w;
+    if (kStage && d.contiguous) w = tma::make_window(reinterpret_cast<const float2 *>(d.p) + d.start, min(d.lim, CAP));
+    return w;
+  };
+  uint32_t phase = 0;
+  TIN r15;  // element k = 15 of the NEXT window (beyond the staging buffer)
+  if (s0 < s1) {
+    const WinDesc<TIN> d = describe(s0, 0);
+    if constexpr (kStage) {
+      if (tid == 0) tma::issue(stage_window(d), S, mbar);
+    }
+    r15 = direct(d, 0, (uint32_t)s0 * (uint32_t)a.L, tid + 15 * NT);
+  }
+  double2 vxp[16];
   for (int s = s0; s < s1; s++) {
     const uint32_t n0 = (uint32_t)s * (uint32_t)a.L;
-    const int len = seg_len(s);
-    const int wlen = len + a.nBins - 1;
-    double2 vxp[16], v[16];
-    // P: the padded segment
-    win_convert<NT>(vxp, raw, len, tid);
-    win_issue<NT, true>(raw, x, xs, N, n0, wlen, tid);  // the same samples again + the next nBins-1: L1/L2 hits
-    dit_transform<LOG2M, -1>(A, a.tw, tid, vxp);
-    __syncthreads();
-    // W: the reference window; a-spectrum += W conj(P)
-    win_convert<NT>(v, raw, wlen, tid);
-    win_issue<NT, false>(raw, y, xs, N, n0, wlen, tid);
-    dit_transform<LOG2M, -1>(A, a.tw, tid, v);
 #pragma unroll
-    for (int q = 0; q < 16; q++) {
-      double2 acc = Za[q * NT + tid];
-      cfmac(acc, v[brev<16>(q)], vxp[brev<16>(q)]);
-      Za[q * NT + tid] = acc;
-    }
-    __syncthreads();
-    // V: the surveillance window; b-spectrum += V conj(P)
-    win_convert<NT>(v, raw, wlen, tid);
-    if (s + 1 < s1) win_issue<NT, true>(raw, x, xs, N, n0 + (uint32_t)a.L, seg_len(s + 1), tid);
-    dit_transform<LOG2M, -1>(A, a.tw, tid, v);
+    for (int t = 0; t < 3; t++) {
+      const WinDesc<TIN> d = describe(s, t);
+      const tma::Window w = stage_window(d);
+      double2 v[16];
+      if constexpr (kStage) {
+        tma::mbar_wait(mbar, phase);
+        phase ^= 1;
+      }
 #pragma unroll
-    for (int q = 0; q < 16; q++) {
-      double2 acc = Zb[q * NT + tid];
-      cfmac(acc, v[brev<16>(q)], vxp[brev<16>(q)]);
-      Zb[q * NT + tid] = acc;
+      for (int k = 0; k < 16; k++) {
+        const int m = tid + NT * k;
+        TIN e;
+        if (k == 15) {
+          e = r15;
+        } else {
+          e = direct(d, t, n0, m);
+          if constexpr (kStage) {
+            if (w.src) e = tma::read(w, S, min(m, d.lim - 1));
+          }
+        }
+        const bool ok = m < d.lim;
+        v[k] = make_double2(ok ? (double)e.x : 0.0, ok ? (double)e.y : 0.0);
+      }
+      // next window (of this or the next segment): staged while this one is transformed
+      const bool more = t < 2 || s + 1 < s1;
+      const int ns = t < 2 ? s : s + 1, nt = t < 2 ? t + 1 : 0;
+      dit_transform<LOG2M, -1>(A, tw, tid, v, [&] {
+        if (more) {
+          const WinDesc<TIN> dn = describe(ns, nt);
+          if constexpr (kStage) {
+            if (tid == 0) tma::issue(stage_window(dn), S, mbar);
+          }
+          r15 = direct(dn, nt, (uint32_t)ns * (uint32_t)a.L, tid + 15 * NT);
+        }
+      });
+      if (t == 0) {
+#pragma unroll
+        for (int q = 0; q < 16; q++) vxp[q] = v[q];
+      } else {
+        double2 *Z = t == 1 ? Za : Zb;  // a-spectrum += W conj(P), b-spectrum += V conj(P)
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+          double2 acc = Z[q * NT + tid];
+          cfmac(acc, v[brev<16>(q)], vxp[brev<16>(q)]);
+          Z[q * NT + tid] = acc;
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   const double scale = 1.0 / (double)P::M;
   double2 *pa = a.partial + (size_t)blockIdx.x * 2 * a.nBins;
@@ -202,7 +286,7 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_corr_kernel(CorrA
 #pragma unroll
   for (int q = 0; q < 16; q++) z[q] = Za[q * NT + tid];
   // IFFT gives ra[k] = sum xs[n+k] conj(xs[n]);  a[k] = conj(ra[k])  (WienerHopf.cpp:82-84)
-  dit_transform<LOG2M, +1>(A, a.tw, tid, z);
+  dit_transform<LOG2M, +1>(A, tw, tid, z);
 #pragma unroll
   for (int q = 0; q < 16; q++) {
     const int m = tid + NT * q;
@@ -211,7 +295,7 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_corr_kernel(CorrA
   __syncthreads();
 #pragma unroll
   for (int q = 0; q < 16; q++) z[q] = Zb[q * NT + tid];
-  dit_transform<LOG2M, +1>(A, a.tw, tid, z);
+  dit_transform<LOG2M, +1>(A, tw, tid, z);
 #pragma unroll
   for (int q = 0; q < 16; q++) {
     const int m = tid + NT * q;
@@ -638,13 +722,14 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_wspec_kernel(cons
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *A = reinterpret_cast<double2 *>(smem_raw);
   const int tid = threadIdx.x;
+  const TwPair t = load_twiddles<LOG2M>(tw, tid);
   double2 v[16];
 #pragma unroll
   for (int k = 0; k < 16; k++) {
     const int m = tid + NT * k;
     v[k] = m < nBins ? w[m] : make_double2(0.0, 0.0);
   }
-  dit_transform<LOG2M, -1>(A, tw, tid, v);
+  dit_transform<LOG2M, -1>(A, t, tid, v);
 #pragma unroll
   for (int q = 0; q < 16; q++) what[q * NT + tid] = v[brev<16>(q)];
 }
@@ -658,7 +743,7 @@ struct ApplyArgs {
   const int *status;
   uint32_t N;
   XsMap xs;
-  int nBins, Lout;
+  int nBins, Lout, nBlocks;
 };
 
 template <class TOUT> __device__ __forceinline__ void st_iq(TOUT *p, uint32_t i, double2 v);
@@ -667,77 +752,117 @@ template <> __device__ __forceinline__ void st_iq<float2>(float2 *p, uint32_t i,
 }
 template <> __device__ __forceinline__ void st_iq<double2>(double2 *p, uint32_t i, double2 v) { p[i] = v; }
 
-// K5.  One CTA per block of Lout outputs: overlap-save with the window of M = Lout + nBins - 1 shifted-reference
-// samples that ends at the block's last output; forward transform, multiply by the weight spectrum, inverse
-// transform, y' = y - conv / M.  y and y_out may be the same buffer (each element is read, then written, by the
-// same thread), hence no __restrict__ on them.
+// K5.  Overlap-save: block b produces the Lout outputs [b Lout, (b+1) Lout) from the window of
+// M = Lout + nBins - 1 shifted-reference samples that ends at the block's last output -- forward transform, multiply
+// by the weight spectrum, inverse transform, y' = y - conv / M.  PERSISTENT CTAs (two per SM at M = 4096) walk the
+// blocks b = blockIdx.x, + gridDim.x, ...: while block b is transformed the window of the CTA's next block is
+// staged into shared memory by a TMA bulk copy (float2 input).  y and y_out may be the same buffer (each element is read, then
+// written, by the same thread), hence no __restrict__ on them.
 template <int LOG2M, class TIN>
 __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, wh_min_ctas<LOG2M>()) wh_apply_kernel(ApplyArgs a) {
   using P = dit::Plan3<LOG2M>;
   constexpr int NT = P::NT;
+  constexpr bool kStage = sizeof(TIN) == sizeof(float2);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *A = reinterpret_cast<double2 *>(smem_raw);
+  float2 *S = reinterpret_cast<float2 *>(A + P::MP);
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(S + P::M + 2);
   const int tid = threadIdx.x;
   const TIN *__restrict__ x = reinterpret_cast<const TIN *>(a.x);
   const TIN *y = reinterpret_cast<const TIN *>(a.y);
   TIN *yo = reinterpret_cast<TIN *>(a.y_out);
   const int hist = a.nBins - 1;
-  const uint32_t i0 = (uint32_t)blockIdx.x * (uint32_t)a.Lout;
-  const int nOut = (int)min((uint32_t)a.Lout, a.N - i0);
-  if (nOut <= 0) return;
   if (*a.status != 0) {  // failed solve: surveillance channel passes through untouched
-    for (int m = tid; m < nOut; m += NT) st_iq<TIN>(yo, i0 + m, ld_iq(y, i0 + m));
+    for (int b = blockIdx.x; b < a.nBlocks; b += gridDim.x) {
+      const uint32_t i0 = (uint32_t)b * (uint32_t)a.Lout;
+      const int nOut = (int)min((uint32_t)a.Lout, a.N - i0);
+      for (int m = tid; m < nOut; m += NT) st_iq<TIN>(yo, i0 + m, ld_iq(y, i0 + m));
+    }
     return;
   }
-  // window element m <-> shifted-reference index i0 - hist + m (zero history before sample 0: the reference's
-  // LINEAR convolution, WienerHopf.cpp:125-153); branch-free: load from a clamped valid index, mask afterwards
   const XsMap xs = a.xs;
-  double2 v[16];
-  {
-    TIN raw[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-      const int64_t i = (int64_t)i0 - hist + (tid + NT * k);
-      const int64_t ic = i < 0 ? 0 : (i >= (int64_t)a.N ? (int64_t)a.N - 1 : i);
-      raw[k] = x[xs((uint32_t)ic)];
+  // window of block b: element m <-> shifted-reference index i0 - hist + m, valid while that index is in [0, N)
+  // and m < hist + nOut (zero history before sample 0: the reference's LINEAR convolution, WienerHopf.cpp:125-153).
+  // Staged when it is one contiguous run of x (delayMin <= 0 rotation, no wrap, not the first block).
+  auto stage_window = [&](int b) {
+    tma::Window w;
+    if constexpr (kStage) {
+      const int64_t first = (int64_t)b * a.Lout - hist;
+      const int nOut = (int)min((uint32_t)a.Lout, a.N - (uint32_t)b * (uint32_t)a.Lout);
+      if (b < a.nBlocks && first >= 0 && xs.thr == 0) {
+        const uint32_t start = xs((uint32_t)first);
+        if ((uint64_t)start + (uint64_t)(hist + nOut) <= (uint64_t)a.N)
+          w = tma::make_window(reinterpret_cast<const float2 *>(x) + start, hist + nOut);
+      }
+    }
+    return w;
+  };
+  uint32_t phase = 0;
+  if constexpr (kStage) {
+    if (tid == 0) {
+      tma::mbar_init(mbar, 1);
+      tma::issue(stage_window(blockIdx.x), S, mbar);
+    }
+    __syncthreads();
+  }
+  for (int b = blockIdx.x; b < a.nBlocks; b += gridDim.x) {
+    const uint32_t i0 = (uint32_t)b * (uint32_t)a.Lout;
+    const int nOut = (int)min((uint32_t)a.Lout, a.N - i0);
+    const tma::Window w = stage_window(b);
+    double2 v[16];
+    if constexpr (kStage) {
+      tma::mbar_wait(mbar, phase);
+      phase ^= 1;
     }
 #pragma unroll
     for (int k = 0; k < 16; k++) {
       const int m = tid + NT * k;
       const int64_t i = (int64_t)i0 - hist + m;
       const bool ok = i >= 0 && i < (int64_t)a.N && m < hist + nOut;
-      v[k] = make_double2(ok ? (double)raw[k].x : 0.0, ok ? (double)raw[k].y : 0.0);
+      TIN e;
+      bool staged = false;
+      if constexpr (kStage) {
+        if (w.src) {
+          e = tma::read(w, S, min(m, hist + nOut - 1));
+          staged = true;
+        }
+      }
+      if (!staged) {  // branch-free: load from a clamped valid index, mask afterwards
+        const int64_t ic = i < 0 ? 0 : (i >= (int64_t)a.N ? (int64_t)a.N - 1 : i);
+        e = x[xs((uint32_t)ic)];
+      }
+      v[k] = make_double2(ok ? (double)e.x : 0.0, ok ? (double)e.y : 0.0);
     }
-  }
-  dit_transform<LOG2M, -1>(A, a.tw, tid, v);
-  double2 z[16];
+    dit_transform_ld<LOG2M, -1>(A, a.tw, tid, v, [&] {
+      if constexpr (kStage) {
+        if (tid == 0) tma::issue(stage_window(b + (int)gridDim.x), S, mbar);
+      }
+    });
+    double2 z[16];
 #pragma unroll
-  for (int q = 0; q < 16; q++) z[q] = cmul(v[brev<16>(q)], __ldg(a.what + q * NT + tid));
-  __syncthreads();
-  // the surveillance samples of the epilogue are requested before the inverse transform's shared-memory passes
-  // (float2 input only: sixteen double2 would not fit beside the transform's registers)
-  constexpr bool kPrefetchY = sizeof(TIN) == sizeof(float2);
-  TIN yy[16];
-  auto load_y = [&]() {
+    for (int q = 0; q < 16; q++) z[q] = cmul(v[brev<16>(q)], __ldg(a.what + q * NT + tid));
+    __syncthreads();
+    dit_transform_ld<LOG2M, +1>(A, a.tw, tid, z, [] {});
+    // epilogue: the surveillance samples are loaded here (prefetching them over the inverse transform costs 32
+    // registers the 128-register bound does not have: measured as spills; the other resident CTA hides the wait)
+    TIN yy[16];
 #pragma unroll
     for (int q = 0; q < 16; q++) {
       const int o = tid + NT * q - hist;
       const int oc = o < 0 ? 0 : (o >= nOut ? nOut - 1 : o);
       yy[q] = y[i0 + oc];  // unconditional, clamped: batched loads
     }
-  };
-  if constexpr (kPrefetchY) load_y();
-  dit_transform<LOG2M, +1>(A, a.tw, tid, z);
-  if constexpr (!kPrefetchY) load_y();
-  const double scale = 1.0 / (double)P::M;
-  // conv[m] valid for m >= hist; output i = i0 + m - hist
+    const double scale = 1.0 / (double)P::M;
+    // conv[m] valid for m >= hist; output i = i0 + m - hist
 #pragma unroll
-  for (int q = 0; q < 16; q++) {
-    const int o = tid + NT * q - hist;
-    if (o >= 0 && o < nOut) {
-      const double2 cv = z[brev<16>(q)];
-      st_iq<TIN>(yo, i0 + o, make_double2((double)yy[q].x - cv.x * scale, (double)yy[q].y - cv.y * scale));
+    for (int q = 0; q < 16; q++) {
+      const int o = tid + NT * q - hist;
+      if (o >= 0 && o < nOut) {
+        const double2 cv = z[brev<16>(q)];
+        st_iq<TIN>(yo, i0 + o, make_double2((double)yy[q].x - cv.x * scale, (double)yy[q].y - cv.y * scale));
+      }
     }
+    __syncthreads();  // the buffer is rewritten by the next block's first pass
   }
 }
 
@@ -772,8 +897,13 @@ struct b200dd_wh {
 
 namespace {
 
-template <int LOG2M> size_t corr_smem() { return (size_t)(dit::Plan3<LOG2M>::MP + 2 * dit::Plan3<LOG2M>::M) * sizeof(double2); }
+// FFT buffer + two accumulators + TMA staging (15 NT + 2 float2) + mbarrier
+template <int LOG2M> size_t corr_smem() {
+  return (size_t)(dit::Plan3<LOG2M>::MP + 2 * dit::Plan3<LOG2M>::M) * sizeof(double2) + (size_t)(CorrStage<LOG2M>::kElems + 2) * sizeof(float2) + 16;
+}
 template <int LOG2M> size_t fft_smem() { return (size_t)dit::Plan3<LOG2M>::MP * sizeof(double2); }
+// FFT buffer + TMA staging of one window (M + 2 float2) + mbarrier
+template <int LOG2M> size_t apply_smem() { return fft_smem<LOG2M>() + (size_t)(dit::Plan3<LOG2M>::M + 2) * sizeof(float2) + 16; }
 
 template <class TIN> constexpr bool is_f32() { return sizeof(TIN) == sizeof(float2); }
 
@@ -796,7 +926,7 @@ template <int LOG2M, class TIN> int wh_launch_apply(b200dd_wh *h, const void *x,
   using P = dit::Plan3<LOG2M>;
   bool &done = is_f32<TIN>() ? h->attr_apply_f32 : h->attr_apply_f64;
   if (!done) {
-    B2_CUDA(cudaFuncSetAttribute(wh_apply_kernel<LOG2M, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M>()));
+    B2_CUDA(cudaFuncSetAttribute(wh_apply_kernel<LOG2M, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem<LOG2M>()));
     B2_CUDA(cudaFuncSetAttribute(wh_wspec_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M>()));
     done = true;
   }
@@ -804,8 +934,14 @@ template <int LOG2M, class TIN> int wh_launch_apply(b200dd_wh *h, const void *x,
   B2_LAUNCH_CHECK();
   ApplyArgs aa;
   aa.x = x; aa.y = y; aa.y_out = y_out; aa.what = h->d_what; aa.tw = h->d_tw_a; aa.status = h->d_status;
-  aa.N = h->N; aa.xs = make_xs_map(h->N, h->delayMin); aa.nBins = h->nBins; aa.Lout = h->Lout;
-  wh_apply_kernel<LOG2M, TIN><<<h->gridApply, P::NT, fft_smem<LOG2M>(), st>>>(aa);
+  aa.N = h->N; aa.xs = make_xs_map(h->N, h->delayMin); aa.nBins = h->nBins; aa.Lout = h->Lout; aa.nBlocks = h->gridApply;
+  // persistent CTAs: as many as are resident at once (shared memory and the 128-register bound decide)
+  int per_sm = (int)((227 * 1024) / apply_smem<LOG2M>());
+  if (per_sm > wh_min_ctas<LOG2M>()) per_sm = wh_min_ctas<LOG2M>();
+  if (per_sm < 1) per_sm = 1;
+  int grid = h->num_sms * per_sm;
+  if (grid > h->gridApply) grid = h->gridApply;
+  wh_apply_kernel<LOG2M, TIN><<<grid, P::NT, apply_smem<LOG2M>(), st>>>(aa);
   B2_LAUNCH_CHECK();
   return B200DD_OK;
 }

@@ -437,6 +437,15 @@ B200DD_API int b200dd_comm_shift_right_async(b200dd_comm *c, const void *d_send,
 B200DD_API int b200dd_comm_join(b200dd_comm *c, void *stream);
 B200DD_API int b200dd_comm_sync(b200dd_comm *c);
 
+/* Measured FP64 FMA rate of the device (TFLOP/s, 2 flop per FMA): the roofline of the FP64 WienerHopf kernels,
+ * which MEASURED_PEAKS.json does not carry.  Takes a few milliseconds. */
+B200DD_API int b200dd_ubench_fp64_tflops(int32_t device, double *tflops);
+
+/* Pin the CALLING host thread to the CPUs local to the device's PCIe root (sysfs local_cpulist, intersected with
+ * the thread's current affinity mask); call it before allocating pinned staging buffers so that they land on the
+ * GPU's NUMA node.  cpulist_out (nullable, `cap` bytes) receives the kernel's list, e.g. "0-31,64-95". */
+B200DD_API int b200dd_bind_host_to_device(int32_t device, char *cpulist_out, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif
