@@ -7,11 +7,12 @@
 // on (profiles/r02_summary.md).
 //
 // Bulk copies need 16-byte aligned source, destination and size, but a float2 window starts on any 8-byte
-// boundary: the copy covers the 16-byte aligned INTERIOR [i0, i1) of the window and lands at S[i + par]
-// (par = 1 when the window starts on an odd float2, which keeps the destination aligned); the at most one element
-// on either side is read with an ordinary load by the thread that owns it.  No byte outside the caller's buffer
-// is touched.  Windows that are not one contiguous run (circular wrap of the Wiener-Hopf correlations, the
-// reference's index quirk for delayMin > 0) are not staged: `src` stays null and their elements are loaded directly.
+// boundary: the copy is widened to the enclosing 16-byte aligned range -- at most one float2 before and one after
+// the window, both INSIDE the caller's array [0, N) -- and lands at S[0]; window element m is then S[m + par]
+// (par = 1 when the window starts on an odd float2).  A window whose widening would leave the array (first /
+// last element of a misaligned array), or that is not one contiguous run (circular wrap of the Wiener-Hopf
+// correlations, the reference's index quirk for delayMin > 0), is not staged: `src` stays null and the caller
+// loads its elements directly.  No byte outside the caller's buffer is touched.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -43,37 +44,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   } while (!done);
 }
 
-// One staged window.  Element m (m < n) of the window is  S[m + par]  when i0 <= m < i1, else  src[m].
+// One staged window: element m (m < n) of the window is S[m + par].
 struct Window {
-  const float2 *src = nullptr;  // window element 0 in global memory; null: not staged
-  int par = 0, i0 = 0, i1 = 0;
-  __device__ __forceinline__ uint32_t bytes() const { return (uint32_t)(i1 - i0) * 8u; }
+  const float2 *src = nullptr;  // first element copied (16-byte aligned); null: not staged
+  int par = 0;
+  uint32_t bytes = 0;
 };
 
-// describe the window of n contiguous elements starting at p (n <= capacity of S minus 2)
-__device__ __forceinline__ Window make_window(const float2 *p, int n) {
+// window of n contiguous elements base[start .. start + n) of an array of N elements (n <= capacity of S minus 2)
+__device__ __forceinline__ Window make_window(const float2 *base, uint32_t N, uint32_t start, int n) {
   Window w;
-  w.src = p;
-  w.par = (int)((reinterpret_cast<uintptr_t>(p) >> 3) & 1);
-  w.i0 = w.par;
-  w.i1 = n - (int)((reinterpret_cast<uintptr_t>(p + n) >> 3) & 1);
-  if (w.i1 < w.i0) w.i1 = w.i0;
+  const float2 *p = base + start;
+  const int par = (int)((reinterpret_cast<uintptr_t>(p) >> 3) & 1);
+  const int tail = (int)((reinterpret_cast<uintptr_t>(p + n) >> 3) & 1);
+  if (n <= 0 || (par && start == 0) || (tail && (uint64_t)start + (uint64_t)n >= (uint64_t)N)) return w;
+  w.src = p - par;
+  w.par = par;
+  w.bytes = (uint32_t)(n + par + tail) * 8u;
   return w;
 }
 
-// one thread: start the copy of w's interior into S (16-byte aligned) and arm the barrier with its byte count
+// one thread: start the copy into S (16-byte aligned) and arm the barrier with its byte count (0: not staged)
 __device__ __forceinline__ void issue(const Window &w, float2 *S, uint64_t *bar) {
-  const uint32_t b = w.src ? w.bytes() : 0u;
-  mbar_expect_tx(bar, b);
-  if (b) bulk_g2s(S + w.i0 + w.par, w.src + w.i0, b, bar);
+  mbar_expect_tx(bar, w.bytes);
+  if (w.bytes) bulk_g2s(S, w.src, w.bytes, bar);
 }
 
-// element m of the window (the caller masks m >= n itself)
-__device__ __forceinline__ float2 read(const Window &w, const float2 *S, int m) {
-  float2 v = S[m + w.par];
-  if (m < w.i0 || m >= w.i1) v = w.src[m];
-  return v;
-}
+__device__ __forceinline__ float2 read(const Window &w, const float2 *S, int m) { return S[m + w.par]; }
 
 }  // namespace tma
 }  // namespace b2

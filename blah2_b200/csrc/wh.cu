@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_corr_kernel(CorrA
   };
   auto stage_window = [&](const WinDesc<TIN> &d) {
     tma::Window w;
-    if (kStage && d.contiguous) w = tma::make_window(reinterpret_cast<const float2 *>(d.p) + d.start, min(d.lim, CAP));
+    if (kStage && d.contiguous) w = tma::make_window(reinterpret_cast<const float2 *>(d.p), N, d.start, min(d.lim, CAP));
     return w;
   };
   uint32_t phase = 0;
@@ -237,21 +237,23 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_corr_kernel(CorrA
         tma::mbar_wait(mbar, phase);
         phase ^= 1;
       }
-#pragma unroll
-      for (int k = 0; k < 16; k++) {
-        const int m = tid + NT * k;
-        TIN e;
-        if (k == 15) {
-          e = r15;
-        } else {
-          e = direct(d, t, n0, m);
-          if constexpr (kStage) {
-            if (w.src) e = tma::read(w, S, min(m, d.lim - 1));
-          }
-        }
-        const bool ok = m < d.lim;
+      auto put = [&](int k, TIN e) {
+        const bool ok = tid + NT * k < d.lim;
         v[k] = make_double2(ok ? (double)e.x : 0.0, ok ? (double)e.y : 0.0);
+      };
+      bool staged = false;
+      if constexpr (kStage) {
+        if (w.src) {  // CTA-uniform branch: the staged path must not drag the direct loads along
+          staged = true;
+#pragma unroll
+          for (int k = 0; k < 15; k++) put(k, tma::read(w, S, min(tid + NT * k, d.lim - 1)));
+        }
       }
+      if (!staged) {
+#pragma unroll
+        for (int k = 0; k < 15; k++) put(k, direct(d, t, n0, tid + NT * k));
+      }
+      put(15, r15);
       // next window (of this or the next segment): staged while this one is transformed
       const bool more = t < 2 || s + 1 < s1;
       const int ns = t < 2 ? s : s + 1, nt = t < 2 ? t + 1 : 0;
@@ -792,7 +794,7 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, wh_min_ctas<LOG2M>()) w
       if (b < a.nBlocks && first >= 0 && xs.thr == 0) {
         const uint32_t start = xs((uint32_t)first);
         if ((uint64_t)start + (uint64_t)(hist + nOut) <= (uint64_t)a.N)
-          w = tma::make_window(reinterpret_cast<const float2 *>(x) + start, hist + nOut);
+          w = tma::make_window(reinterpret_cast<const float2 *>(x), a.N, start, hist + nOut);
       }
     }
     return w;
