@@ -13,14 +13,18 @@ Contract (one JSON line on rank 0):
   e2e     same metric through the public host API (Pipeline.submit_host / fetch = C ABI
           b200dd_pipeline_submit_host / _fetch, PINNED complex128 host buffers): H2D of x and y and D2H of
           the map + detections inside the timed region, every step.
-  roofline  the CAF range-correlation kernel (the kernel BASELINE.json's metric names), timed live
-          with CUDA events around that kernel (b200dd_caf_profile_device), algorithmic bytes per
-          launch = 16 N_used + 8 nDop nDel, against MEASURED_PEAKS.json hbm_gbs.
+  roofline  the kernel with the largest SM-time share of the step (CUDA events around every stage, live:
+          b200dd_wh_profile_device / b200dd_caf_profile_device; the single-CTA solve is a latency chain on one SM and
+          is not a candidate): its ALGORITHMIC bytes per launch / its time against MEASURED_PEAKS.json hbm_gbs, plus --
+          for the FP64 FFT kernels -- nominal FFT flops against the FP64 FMA rate measured in this run
+          (b200dd_ubench_fp64_tflops: builder-measured).  `step` uses SURVEY.md s8(d)'s fused-chain bytes
+          2 (16 N) + 8 nDop nDel = 64 616 800; `cfg3` times BASELINE configs[2] (CAF, 2e7 samples, 512 x 1025).
   cpu_baseline  the reference's own src/process code (oracle/_ref, unmodified sources + our FFT /
           Armadillo shims) on ONE host thread for ONE CPI of the same workload.
   --impl reference: the same reference code, one host process per concurrent CPI (time-bounded).
 Multi-GPU: independent CPIs sharded over ranks ("weak" scaling, no data-path collective); the only
-collective is the final NCCL gather of every rank's last map to rank 0 (inside the timed region).
+communication is the gather of EVERY finished map to rank 0 (C ABI b200dd_comm_gather_async: NCCL send/recv on a
+dedicated stream, overlapped with the next CPI's kernels, inside the timed region).
 """
 from __future__ import annotations
 
@@ -48,17 +52,16 @@ KERNELS_PER_STEP = 4 + 2 + 2 + 3 + 1  # wh(corr,solve,wspec,apply) caf(range,dop
 
 
 def ncu_traffic(kernel="caf_range_", capture="cfg2"):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the range kernel (caf_range_kernel or
-    caf_range_grouped_kernel, whichever the plan uses) in the config-2 capture of the committed ncu --set full
-    extract (profiles/r01z_kernels.json), or None."""
-    p = os.path.join(ROOT, "profiles", "r01z_kernels.json")
-    try:
-        ks = json.load(open(p))["kernels"]
-        for k in ks:
-            if kernel in k["name"] and capture in str(k.get("capture", capture)):
-                return int(k["dram_bytes_read"] + k["dram_bytes_write"])
-    except Exception:
-        pass
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` in the `capture` section of the committed
+    ncu --set full extract (profiles/r02_kernels.json, else round 1's), or None."""
+    for name in ("r02_kernels.json", "r01z_kernels.json"):
+        try:
+            ks = json.load(open(os.path.join(ROOT, "profiles", name)))["kernels"]
+            for k in ks:
+                if kernel in k["name"] and capture in str(k.get("capture", capture)):
+                    return int(k["dram_bytes_read"] + k["dram_bytes_write"])
+        except Exception:
+            pass
     return None
 
 
@@ -172,7 +175,7 @@ def run_reference(args, rank, world):
     workers = []
     for i in range(procs_n):
         a, b = ctx.Pipe()
-        p = ctx.Process(target=_ref_worker, args=(b, 20260923), daemon=True)
+        p = ctx.Process(target=_ref_worker, args=(b, 20260923))
         p.start()
         workers.append((p, a))
     kind = "reference"
@@ -201,6 +204,10 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     for p, c in workers:
         c.send("stop")
+    for p, c in workers:  # let them run their exit handlers (the driver records the libraries they loaded)
+        p.join(timeout=30)
+        if p.is_alive():
+            p.terminate()
     requested = args.steps
     args.steps = done
     cpis = procs_n * args.steps
@@ -233,7 +240,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="replay the device chain as CUDA graphs (prepare_device)")
+    ap.add_argument("--eager", action="store_true", help="launch every kernel of every CPI instead of replaying the chain as a CUDA graph")
     ap.add_argument("--streams", type=int, default=6, help="CPIs in flight per GPU (independent pipelines on their own streams)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -241,6 +248,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    args.graph = not args.eager
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -249,22 +257,31 @@ def main():
     import torch
     import torch.distributed as dist
 
+    import ctypes
+
+    from blah2_b200 import capi
     from blah2_b200.process import Ambiguity, Pipeline, WienerHopf
     from blah2_b200.scene import make_scene
-    from blah2_b200.shard import gather_maps
+    from blah2_b200.shard import Comm
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # the submitting thread and its pinned staging buffers on the GPU's NUMA node (the end-to-end path is PCIe-bound)
+    cpulist = ctypes.create_string_buffer(256)
+    numa_rc = capi.load().b200dd_bind_host_to_device(local_rank, cpulist, 256)
+    host_cpus = cpulist.value.decode() if numa_rc == 0 else None
     # stdout carries exactly ONE line, the JSON: keep the real stdout aside and point file descriptor 1 at stderr, so
     # that anything a library prints there (NCCL's "NCCL version ..." banner, which it writes at WARN level too)
     # lands on stderr instead
     sys.stdout.flush()
     json_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
+    comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = Comm(rank, world, local_rank)
 
     NPIPE = max(1, args.streams)
     pipes = [Pipeline(**GEOM, clutter=CLUTTER, detection=DET, device=local_rank) for _ in range(NPIPE)]
@@ -284,7 +301,6 @@ def main():
     hmap = torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex128).pin_memory()
     dmaps = [torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda") for _ in range(NPIPE)]
     dmap = dmaps[0]
-    gathered = None
     streams = [torch.cuda.Stream() for _ in range(NPIPE)]
     stream = streams[0]
     st = stream.cuda_stream
@@ -295,32 +311,48 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def submit(i):
+    # rank 0 receives every rank's finished maps: [NPIPE ring slots][world] maps, allocated once
+    map_bytes = cells * 8
+    recv_ring = None
+    if comm is not None and rank == 0:
+        recv_ring = torch.empty((NPIPE, world, g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda")
+
+    def submit(i, gather=True):
         p = i % NPIPE
         with torch.cuda.stream(streams[p]):
+            if comm is not None and gather:
+                comm.join(streams[p])  # the gather of this pipeline's previous map has read dmaps[p]
             pipes[p].submit_device(xs[i % NB], ys[i % NB], dmaps[p], streams[p].cuda_stream)
+            if comm is not None and gather:  # NCCL send/recv on the communicator's stream, behind this CPI's kernels only
+                comm.gather_async(dmaps[p], recv_ring[p] if rank == 0 else None, 0, after=streams[p])
 
     # ---- device-resident throughput: a stream of independent CPIs, NPIPE in flight ----
-    # --graph: plan creation (untimed, before the warm-up steps) = the CUDA graph of the chain for every (input set,
-    # pipeline) pair the loop below submits.  Off by default: with 50 CPIs enqueued ahead eager launches measured 3 %
-    # faster than graph replay (profiles/r01_summary.md s6)
+    # Plan creation (untimed, before the warm-up steps): the CUDA graph of the chain for every (input set, pipeline)
+    # pair the loop below submits -- one launch per CPI instead of 13.  (Round 1 measured replay 3 % slower than eager
+    # launches at 111 us per CPI; at this round's ~60 us per CPI the 13 launches of a CPI are what the submitting
+    # thread cannot keep up with.)  --eager turns it off.
     if args.graph:
         for i in range(NB * NPIPE):   # submit(i) uses (i % NB, i % NPIPE): the pattern repeats after lcm(NB, NPIPE) steps
             p = i % NPIPE
             pipes[p].prepare_device(xs[i % NB], ys[i % NB], dmaps[p], streams[p].cuda_stream)
     for i in range(args.warmup):
-        submit(i)
+        submit(i)   # (also warms the communicator and the gather path)
     for p in range(NPIPE):
         last = pipes[p].fetch(streams[p].cuda_stream)
-    if world > 1:  # warm the NCCL communicator and the gather path outside the timed region
-        with torch.cuda.stream(stream):
-            for _ in range(2):
-                gather_maps(dmap.unsqueeze(0), world, rank, world)
+    if comm is not None:
+        comm.sync()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if comm is not None:
+        # start line on the DEVICE timelines: every rank's streams wait for one tiny all-reduce, which completes on all
+        # ranks within microseconds of each other (host-side barrier skew would otherwise be charged to the region)
+        tick = torch.zeros(2, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        comm.allreduce_f64_async(tick, after=None)
+        comm.join(stream)
     e0.record(stream)
     for s_ in streams[1:]:
         s_.wait_event(e0)
@@ -329,14 +361,18 @@ def main():
     for p in reversed(range(NPIPE)):  # synchronises each stream; detections + metrics of the final CPIs on the host
         last = pipes[p].fetch(streams[p].cuda_stream)
     with torch.cuda.stream(stream):
-        if world > 1:  # the final map gather (NCCL over NVLink), ordered after the kernels on `stream`
-            gathered = gather_maps(dmap.unsqueeze(0), world, rank, world)
+        if comm is not None:  # the last gathers (rank 0: every rank's maps have arrived) end the region
+            comm.join(stream)
         e1.record(stream)
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
+    gather_check = None
+    if comm is not None and rank == 0:   # rank 0's own slot of the ring equals its device map: the gather really ran
+        pl = (args.steps - 1) % NPIPE
+        gather_check = bool(torch.equal(recv_ring[pl, 0], dmaps[pl])) and bool(torch.isfinite(torch.view_as_real(recv_ring)).all())
 
     # ---- end to end through the host API (pinned complex128 in, complex128 map out) ----
     # Two pipelines alternate: submit_host(i) enqueues H2D + kernels + D2H, fetch(i-1) collects the
@@ -423,7 +459,32 @@ def main():
             spectrum[label] = {"n_spectrum": sa.nSpectrum, "decimation": sa.decimation, "fold_ms": round(fm, 5),
                                "reduce_dft_ms": round(rm, 5), "achieved_gbs": round(8 * sa.nfft / (fm * 1e-3) / 1e9, 1)}
             sa.close()
-        del big
+
+    # ---- BASELINE configs[2] (the configuration designated for the HBM capture): CAF alone, 2 s CPI @ 10 MS/s,
+    # 512 delay x 1025 Doppler, device-resident float2 IQ (2 x 160 MB per map > L2), CUDA events around each kernel ----
+    cfg3 = None
+    fp64_peak = None
+    if rank == 0:
+        tf = ctypes.c_double()
+        capi.check(capi.load().b200dd_ubench_fp64_tflops(local_rank, ctypes.byref(tf)))
+        fp64_peak = float(tf.value)
+        amb3 = Ambiguity(0, 511, -256, 256, 10_000_000, 20_000_000, True, device=local_rank)
+        g3 = amb3.geometry
+        bigy = [torch.randn(20_000_000, dtype=torch.complex64, device="cuda") for _ in range(2)]
+        out3 = torch.empty((g3.n_doppler_bins, g3.n_delay_bins), dtype=torch.complex64, device="cuda")
+        r3, d3 = [], []
+        with torch.cuda.stream(stream):
+            for i in range(3 + 10):
+                a_, b_ = amb3.profile_device(big[i % 2], bigy[i % 2], out3, st)
+                if i >= 3:
+                    r3.append(a_); d3.append(b_)
+        torch.cuda.synchronize()
+        cfg3 = {"workload": "cfg3: Ambiguity 512 delay x 1025 Doppler, 2 s CPI @ 10 MS/s, N=2e7 per channel",
+                "range_ms": round(float(np.mean(r3)), 5), "doppler_ms": round(float(np.mean(d3)), 5),
+                "algorithmic_bytes": 16 * g3.n_used + 8 * g3.n_doppler_bins * g3.n_delay_bins,
+                "range_fft": f"M={g3.range_fft_len} x{g3.range_segments} segments, hop {g3.range_hop}"}
+        amb3.close()
+        del big, bigy, out3
 
     if rank != 0:
         if world > 1:
@@ -433,10 +494,46 @@ def main():
     peak, peak_src = measured_peaks()
     for label in ("n2e6", "n2e7"):
         spectrum[label]["frac"] = round(spectrum[label]["achieved_gbs"] / peak, 4)
-    bytes_range = 16 * g.n_used + 8 * cells                 # x, y read once; range matrix written once
+    # ---- roofline: the kernel that owns the SMs (largest CUDA-event time among the full-grid kernels) ----
+    plan = wh.plan
+    fft_flop = lambda m: 5.0 * m * np.log2(m)   # nominal flops of one m-point complex transform
+    cand = {
+        "wh_corr": dict(kernel="wh_corr_kernel", ms=kms["wh_corr"], bytes=16 * N,
+                        flop=(3 * plan.corr_segments + 2 * plan.corr_ctas) * fft_flop(plan.corr_fft_len), dtype="f64"),
+        "wh_apply": dict(kernel="wh_apply_kernel", ms=kms["wh_apply"], bytes=16 * N + 8 * N,
+                         flop=(2 * plan.filter_blocks + 1) * fft_flop(plan.filter_fft_len), dtype="f64"),
+        "range": dict(kernel="caf_range_grouped_kernel" if g.range_groups > 1 else "caf_range_kernel", ms=kms["range"],
+                      bytes=16 * g.n_used + 8 * g.range_parts * cells, flop=None, dtype="f32"),
+        "doppler": dict(kernel="caf_doppler_kernel", ms=kms["doppler"], bytes=8 * cells, flop=None, dtype="f32"),
+    }
+    dom_key = max(cand, key=lambda k: cand[k]["ms"])
+    dom = cand[dom_key]
+    ach = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
     bytes_caf = 16 * g.n_used + 8 * cells                   # SURVEY s8(d) B_caf (map written; R stays in L2)
-    bytes_step = 2 * 16 * N + 8 * N + 8 * cells             # two compulsory passes over x,y + y' + map
-    ach_range = bytes_range / (kms["range"] * 1e-3) / 1e9
+    bytes_step = 2 * 16 * N + 8 * cells                     # SURVEY s8(d) B_wh+caf: two compulsory passes over x, y + the map
+    roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "traffic": ncu_traffic(dom["kernel"].replace("_grouped_kernel", "_").replace("_kernel", "")),
+                "peak_source": peak_src, "algorithmic_bytes": dom["bytes"], "kernel_ms": round(dom["ms"], 5),
+                "chosen_by": "largest CUDA-event time among the full-grid kernels of the step (wh_solve is one CTA on one SM: "
+                             "a latency chain that overlaps the other CPIs' kernels, no roofline applies)",
+                "share_of_kernel_time": round(dom["ms"] / sum(c["ms"] for c in cand.values()), 3)}
+    if dom["flop"]:
+        tfl = dom["flop"] / (dom["ms"] * 1e-3) / 1e12
+        roofline["fp64"] = {"achieved_tflops": round(tfl, 2), "peak_tflops": round(fp64_peak, 2), "frac": round(tfl / fp64_peak, 4),
+                            "flops": "5 M log2 M per transform (nominal), transforms per launch from b200dd_wh_get_plan",
+                            "peak_source": "b200dd_ubench_fp64_tflops in this run (builder-measured DFMA rate)"}
+    roofline["per_kernel"] = {k: {"ms": round(c["ms"], 5), "hbm_frac": round(c["bytes"] / (c["ms"] * 1e-3) / 1e9 / peak, 4),
+                                  **({"fp64_frac": round(c["flop"] / (c["ms"] * 1e-3) / 1e12 / fp64_peak, 4)} if c["flop"] else {})}
+                              for k, c in cand.items()}
+    roofline["caf_total"] = {"ms": round(kms["range"] + kms["doppler"], 5),
+                             "frac": round(bytes_caf / ((kms["range"] + kms["doppler"]) * 1e-3) / 1e9 / peak, 4)}
+    roofline["step"] = {"algorithmic_bytes": bytes_step, "frac": round(bytes_step / (ms_total / args.steps * 1e-3) / 1e9 / peak, 4)}
+    cfg3["ms"] = round(cfg3["range_ms"] + cfg3["doppler_ms"], 5)
+    cfg3["achieved_gbs"] = round(cfg3["algorithmic_bytes"] / (cfg3["ms"] * 1e-3) / 1e9, 1)
+    cfg3["frac"] = round(cfg3["achieved_gbs"] / peak, 4)
+    cfg3["range_kernel_frac"] = round(cfg3["algorithmic_bytes"] / (cfg3["range_ms"] * 1e-3) / 1e9 / peak, 4)
+    cfg3["traffic"] = ncu_traffic("caf_range_", "cfg3")
+    cfg3["msamples_per_s"] = round(20_000_000 / (cfg3["ms"] * 1e-3) / 1e6, 1)
     value = world * args.steps * N / (ms_total * 1e-3) / 1e6
     e2e_value = world * e2e_steps * N / e2e_s / 1e6
     line = {
@@ -446,7 +543,8 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (CAF) / f64 (WienerHopf, detection)",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "cpis_per_step_per_gpu": 1, "parallelism": f"independent CPIs x{world}",
-                   "l2": f"{NB} distinct CPI input sets rotated ({NB * 32} MB > L2)", "cpis_in_flight": NPIPE, "submission": "cuda graph replay" if args.graph else "eager launches",
+                   "l2": f"{NB} distinct CPI input sets rotated ({NB * 32} MB > L2)", "cpis_in_flight": NPIPE, "submission": "cuda graph replay (b200dd_pipeline_prepare_device)" if args.graph else "eager launches",
+                   "host_cpus": host_cpus, "map_gather": (f"every finished map to rank 0 by b200dd_comm_gather_async (NCCL send/recv on a dedicated stream), check {gather_check}" if world > 1 else "none (1 GPU)"),
                    "range_fft": f"M={g.range_fft_len} x{g.range_segments} segments, hop {g.range_hop}, "
                                 f"{g.range_groups} warp group(s) x {g.range_parts} part(s) per batch",
                    "doppler_fft": f"Bluestein M2={g.doppler_fft_len}"},
@@ -461,13 +559,8 @@ def main():
                              "n_detections": int(r_i16["detections"].get_nDetections())},
         "gpu_launches": KERNELS_PER_STEP * args.steps,
         "clocks": clocks,
-        "roofline": {"kernel": "caf_range_grouped_kernel" if g.range_groups > 1 else "caf_range_kernel", "bound": "hbm", "achieved": round(ach_range, 1), "peak": peak,
-                     "unit": "GB/s", "frac": round(ach_range / peak, 4), "traffic": ncu_traffic(), "peak_source": peak_src,
-                     "algorithmic_bytes": bytes_range, "kernel_ms": round(kms["range"], 5),
-                     "caf_total": {"ms": round(kms["range"] + kms["doppler"], 5),
-                                   "frac": round(bytes_caf / ((kms["range"] + kms["doppler"]) * 1e-3) / 1e9 / peak, 4)},
-                     "step": {"algorithmic_bytes": bytes_step,
-                              "frac": round(bytes_step / (ms_total / args.steps * 1e-3) / 1e9 / peak, 4)}},
+        "roofline": roofline,
+        "cfg3": cfg3,
         "kernel_ms": {k: round(v, 5) for k, v in kms.items()},
         "spectrum": spectrum,
         "result": {"n_detections": int(last["detections"].get_nDetections()), "noisePower": round(last["noisePower"], 4),

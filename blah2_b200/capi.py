@@ -62,6 +62,12 @@ class SpectrumGeometry(C.Structure):
                 ("n_frequency", C.c_uint32), ("fold_chunks", C.c_uint32), ("fold_rows_per_chunk", C.c_uint32)]
 
 
+class WhPlan(C.Structure):
+    _fields_ = [("corr_fft_len", C.c_uint32), ("corr_hop", C.c_uint32), ("corr_segments", C.c_uint32),
+                ("corr_ctas", C.c_uint32), ("filter_fft_len", C.c_uint32), ("filter_hop", C.c_uint32),
+                ("filter_blocks", C.c_uint32)]
+
+
 class CpiResult(C.Structure):
     _fields_ = [("filter_status", C.c_int32), ("n_detections", C.c_uint32), ("noise_power", C.c_double),
                 ("max_power", C.c_double)]
@@ -99,6 +105,7 @@ SIGNATURES = [
                                            C.POINTER(C.c_float)]),
     ("b200dd_wh_debug_weights", C.c_int, [_VP, _VP, _VP, _VP]),
     ("b200dd_wh_n_bins", C.c_uint32, [_VP]),
+    ("b200dd_wh_get_plan", C.c_int, [_VP, C.POINTER(WhPlan)]),
     ("b200dd_wh_stream", _VP, [_VP]),
     ("b200dd_det_create", C.c_int, [C.POINTER(DetParams), C.c_uint32, C.c_uint32, C.POINTER(_VP)]),
     ("b200dd_det_destroy", None, [_VP]),

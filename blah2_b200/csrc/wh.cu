@@ -228,7 +228,9 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_corr_kernel(CorrA
   double2 vxp[16];
   for (int s = s0; s < s1; s++) {
     const uint32_t n0 = (uint32_t)s * (uint32_t)a.L;
-#pragma unroll
+    // NOT unrolled: three (five with the inverses) copies of the transform overflow the instruction cache
+    // (11 % of the stall samples were no_instruction, profiles/r02_summary.md)
+#pragma unroll 1
     for (int t = 0; t < 3; t++) {
       const WinDesc<TIN> d = describe(s, t);
       const tma::Window w = stage_window(d);
@@ -284,24 +286,22 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_corr_kernel(CorrA
   const double scale = 1.0 / (double)P::M;
   double2 *pa = a.partial + (size_t)blockIdx.x * 2 * a.nBins;
   double2 *pb = pa + a.nBins;
-  double2 z[16];
+  // IFFT gives ra[k] = sum xs[n+k] conj(xs[n]);  a[k] = conj(ra[k])  (WienerHopf.cpp:82-84); b[k] = rb[k]
+#pragma unroll 1
+  for (int c = 0; c < 2; c++) {
+    const double2 *Z = c == 0 ? Za : Zb;
+    double2 *out = c == 0 ? pa : pb;
+    const double sgn = c == 0 ? -scale : scale;
+    double2 z[16];
 #pragma unroll
-  for (int q = 0; q < 16; q++) z[q] = Za[q * NT + tid];
-  // IFFT gives ra[k] = sum xs[n+k] conj(xs[n]);  a[k] = conj(ra[k])  (WienerHopf.cpp:82-84)
-  dit_transform<LOG2M, +1>(A, tw, tid, z);
+    for (int q = 0; q < 16; q++) z[q] = Z[q * NT + tid];
+    dit_transform<LOG2M, +1>(A, tw, tid, z);
 #pragma unroll
-  for (int q = 0; q < 16; q++) {
-    const int m = tid + NT * q;
-    if (m < a.nBins) pa[m] = make_double2(z[brev<16>(q)].x * scale, -z[brev<16>(q)].y * scale);
-  }
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 16; q++) z[q] = Zb[q * NT + tid];
-  dit_transform<LOG2M, +1>(A, tw, tid, z);
-#pragma unroll
-  for (int q = 0; q < 16; q++) {
-    const int m = tid + NT * q;
-    if (m < a.nBins) pb[m] = make_double2(z[brev<16>(q)].x * scale, z[brev<16>(q)].y * scale);
+    for (int q = 0; q < 16; q++) {
+      const int m = tid + NT * q;
+      if (m < a.nBins) out[m] = make_double2(z[brev<16>(q)].x * scale, z[brev<16>(q)].y * sgn);
+    }
+    __syncthreads();
   }
 }
 
@@ -754,6 +754,24 @@ template <> __device__ __forceinline__ void st_iq<float2>(float2 *p, uint32_t i,
 }
 template <> __device__ __forceinline__ void st_iq<double2>(double2 *p, uint32_t i, double2 v) { p[i] = v; }
 
+// The weight spectrum is re-read by every block a CTA processes: keep it in L1 (evict_last) and keep the streamed
+// surveillance samples out of it (no_allocate).
+__device__ __forceinline__ double2 ld_keep(const double2 *p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ld_stream(const float2 *p) {
+  float2 v;
+  asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ld_stream(const double2 *p) {
+  double2 v;
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
 // K5.  Overlap-save: block b produces the Lout outputs [b Lout, (b+1) Lout) from the window of
 // M = Lout + nBins - 1 shifted-reference samples that ends at the block's last output -- forward transform, multiply
 // by the weight spectrum, inverse transform, y' = y - conv / M.  PERSISTENT CTAs (two per SM at M = 4096) walk the
@@ -812,6 +830,9 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, wh_min_ctas<LOG2M>()) w
     const int nOut = (int)min((uint32_t)a.Lout, a.N - i0);
     const tma::Window w = stage_window(b);
     double2 v[16];
+    // the block's surveillance samples are needed two transforms from now: ask L2 for them (one line per thread)
+    for (uint32_t e = (uint32_t)tid * (128 / sizeof(TIN)); e < (uint32_t)nOut; e += (uint32_t)NT * (128 / sizeof(TIN)))
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(y + i0 + e));
     if constexpr (kStage) {
       tma::mbar_wait(mbar, phase);
       phase ^= 1;
@@ -842,7 +863,7 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, wh_min_ctas<LOG2M>()) w
     });
     double2 z[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) z[q] = cmul(v[brev<16>(q)], __ldg(a.what + q * NT + tid));
+    for (int q = 0; q < 16; q++) z[q] = cmul(v[brev<16>(q)], ld_keep(a.what + q * NT + tid));
     __syncthreads();
     dit_transform_ld<LOG2M, +1>(A, a.tw, tid, z, [] {});
     // epilogue: the surveillance samples are loaded here (prefetching them over the inverse transform costs 32
@@ -852,7 +873,7 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, wh_min_ctas<LOG2M>()) w
     for (int q = 0; q < 16; q++) {
       const int o = tid + NT * q - hist;
       const int oc = o < 0 ? 0 : (o >= nOut ? nOut - 1 : o);
-      yy[q] = y[i0 + oc];  // unconditional, clamped: batched loads
+      yy[q] = ld_stream(y + i0 + oc);  // unconditional, clamped: batched loads
     }
     const double scale = 1.0 / (double)P::M;
     // conv[m] valid for m >= hist; output i = i0 + m - hist
@@ -1192,6 +1213,18 @@ int b200dd_wh_debug_weights(b200dd_wh *h, double *w, double *a, double *b) {
 }
 
 uint32_t b200dd_wh_n_bins(const b200dd_wh *h) { return h ? (uint32_t)h->nBins : 0; }
+
+int b200dd_wh_get_plan(const b200dd_wh *h, b200dd_wh_plan *out) {
+  if (!h || !out) return arg_fail("b200dd_wh_get_plan: null argument");
+  out->corr_fft_len = 1u << h->log2m_c;
+  out->corr_hop = (uint32_t)h->L;
+  out->corr_segments = (uint32_t)h->nSeg;
+  out->corr_ctas = (uint32_t)h->gridCorr;
+  out->filter_fft_len = 1u << h->log2m_a;
+  out->filter_hop = (uint32_t)h->Lout;
+  out->filter_blocks = (uint32_t)h->gridApply;
+  return B200DD_OK;
+}
 void *b200dd_wh_stream(b200dd_wh *h) { return h ? (void *)h->stream : nullptr; }
 
 }  // extern "C"

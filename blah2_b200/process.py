@@ -167,6 +167,8 @@ class WienerHopf:
         self._lib, self._h = lib, h
         self.nSamples = int(nSamples)
         self.nBins = int(lib.b200dd_wh_n_bins(h))
+        self.plan = capi.WhPlan()
+        capi.check(lib.b200dd_wh_get_plan(h, C.byref(self.plan)))
 
     def process(self, x, y):
         """Host path.  Returns (ok, y_filtered): ok False <=> the reference returns false

@@ -6,8 +6,90 @@ the finished maps to rank 0 (NCCL over NVLink on GPUs, gloo in the CPU tests).  
 """
 from __future__ import annotations
 
+import ctypes as C
+
+import numpy as np
 import torch
 import torch.distributed as dist
+
+
+class Comm:
+    """The C-ABI communicator (include/b200dd.h b200dd_comm_*: NCCL issued from C on its own stream).
+
+    One per process / GPU.  The 128-byte NCCL id is created on rank 0 and handed to the other ranks through
+    torch.distributed's default process group (any backend) -- plumbing; the data path below never touches torch.
+    """
+
+    def __init__(self, rank: int, world: int, device: int):
+        from . import capi
+        self._capi = capi
+        self._lib = capi.load()
+        ident = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            capi.check(self._lib.b200dd_comm_get_unique_id(capi.ptr(ident)))
+        if world > 1:
+            t = torch.from_numpy(ident)
+            if dist.get_backend() == "nccl":
+                t = t.cuda(device)
+            dist.broadcast(t, src=0)
+            ident = t.cpu().numpy().copy()
+        h = C.c_void_p()
+        capi.check(self._lib.b200dd_comm_create(int(rank), int(world), capi.ptr(ident), int(device), C.byref(h)))
+        self._h, self.rank, self.world = h, rank, world
+
+    @staticmethod
+    def _sp(stream):
+        if stream is None:
+            return None
+        return C.c_void_p(stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream))
+
+    def gather_async(self, send: torch.Tensor, recv, dst: int = 0, after=None):
+        """Every rank's `send` (same byte size) lands on rank dst at recv[r]; returns at once."""
+        nbytes = send.numel() * send.element_size()
+        self._capi.check(self._lib.b200dd_comm_gather_async(self._h, self._capi.ptr(send),
+                                                            self._capi.ptr(recv) if recv is not None else None,
+                                                            nbytes, int(dst), self._sp(after)))
+
+    def gatherv_async(self, send: torch.Tensor, recv, sizes, offsets, dst: int = 0, after=None):
+        nbytes = send.numel() * send.element_size()
+        sz = (C.c_size_t * self.world)(*[int(v) for v in sizes])
+        of = (C.c_size_t * self.world)(*[int(v) for v in offsets])
+        self._capi.check(self._lib.b200dd_comm_gatherv_async(self._h, self._capi.ptr(send), nbytes,
+                                                             self._capi.ptr(recv) if recv is not None else None,
+                                                             sz, of, int(dst), self._sp(after)))
+
+    def allgatherv_async(self, send: torch.Tensor, recv: torch.Tensor, sizes, offsets, after=None):
+        sz = (C.c_size_t * self.world)(*[int(v) for v in sizes])
+        of = (C.c_size_t * self.world)(*[int(v) for v in offsets])
+        self._capi.check(self._lib.b200dd_comm_allgatherv_async(self._h, self._capi.ptr(send), self._capi.ptr(recv), sz, of,
+                                                                self._sp(after)))
+
+    def allreduce_f64_async(self, buf: torch.Tensor, after=None):
+        count = buf.numel() * (2 if buf.is_complex() else 1)
+        self._capi.check(self._lib.b200dd_comm_allreduce_f64_async(self._h, self._capi.ptr(buf), count, self._sp(after)))
+
+    def shift_right_async(self, send, recv, nbytes: int, after=None):
+        self._capi.check(self._lib.b200dd_comm_shift_right_async(self._h, self._capi.ptr(send) if send is not None else None,
+                                                                 self._capi.ptr(recv) if recv is not None else None,
+                                                                 int(nbytes), self._sp(after)))
+
+    def join(self, stream):
+        """`stream` waits for everything enqueued on the communicator so far."""
+        self._capi.check(self._lib.b200dd_comm_join(self._h, self._sp(stream)))
+
+    def sync(self):
+        self._capi.check(self._lib.b200dd_comm_sync(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200dd_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def cpi_indices(n_cpis: int, rank: int, world: int) -> list[int]:

@@ -201,6 +201,14 @@ B200DD_API const int *b200dd_wh_device_status(b200dd_wh *h);
 /* Filter weights w[nBins] / correlations a, b of the last call as complex128 -- parity tests. */
 B200DD_API int b200dd_wh_debug_weights(b200dd_wh *h, double *w, double *a, double *b);
 B200DD_API uint32_t b200dd_wh_n_bins(const b200dd_wh *h);
+
+/* The FFT plan of the two FFT stages (for measurement: transforms per CPI = 3 corr_segments + 2 corr_ctas in the
+ * correlation kernel, 2 filter_blocks + 1 in the filter stage). */
+typedef struct {
+  uint32_t corr_fft_len, corr_hop, corr_segments, corr_ctas;
+  uint32_t filter_fft_len, filter_hop, filter_blocks;
+} b200dd_wh_plan;
+B200DD_API int b200dd_wh_get_plan(const b200dd_wh *h, b200dd_wh_plan *out);
 B200DD_API void *b200dd_wh_stream(b200dd_wh *h);
 
 /* ------------------------------------------------------------------ detection tail */
