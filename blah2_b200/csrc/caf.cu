@@ -28,6 +28,8 @@
 // roundHamming (only Ambiguity::get_nfft() exposes those).
 #include "common.cuh"
 #include "fft_core.cuh"
+#include "fft_dit.cuh"
+#include "tma_stage.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -109,6 +111,7 @@ struct RangeArgs {
   int nCorr, nDel, lagMin, nSeg, L;
   int segPerPart, nDop;
   int batch0;  // first batch of this launch (sharded single-CPI mode); x, y point at batch 0 of the CPI
+  long long validLo, validHi;  // elements [validLo, validHi) of x / y (relative to the pointers above) may be read
 };
 
 // ---- TMA (bulk async copy) staging of the IQ segments ---------------------------------------------
@@ -304,6 +307,155 @@ __global__ void __launch_bounds__(Plan<LOG2M, LR>::NT, range_min_ctas<LOG2M, STA
 #pragma unroll 1
   for (int b = tid; b < P::M / P::R0; b += P::NT) {
     if ((b & (S0 - 1)) < a.nDel) fft_butterfly<float, P::R0, +1, LOG2M>(b, P::log2S(0), a.tw, ldA, stR);
+  }
+}
+
+// ---- second-generation range kernel: fused-butterfly DIT transforms (fft_dit.cuh), TMA-staged IQ ----------------
+// Same algebra as caf_range_kernel (R[i][j] = sum_n y_i[n + l] conj(x_i[n]) by segmented cross-spectra, one inverse
+// transform per part), different machine mapping:
+//   * the transforms are the decimation-in-time ones of fft_dit.cuh: 3 packed FP32 instructions per radix-2
+//     butterfly, twiddle included, instead of ~5 (the round-1 kernel was FP32-issue bound, profiles/r01_summary.md s3);
+//   * the x segment and the y window of a segment are transformed ONE AFTER THE OTHER through a single FFT buffer
+//     (the x spectrum waits in registers), which halves the shared memory of a CTA and pays for
+//   * TMA staging of the NEXT segment's two windows (cp.async.bulk, tma_stage.cuh) while the current one is
+//     transformed, with MORE resident CTAs per SM than the round-1 direct-load kernel had (5 instead of 4 at M = 2048).
+template <int LOG2M> struct RangeDit {
+  using P = dit::Plan3<LOG2M>;
+  static constexpr int kStageX = P::M + 2, kStageY = P::M + 2;  // float2 elements (hop <= M, window <= M)
+  static constexpr size_t kSmem = (size_t)P::MP * 8 + (size_t)(kStageX + kStageY) * 8 + 16;
+  static constexpr int kMinCtas = (227 * 1024) / (int)kSmem < 1 ? 1 : ((227 * 1024) / (int)kSmem > 16 ? 16 : (227 * 1024) / (int)kSmem);
+};
+
+struct TwPairF { float2 t1, t2; };
+
+template <int LOG2M, int DIR, class F>
+__device__ __forceinline__ void dit_transform_f32(float2 *A, const TwPairF &tw, int tid, float2 (&v)[16], F after_store) {
+  dit::pass0_store<float, LOG2M, DIR>(A, tid, v);
+  __syncthreads();
+  after_store();
+  dit::pass1_load<float, LOG2M>(A, tid, v);
+  dit::pass1_compute<float, LOG2M, DIR>(tw.t1, v);
+  dit::pass1_store<float, LOG2M>(A, tid, v);
+  __syncthreads();
+  dit::pass2_load<float, LOG2M>(A, tid, v);
+  dit::pass2_compute<float, LOG2M, DIR>(tw.t2, v);
+}
+
+template <int LOG2M>
+__global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, (RangeDit<LOG2M>::kMinCtas * dit::Plan3<LOG2M>::NT > 512 ? 512 / dit::Plan3<LOG2M>::NT : RangeDit<LOG2M>::kMinCtas))
+caf_range_dit_kernel(RangeArgs a) {
+  using P = dit::Plan3<LOG2M>;
+  using K = RangeDit<LOG2M>;
+  constexpr int NT = P::NT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2 *A = reinterpret_cast<float2 *>(smem_raw);
+  float2 *SX = A + P::MP;
+  float2 *SY = SX + K::kStageX;
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(SY + K::kStageY);
+  const int tid = threadIdx.x;
+  const int batch = a.batch0 + blockIdx.x;
+  const long long boff = (long long)batch * a.nCorr;
+  const float2 *__restrict__ xb = a.x + boff;
+  const float2 *__restrict__ yb = a.y + boff;
+  const float2 zero = make_float2(0.f, 0.f);
+  TwPairF tw;
+  tw.t1 = dit::pass1_twiddle<float, LOG2M>(a.tw, tid);
+  tw.t2 = dit::pass2_twiddle<float, LOG2M>(a.tw, tid);
+
+  float2 Z[16];  // cross-spectrum of frequency tid + NT q in Z[q]
+#pragma unroll
+  for (int q = 0; q < 16; q++) Z[q] = zero;
+  const int seg0 = blockIdx.y * a.segPerPart;
+  const int seg1 = min(a.nSeg, seg0 + a.segPerPart);
+
+  // wanted element ranges of segment `seg` relative to the start of the batch: x [n0, n0 + len), y [j0, j1)
+  struct SegWin { int n0, len, yoff, ylen, j0, j1; };
+  auto seg_win = [&](int seg) {
+    SegWin w;
+    w.n0 = seg * a.L;
+    w.len = min(a.L, a.nCorr - w.n0);
+    w.ylen = w.len + a.nDel - 1;   // window entries that can reach a wanted lag
+    w.yoff = w.n0 + a.lagMin;
+    w.j0 = min(max(w.yoff, 0), a.nCorr);
+    w.j1 = max(w.j0, min(w.yoff + w.ylen, a.nCorr));
+    return w;
+  };
+  auto win_x = [&](const SegWin &w) { return tma::make_window(a.x, a.validLo, a.validHi, boff + w.n0, w.len); };
+  auto win_y = [&](const SegWin &w) { return tma::make_window(a.y, a.validLo, a.validHi, boff + w.j0, w.j1 - w.j0); };
+  auto issue = [&](int seg) {  // one thread: both windows of a segment on one barrier phase
+    const SegWin w = seg_win(seg);
+    const tma::Window wx = win_x(w), wy = win_y(w);
+    tma::mbar_expect_tx(mbar, wx.bytes + wy.bytes);
+    if (wx.bytes) tma::bulk_g2s(SX, wx.src, wx.bytes, mbar);
+    if (wy.bytes) tma::bulk_g2s(SY, wy.src, wy.bytes, mbar);
+  };
+  if (tid == 0) {
+    tma::mbar_init(mbar, 1);
+    if (seg0 < seg1) issue(seg0);
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+
+  for (int seg = seg0; seg < seg1; seg++) {
+    const SegWin w = seg_win(seg);
+    const tma::Window wx = win_x(w), wy = win_y(w);
+    tma::mbar_wait(mbar, phase);
+    phase ^= 1;
+    float2 vx[16], vy[16];
+    // Element m = tid + NT k of a window is valid for k in a per-thread range [klo, khi) (m grows with k), so the
+    // masks are two compares against compile-time k; staged reads need no index clamp: the staging buffers hold
+    // M + 2 elements and an index below zero (first segment, negative first lag) still lies inside this CTA's
+    // shared memory -- whatever is read there is masked.
+    auto kceil = [&](int bound) { return min(16, max(0, (bound - tid + NT - 1) / NT)); };  // # of k with tid + NT k < bound
+    // x: the zero-padded segment
+    const int kx = kceil(w.len);
+    if (wx.src) {
+      const float2 *sx = SX + tid + wx.par;
+#pragma unroll
+      for (int k = 0; k < 16; k++) vx[k] = k < kx ? sx[NT * k] : zero;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const int m = tid + NT * k;
+        const float2 e = __ldg(xb + w.n0 + min(m, w.len - 1));
+        vx[k] = m < w.len ? e : zero;
+      }
+    }
+    // y: the window masked to the batch (everything outside the batch is zero: the reference zero-pads per batch)
+    const int ny = w.j1 - w.j0;
+    const int kylo = kceil(w.j0 - w.yoff), kyhi = ny > 0 ? kceil(min(w.ylen, w.j1 - w.yoff)) : 0;
+    if (wy.src || ny == 0) {
+      const float2 *sy = SY + (w.yoff - w.j0) + tid + wy.par;
+#pragma unroll
+      for (int k = 0; k < 16; k++) vy[k] = (k >= kylo && k < kyhi) ? sy[NT * k] : zero;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const int j = w.yoff + tid + NT * k;
+        const float2 e = __ldg(yb + min(max(j, w.j0), w.j1 - 1));
+        vy[k] = (k >= kylo && k < kyhi) ? e : zero;
+      }
+    }
+    // both staging buffers are consumed once every thread has passed the first barrier of the x transform:
+    // the next segment's copies start there and have the rest of this segment to land
+    dit_transform_f32<LOG2M, -1>(A, tw, tid, vx, [&] {
+      if (tid == 0 && seg + 1 < seg1) issue(seg + 1);
+    });
+    __syncthreads();
+    dit_transform_f32<LOG2M, -1>(A, tw, tid, vy, [] {});
+#pragma unroll
+    for (int q = 0; q < 16; q++) cfmac(Z[q], vy[brev<16>(q)], vx[brev<16>(q)]);  // Z += Y conj(X)
+    __syncthreads();
+  }
+
+  // one inverse transform per part; output sample m = tid + NT q is lag lagMin + m: keep m < nDel
+  dit_transform_f32<LOG2M, +1>(A, tw, tid, Z, [] {});
+  const float scale = 1.0f / (float)P::M;
+  float2 *__restrict__ Rrow = a.R + ((size_t)blockIdx.y * a.nDop + batch) * a.nDel;
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    const int m = tid + NT * q;
+    if (m < a.nDel) Rrow[m] = make_float2(Z[brev<16>(q)].x * scale, Z[brev<16>(q)].y * scale);
   }
 }
 
@@ -650,6 +802,17 @@ template <int LOG2M, int G> int launch_range_grouped(const RangeArgs &a, int nDo
   return B200DD_OK;
 }
 
+template <int LOG2M> int launch_range_dit(const RangeArgs &a, int nDop, int nParts, cudaStream_t st) {
+  using P = dit::Plan3<LOG2M>;
+  caf_range_dit_kernel<LOG2M><<<dim3(nDop, nParts), P::NT, RangeDit<LOG2M>::kSmem, st>>>(a);
+  B2_LAUNCH_CHECK();
+  return B200DD_OK;
+}
+template <int LOG2M> int prepare_range_dit() {
+  B2_CUDA(cudaFuncSetAttribute(caf_range_dit_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RangeDit<LOG2M>::kSmem));
+  return B200DD_OK;
+}
+
 // groups > 1: the grouped kernel (direct loads, radix 16) for the FFT lengths small CPIs use
 template <int LOG2M> int launch_range(const RangeArgs &a, int nDop, int nParts, int groups, cudaStream_t st) {
   const char *e = getenv("B200DD_CAF_TMA"), *r = getenv("B200DD_CAF_RADIX");  // per call, like launch_range below
@@ -699,6 +862,25 @@ template <int LOG2M> int launch_fft_forward(const float2 *in, float2 *out, const
   fft_forward_kernel<LOG2M><<<1, P::NT, smem, st>>>(in, out, tw);
   B2_LAUNCH_CHECK();
   return B200DD_OK;
+}
+
+int dispatch_range_dit(int log2m, const RangeArgs &a, int nDop, int nParts, cudaStream_t st) {
+  switch (log2m) {
+    case 9: return launch_range_dit<9>(a, nDop, nParts, st);
+    case 10: return launch_range_dit<10>(a, nDop, nParts, st);
+    case 11: return launch_range_dit<11>(a, nDop, nParts, st);
+    case 12: return launch_range_dit<12>(a, nDop, nParts, st);
+  }
+  return geom_fail("range FFT length out of range");
+}
+int prepare_range_dit(int log2m) {
+  switch (log2m) {
+    case 9: return prepare_range_dit<9>();
+    case 10: return prepare_range_dit<10>();
+    case 11: return prepare_range_dit<11>();
+    case 12: return prepare_range_dit<12>();
+  }
+  return geom_fail("range FFT length out of range");
 }
 
 int dispatch_range(int log2m, const RangeArgs &a, int nDop, int nParts, int groups, cudaStream_t st) {
@@ -760,6 +942,7 @@ struct b200dd_caf {
   cudaStream_t stream = nullptr;
   // range stage plan
   int log2m = 12, nSeg = 1, L = 0, nParts = 1, segPerPart = 1, nGroups = 1;
+  bool dit_range = false;  // second-generation range kernel (fft_dit.cuh + TMA staging): FFT lengths 512 .. 4096
   int num_sms = 148;
   // doppler stage plan
   int log2m2 = 10;
@@ -807,8 +990,12 @@ void plan_range(b200dd_caf *h) {
     // FFT and one more partial range matrix each).  B200DD_CAF_GROUPS / B200DD_CAF_PARTS override.
     const int nDop = (int)h->g.nDop;
     int want = nDop >= 3 * h->num_sms ? 1 : (3 * h->num_sms + nDop - 1) / nDop;  // segment streams per batch
+    // B200DD_CAF_KERNEL=legacy selects the round-1 kernels (and their TMA / radix-8 / group variants)
+    const char *kenv = getenv("B200DD_CAF_KERNEL");
+    const bool legacy = (kenv && strcmp(kenv, "legacy") == 0) || getenv("B200DD_CAF_TMA") || getenv("B200DD_CAF_RADIX") || getenv("B200DD_CAF_GROUPS");
+    h->dit_range = !legacy && best_l >= 9 && best_l <= 12;
     int gmax = best_l == 12 ? 2 : 4;
-    if (best_l < 10 || best_l > 12) gmax = 1;
+    if (best_l < 10 || best_l > 12 || h->dit_range) gmax = 1;
     if (const char *r = getenv("B200DD_CAF_RADIX")) { if (atoi(r) == 8) gmax = 1; }
     if (const char *t = getenv("B200DD_CAF_TMA")) { if (atoi(t) == 1) gmax = 1; }
     int groups = want < gmax ? want : gmax;
@@ -859,6 +1046,10 @@ int caf_setup_device(b200dd_caf *h) {
   if (rc != B200DD_OK) { cudaFree(d_bw); return rc; }
   B2_CUDA(cudaStreamSynchronize(h->stream));
   cudaFree(d_bw);
+  if (h->dit_range) {
+    rc = prepare_range_dit(h->log2m);
+    if (rc != B200DD_OK) return rc;
+  }
   B2_CUDA(cudaMalloc(&h->d_R, sizeof(float2) * (size_t)h->nParts * g.nDop * g.nDel));
   B2_CUDA(cudaMalloc(&h->d_map, sizeof(float2) * (size_t)g.nDop * g.nDel));
   return B200DD_OK;
@@ -880,8 +1071,11 @@ int caf_run_device(b200dd_caf *h, const float2 *d_x, const float2 *d_y, float2 *
   ra.segPerPart = h->segPerPart;
   ra.nDop = (int)g.nDop;
   ra.batch0 = 0;
+  ra.validLo = 0;
+  ra.validHi = (long long)g.nDop * g.nCorr;
   if (ev) B2_CUDA(cudaEventRecord(ev[0], st));
-  int rc = dispatch_range(h->log2m, ra, (int)g.nDop, h->nParts, h->nGroups, st);
+  int rc = h->dit_range ? dispatch_range_dit(h->log2m, ra, (int)g.nDop, h->nParts, st)
+                        : dispatch_range(h->log2m, ra, (int)g.nDop, h->nParts, h->nGroups, st);
   if (rc != B200DD_OK) return rc;
   if (ev) B2_CUDA(cudaEventRecord(ev[1], st));
   DopplerArgs da;
@@ -1110,7 +1304,10 @@ int b200dd_caf_range_device(b200dd_caf *h, const void *d_x, const void *d_y, uin
   ra.tw = h->d_tw1;
   ra.nCorr = (int)g.nCorr; ra.nDel = (int)g.nDel; ra.lagMin = g.delayMin; ra.nSeg = h->nSeg; ra.L = h->L;
   ra.segPerPart = h->segPerPart; ra.nDop = (int)g.nDop; ra.batch0 = (int)batch0;
-  int rc = dispatch_range(h->log2m, ra, (int)n_batches, h->nParts, h->nGroups, st);
+  ra.validLo = (long long)batch0 * g.nCorr;
+  ra.validHi = (long long)(batch0 + n_batches) * g.nCorr;
+  int rc = h->dit_range ? dispatch_range_dit(h->log2m, ra, (int)n_batches, h->nParts, st)
+                        : dispatch_range(h->log2m, ra, (int)n_batches, h->nParts, h->nGroups, st);
   if (rc != B200DD_OK) return rc;
   const size_t plane = (size_t)g.nDop * g.nDel, first = (size_t)batch0 * g.nDel, count = (size_t)n_batches * g.nDel;
   caf_sum_parts_kernel<<<grid_for((uint32_t)count), 256, 0, st>>>(h->d_R, h->nParts, plane, first, count, (float2 *)d_R);

@@ -143,6 +143,15 @@ template <int DIR, int ROT> __device__ __forceinline__ void bf_tw_f32(float2 &a,
   b = p2::fma(make_float2(2.f, 2.f), a, make_float2(-p.x, -p.y));
   a = p;
 }
+// a +- (DIR i) b as two packed adds
+template <int DIR> __device__ __forceinline__ void bf_unit_rot_f32(float2 &a, float2 &b) {
+  const float2 r = DIR > 0 ? make_float2(-b.y, b.x) : make_float2(b.y, -b.x);
+  const float2 p = p2::add(a, r), m = p2::sub(a, r);
+  a = p;
+  b = m;
+}
+template <> __device__ __forceinline__ void bf_unit<float, 1, 1>(float2 &a, float2 &b) { bf_unit_rot_f32<1>(a, b); }
+template <> __device__ __forceinline__ void bf_unit<float, -1, 1>(float2 &a, float2 &b) { bf_unit_rot_f32<-1>(a, b); }
 template <> __device__ __forceinline__ void bf_tw<float, 1, 0>(float2 &a, float2 &b, float2 w) { bf_tw_f32<1, 0>(a, b, w); }
 template <> __device__ __forceinline__ void bf_tw<float, 1, 1>(float2 &a, float2 &b, float2 w) { bf_tw_f32<1, 1>(a, b, w); }
 template <> __device__ __forceinline__ void bf_tw<float, -1, 0>(float2 &a, float2 &b, float2 w) { bf_tw_f32<-1, 0>(a, b, w); }

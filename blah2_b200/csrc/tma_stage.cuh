@@ -51,17 +51,21 @@ struct Window {
   uint32_t bytes = 0;
 };
 
-// window of n contiguous elements base[start .. start + n) of an array of N elements (n <= capacity of S minus 2)
-__device__ __forceinline__ Window make_window(const float2 *base, uint32_t N, uint32_t start, int n) {
+// window of n contiguous elements base[start .. start + n) of an array whose elements [lo, hi) may be read
+// (n <= capacity of S minus 2)
+__device__ __forceinline__ Window make_window(const float2 *base, long long lo, long long hi, long long start, int n) {
   Window w;
   const float2 *p = base + start;
   const int par = (int)((reinterpret_cast<uintptr_t>(p) >> 3) & 1);
   const int tail = (int)((reinterpret_cast<uintptr_t>(p + n) >> 3) & 1);
-  if (n <= 0 || (par && start == 0) || (tail && (uint64_t)start + (uint64_t)n >= (uint64_t)N)) return w;
+  if (n <= 0 || (par && start <= lo) || (tail && start + n >= hi)) return w;
   w.src = p - par;
   w.par = par;
   w.bytes = (uint32_t)(n + par + tail) * 8u;
   return w;
+}
+__device__ __forceinline__ Window make_window(const float2 *base, uint32_t N, uint32_t start, int n) {
+  return make_window(base, 0ll, (long long)N, (long long)start, n);
 }
 
 // one thread: start the copy into S (16-byte aligned) and arm the barrier with its byte count (0: not staged)

@@ -1023,7 +1023,7 @@ template <class TIN> int wh_dispatch(b200dd_wh *h, const void *x, const void *y,
 }
 
 // FFT length minimising FFT work per new sample, M log2 M / (M - nBins + 1), among lengths that fit
-int wh_pick_log2m(const b200dd_wh *h, const char *env1, const char *env2) {
+int wh_pick_log2m(const b200dd_wh *h, const char *env1, const char *env2, bool filter_stage) {
   int forced = 0;
   if (const char *e = getenv(env1)) forced = atoi(e);
   if (const char *e = getenv(env2)) forced = atoi(e);
@@ -1035,6 +1035,10 @@ int wh_pick_log2m(const b200dd_wh *h, const char *env1, const char *env2) {
     if (L < M / 8) continue;
     if ((uint32_t)M > h->N) continue;  // a window never wraps around the signal more than once
     double cost = (double)M * l / (double)L;
+    // filter stage: M = 2048 runs four CTAs per SM (independent barrier domains) against two at M = 4096, which
+    // hides the per-block load latencies better than its 3 % more arithmetic costs (measured 33.8 vs 37.9 us at
+    // 410 taps, profiles/r02_summary.md)
+    if (filter_stage && l == 12) cost *= 1.12;
     if (forced == l) cost = -1.0;
     if (cost < best) { best = cost; best_l = l; }
   }
@@ -1043,8 +1047,8 @@ int wh_pick_log2m(const b200dd_wh *h, const char *env1, const char *env2) {
 
 void wh_plan(b200dd_wh *h) {
   if (const char *e = getenv("B200DD_WH_SOLVE_SHORT")) h->solve_short = atoi(e) != 0;
-  h->log2m_c = wh_pick_log2m(h, "B200DD_WH_LOG2M", "B200DD_WH_CORR_LOG2M");
-  h->log2m_a = wh_pick_log2m(h, "B200DD_WH_LOG2M", "B200DD_WH_APPLY_LOG2M");
+  h->log2m_c = wh_pick_log2m(h, "B200DD_WH_LOG2M", "B200DD_WH_CORR_LOG2M", false);
+  h->log2m_a = wh_pick_log2m(h, "B200DD_WH_LOG2M", "B200DD_WH_APPLY_LOG2M", true);
   if (!h->log2m_c || !h->log2m_a) return;
   const int M = 1 << h->log2m_c;
   h->L = M - h->nBins + 1;
