@@ -106,6 +106,10 @@ SIGNATURES = [
     ("b200dd_wh_debug_weights", C.c_int, [_VP, _VP, _VP, _VP]),
     ("b200dd_wh_n_bins", C.c_uint32, [_VP]),
     ("b200dd_wh_get_plan", C.c_int, [_VP, C.POINTER(WhPlan)]),
+    ("b200dd_wh_create_chunk", C.c_int, [C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(_VP)]),
+    ("b200dd_wh_chunk_halos", C.c_int, [_VP, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    ("b200dd_wh_chunk_corr_device", C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    ("b200dd_wh_chunk_filter_device", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     ("b200dd_wh_stream", _VP, [_VP]),
     ("b200dd_det_create", C.c_int, [C.POINTER(DetParams), C.c_uint32, C.c_uint32, C.POINTER(_VP)]),
     ("b200dd_det_destroy", None, [_VP]),
@@ -156,7 +160,7 @@ SIGNATURES = [
     ("b200dd_comm_gatherv_async", C.c_int, [_VP, _VP, C.c_size_t, _VP, _VP, _VP, C.c_int32, _VP]),
     ("b200dd_comm_allgatherv_async", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     ("b200dd_comm_allreduce_f64_async", C.c_int, [_VP, _VP, C.c_size_t, _VP]),
-    ("b200dd_comm_shift_right_async", C.c_int, [_VP, _VP, _VP, C.c_size_t, _VP]),
+    ("b200dd_comm_sendrecv_async", C.c_int, [_VP, _VP, C.c_size_t, C.c_int32, _VP, C.c_size_t, C.c_int32, _VP]),
     ("b200dd_comm_join", C.c_int, [_VP, _VP]),
     ("b200dd_comm_sync", C.c_int, [_VP]),
     ("b200dd_ubench_fp64_tflops", C.c_int, [C.c_int32, C.POINTER(C.c_double)]),

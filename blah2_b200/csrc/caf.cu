@@ -1005,7 +1005,9 @@ void plan_range(b200dd_caf *h) {
     if (groups < 1) groups = 1;
     h->nGroups = groups;
     int parts = (want + groups - 1) / groups;
-    if (nDop >= h->num_sms) parts = 1;
+    if (nDop >= h->num_sms && !h->dit_range) parts = 1;
+    // second-generation kernel: 4-5 CTAs are resident per SM; split batches into parts until they are filled once
+    if (h->dit_range && nDop * parts > 5 * h->num_sms) parts = (5 * h->num_sms) / nDop < 1 ? 1 : (5 * h->num_sms) / nDop;
     if (const char *e = getenv("B200DD_CAF_PARTS")) parts = atoi(e);
     if (parts < 1) parts = 1;
     if (parts * groups > h->nSeg) parts = h->nSeg / groups;

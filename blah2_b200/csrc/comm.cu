@@ -6,7 +6,7 @@
 //   * one large CPI split over the GPUs: all-gather of the range matrix between the two CAF stages, gather of the
 //     delay-column tiles, and for the clutter filter an all-reduce of the 2 nBins partial correlations plus an
 //     nBins-sample halo from the left neighbour (b200dd_comm_allgatherv_async, _allreduce_f64_async,
-//     _shift_right_async).
+//     _sendrecv_async).
 // One process per GPU; the communicator is NCCL over NVLink / NVSwitch.  NCCL is resolved at run time with
 // dlopen("libnccl.so.2") -- the single-GPU library has no link-time dependency on it, and inside a process that
 // already loaded a NCCL (PyTorch's bundled one) the same copy is reused.  Every call enqueues on the
@@ -249,23 +249,28 @@ int b200dd_comm_allreduce_f64_async(b200dd_comm *c, void *d_buf, size_t count, v
   return B200DD_OK;
 }
 
-int b200dd_comm_shift_right_async(b200dd_comm *c, const void *d_send, void *d_recv, size_t bytes, void *after) {
-  if (!c) return arg_fail("b200dd_comm_shift_right_async: null handle");
+int b200dd_comm_sendrecv_async(b200dd_comm *c, const void *d_send, size_t send_bytes, int32_t send_peer, void *d_recv,
+                               size_t recv_bytes, int32_t recv_peer, void *after) {
+  if (!c) return arg_fail("b200dd_comm_sendrecv_async: null handle");
+  const bool do_send = send_peer >= 0 && send_bytes > 0, do_recv = recv_peer >= 0 && recv_bytes > 0;
+  if ((do_send && (!d_send || send_peer >= c->world)) || (do_recv && (!d_recv || recv_peer >= c->world)))
+    return arg_fail("b200dd_comm_sendrecv_async: bad peer or null buffer");
   DeviceGuard guard(c->device);
   int rc = comm_after(c, after);
   if (rc != B200DD_OK) return rc;
-  if (c->world == 1 || bytes == 0) return B200DD_OK;
   NcclApi &a = nccl_api();
+  if (do_send && do_recv && send_peer == c->rank && recv_peer == c->rank) {  // talking to oneself (world == 1 rings)
+    if (send_bytes != recv_bytes) return arg_fail("b200dd_comm_sendrecv_async: self exchange with different sizes");
+    B2_CUDA(cudaMemcpyAsync(d_recv, d_send, send_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return B200DD_OK;
+  }
   B2_NCCL(a.GroupStart());
-  if (c->rank + 1 < c->world) {
-    if (!d_send) { a.GroupEnd(); return arg_fail("b200dd_comm_shift_right_async: null send buffer"); }
-    B2_NCCL(a.Send(d_send, bytes, ncclUint8, c->rank + 1, c->comm, c->stream));
-  }
-  if (c->rank > 0) {
-    if (!d_recv) { a.GroupEnd(); return arg_fail("b200dd_comm_shift_right_async: null receive buffer"); }
-    B2_NCCL(a.Recv(d_recv, bytes, ncclUint8, c->rank - 1, c->comm, c->stream));
-  }
+  ncclResult_t r1 = ncclSuccess, r2 = ncclSuccess;
+  if (do_send) r1 = a.Send(d_send, send_bytes, ncclUint8, send_peer, c->comm, c->stream);
+  if (do_recv) r2 = a.Recv(d_recv, recv_bytes, ncclUint8, recv_peer, c->comm, c->stream);
   B2_NCCL(a.GroupEnd());
+  if (r1 != ncclSuccess) return nccl_fail(r1, "ncclSend");
+  if (r2 != ncclSuccess) return nccl_fail(r2, "ncclRecv");
   return B200DD_OK;
 }
 

@@ -91,7 +91,9 @@ struct CorrArgs {
   const void *y;
   double2 *partial;   // [grid][2][nBins]
   const double2 *tw;  // exp(-2 pi i j / M)
-  uint32_t N;
+  uint32_t N;                // modulus of the circular indexing (2^31 in chunk mode: no wrap, the halo carries it)
+  uint32_t nBegin, nEnd;     // the segments cover the samples n in [nBegin, nEnd)   ([0, N) for a whole signal)
+  long long xLo, xHi, yLo, yHi;  // readable element ranges of x / y relative to the pointers above
   XsMap xs;
   int nBins, L, nSegTotal, segPerCta;
 };
@@ -189,8 +191,8 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_corr_kernel(CorrA
   // window t (0: P, 1: W, 2: V) of segment s
   auto describe = [&](int s, int t) {
     WinDesc<TIN> d;
-    const uint32_t n0 = (uint32_t)s * (uint32_t)a.L;
-    const int len = (int)min((uint32_t)a.L, N - n0);
+    const uint32_t n0 = a.nBegin + (uint32_t)s * (uint32_t)a.L;
+    const int len = (int)min((uint32_t)a.L, a.nEnd - n0);
     d.N = N;
     d.lim = t == 0 ? len : len + a.nBins - 1;
     if (t < 2) {
@@ -213,7 +215,11 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_corr_kernel(CorrA
   };
   auto stage_window = [&](const WinDesc<TIN> &d) {
     tma::Window w;
-    if (kStage && d.contiguous) w = tma::make_window(reinterpret_cast<const float2 *>(d.p), N, d.start, min(d.lim, CAP));
+    if (kStage && d.contiguous) {
+      const bool isx = reinterpret_cast<const void *>(d.p) == a.x;
+      w = tma::make_window(reinterpret_cast<const float2 *>(d.p), isx ? a.xLo : a.yLo, isx ? a.xHi : a.yHi, (long long)d.start,
+                           min(d.lim, CAP));
+    }
     return w;
   };
   uint32_t phase = 0;
@@ -223,11 +229,11 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_corr_kernel(CorrA
     if constexpr (kStage) {
       if (tid == 0) tma::issue(stage_window(d), S, mbar);
     }
-    r15 = direct(d, 0, (uint32_t)s0 * (uint32_t)a.L, tid + 15 * NT);
+    r15 = direct(d, 0, a.nBegin + (uint32_t)s0 * (uint32_t)a.L, tid + 15 * NT);
   }
   double2 vxp[16];
   for (int s = s0; s < s1; s++) {
-    const uint32_t n0 = (uint32_t)s * (uint32_t)a.L;
+    const uint32_t n0 = a.nBegin + (uint32_t)s * (uint32_t)a.L;
     // NOT unrolled: three (five with the inverses) copies of the transform overflow the instruction cache
     // (11 % of the stall samples were no_instruction, profiles/r02_summary.md)
 #pragma unroll 1
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_corr_kernel(CorrA
           if constexpr (kStage) {
             if (tid == 0) tma::issue(stage_window(dn), S, mbar);
           }
-          r15 = direct(dn, nt, (uint32_t)ns * (uint32_t)a.L, tid + 15 * NT);
+          r15 = direct(dn, nt, a.nBegin + (uint32_t)ns * (uint32_t)a.L, tid + 15 * NT);
         }
       });
       if (t == 0) {
@@ -344,6 +350,20 @@ struct SolveArgs {
   double2 *a_out, *b_out, *w_out;
   int *status;  // 0 ok, 1 failed
 };
+
+// chunk mode: this GPU's correlation sums = fixed-order sum of its CTAs' partials (the all-reduce over the GPUs and
+// the replicated solve follow)
+__global__ void wh_reduce_partials_kernel(const double2 *__restrict__ partial, int nPartial, int n2, double2 *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  double2 s = make_double2(0.0, 0.0);
+  for (int p = 0; p < nPartial; p++) {
+    const double2 v = partial[(size_t)p * n2 + i];
+    s.x += v.x;
+    s.y += v.y;
+  }
+  out[i] = s;
+}
 
 // 2^(1-e) where p*p = m 2^e, m in [0.5, 1): exact power of two, integer ops only
 __device__ __forceinline__ double pow2_scale(double p) {
@@ -743,7 +763,9 @@ struct ApplyArgs {
   const double2 *what;
   const double2 *tw;
   const int *status;
-  uint32_t N;
+  uint32_t N;              // modulus of the reference's index map (2^31 in chunk mode)
+  uint32_t iBegin, iEnd;   // the blocks cover the outputs i in [iBegin, iEnd)   ([0, N) for a whole signal)
+  long long xLo, xHi;      // readable element range of x relative to the pointer above
   XsMap xs;
   int nBins, Lout, nBlocks;
 };
@@ -794,8 +816,8 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, wh_min_ctas<LOG2M>()) w
   const int hist = a.nBins - 1;
   if (*a.status != 0) {  // failed solve: surveillance channel passes through untouched
     for (int b = blockIdx.x; b < a.nBlocks; b += gridDim.x) {
-      const uint32_t i0 = (uint32_t)b * (uint32_t)a.Lout;
-      const int nOut = (int)min((uint32_t)a.Lout, a.N - i0);
+      const uint32_t i0 = a.iBegin + (uint32_t)b * (uint32_t)a.Lout;
+      const int nOut = (int)min((uint32_t)a.Lout, a.iEnd - i0);
       for (int m = tid; m < nOut; m += NT) st_iq<TIN>(yo, i0 + m, ld_iq(y, i0 + m));
     }
     return;
@@ -807,12 +829,12 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, wh_min_ctas<LOG2M>()) w
   auto stage_window = [&](int b) {
     tma::Window w;
     if constexpr (kStage) {
-      const int64_t first = (int64_t)b * a.Lout - hist;
-      const int nOut = (int)min((uint32_t)a.Lout, a.N - (uint32_t)b * (uint32_t)a.Lout);
+      const int64_t first = (int64_t)a.iBegin + (int64_t)b * a.Lout - hist;
       if (b < a.nBlocks && first >= 0 && xs.thr == 0) {
+        const int nOut = (int)min((uint32_t)a.Lout, a.iEnd - (a.iBegin + (uint32_t)b * (uint32_t)a.Lout));
         const uint32_t start = xs((uint32_t)first);
         if ((uint64_t)start + (uint64_t)(hist + nOut) <= (uint64_t)a.N)
-          w = tma::make_window(reinterpret_cast<const float2 *>(x), a.N, start, hist + nOut);
+          w = tma::make_window(reinterpret_cast<const float2 *>(x), a.xLo, a.xHi, (long long)start, hist + nOut);
       }
     }
     return w;
@@ -826,8 +848,8 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, wh_min_ctas<LOG2M>()) w
     __syncthreads();
   }
   for (int b = blockIdx.x; b < a.nBlocks; b += gridDim.x) {
-    const uint32_t i0 = (uint32_t)b * (uint32_t)a.Lout;
-    const int nOut = (int)min((uint32_t)a.Lout, a.N - i0);
+    const uint32_t i0 = a.iBegin + (uint32_t)b * (uint32_t)a.Lout;
+    const int nOut = (int)min((uint32_t)a.Lout, a.iEnd - i0);
     const tma::Window w = stage_window(b);
     double2 v[16];
     // the block's surveillance samples are needed two transforms from now: ask L2 for them (one line per thread)
@@ -852,7 +874,8 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, wh_min_ctas<LOG2M>()) w
       }
       if (!staged) {  // branch-free: load from a clamped valid index, mask afterwards
         const int64_t ic = i < 0 ? 0 : (i >= (int64_t)a.N ? (int64_t)a.N - 1 : i);
-        e = x[xs((uint32_t)ic)];
+        const long long xi = (long long)xs((uint32_t)ic);
+        e = x[xi < a.xLo ? a.xLo : (xi >= a.xHi ? a.xHi - 1 : xi)];  // (masked elements only; keeps the address readable)
       }
       v[k] = make_double2(ok ? (double)e.x : 0.0, ok ? (double)e.y : 0.0);
     }
@@ -915,6 +938,11 @@ struct b200dd_wh {
   double2 *d_xd = nullptr, *d_yd = nullptr;  // host path staging (complex128)
   int num_sms = 148;
   bool solve_short = true;  // B200DD_WH_SOLVE_SHORT, read once at create
+  // chunk mode (one CPI split over several GPUs): this handle filters the samples [c0, c0 + nc) of an N-sample signal
+  bool chunked = false;
+  uint32_t c0 = 0, nc = 0;
+  int haloXL = 0, haloXR = 0, haloYR = 0;
+  double2 *d_ab = nullptr;  // [2][nBins] this chunk's correlation sums (reduced over its CTAs)
   bool attr_corr_f32 = false, attr_corr_f64 = false, attr_apply_f32 = false, attr_apply_f64 = false, attr_solve = false;
 };
 
@@ -938,7 +966,16 @@ template <int LOG2M, class TIN> int wh_launch_corr(b200dd_wh *h, const void *x, 
     done = true;
   }
   CorrArgs ca;
-  ca.x = x; ca.y = y; ca.partial = h->d_partial; ca.tw = h->d_tw_c; ca.N = h->N; ca.xs = make_xs_map(h->N, h->delayMin);
+  ca.x = x; ca.y = y; ca.partial = h->d_partial; ca.tw = h->d_tw_c;
+  if (h->chunked) {  // x, y are virtual pointers indexed by GLOBAL sample number; the halos carry the circular wrap
+    ca.N = 1u << 31; ca.nBegin = h->c0; ca.nEnd = h->c0 + h->nc;
+    ca.xs.N = 1u << 31; ca.xs.thr = 0; ca.xs.add1 = (uint32_t)(-h->delayMin); ca.xs.add2 = 0;
+    ca.xLo = (long long)h->c0 - h->haloXL; ca.xHi = (long long)h->c0 + h->nc + h->haloXR;
+    ca.yLo = (long long)h->c0; ca.yHi = (long long)h->c0 + h->nc + h->haloYR;
+  } else {
+    ca.N = h->N; ca.nBegin = 0; ca.nEnd = h->N; ca.xs = make_xs_map(h->N, h->delayMin);
+    ca.xLo = ca.yLo = 0; ca.xHi = ca.yHi = (long long)h->N;
+  }
   ca.nBins = h->nBins; ca.L = h->L; ca.nSegTotal = h->nSeg; ca.segPerCta = h->segPerCta;
   wh_corr_kernel<LOG2M, TIN><<<h->gridCorr, P::NT, corr_smem<LOG2M>(), st>>>(ca);
   B2_LAUNCH_CHECK();
@@ -957,7 +994,15 @@ template <int LOG2M, class TIN> int wh_launch_apply(b200dd_wh *h, const void *x,
   B2_LAUNCH_CHECK();
   ApplyArgs aa;
   aa.x = x; aa.y = y; aa.y_out = y_out; aa.what = h->d_what; aa.tw = h->d_tw_a; aa.status = h->d_status;
-  aa.N = h->N; aa.xs = make_xs_map(h->N, h->delayMin); aa.nBins = h->nBins; aa.Lout = h->Lout; aa.nBlocks = h->gridApply;
+  if (h->chunked) {
+    aa.N = 1u << 31; aa.iBegin = h->c0; aa.iEnd = h->c0 + h->nc;
+    aa.xs.N = 1u << 31; aa.xs.thr = 0; aa.xs.add1 = (uint32_t)(-h->delayMin); aa.xs.add2 = 0;
+    aa.xLo = (long long)h->c0 - h->haloXL; aa.xHi = (long long)h->c0 + h->nc + h->haloXR;
+  } else {
+    aa.N = h->N; aa.iBegin = 0; aa.iEnd = h->N; aa.xs = make_xs_map(h->N, h->delayMin);
+    aa.xLo = 0; aa.xHi = (long long)h->N;
+  }
+  aa.nBins = h->nBins; aa.Lout = h->Lout; aa.nBlocks = h->gridApply;
   // persistent CTAs: as many as are resident at once (shared memory and the 128-register bound decide)
   int per_sm = (int)((227 * 1024) / apply_smem<LOG2M>());
   if (per_sm > wh_min_ctas<LOG2M>()) per_sm = wh_min_ctas<LOG2M>();
@@ -980,7 +1025,7 @@ int wh_launch_solve(b200dd_wh *h, cudaStream_t st) {
     h->attr_solve = true;
   }
   SolveArgs sa;
-  sa.partial = h->d_partial; sa.nPartial = h->gridCorr; sa.nBins = h->nBins;
+  sa.partial = h->chunked ? h->d_ab : h->d_partial; sa.nPartial = h->chunked ? 1 : h->gridCorr; sa.nBins = h->nBins;
   sa.a_out = h->d_a; sa.b_out = h->d_b; sa.w_out = h->d_w; sa.status = h->d_status;
   const int threads = ((h->nBins + 31) / 32) * 32;
   if (h->solve_short && threads + 32 <= 1024) {  // includes the reference's configuration (410 taps)
@@ -1052,7 +1097,8 @@ void wh_plan(b200dd_wh *h) {
   if (!h->log2m_c || !h->log2m_a) return;
   const int M = 1 << h->log2m_c;
   h->L = M - h->nBins + 1;
-  h->nSeg = (int)(((uint64_t)h->N + h->L - 1) / h->L);
+  const uint64_t span = h->chunked ? h->nc : h->N;  // samples this handle's kernels walk
+  h->nSeg = (int)((span + h->L - 1) / h->L);
   // CTAs resident at once: shared memory allows 1 (M=4096) or 2 (smaller) per SM
   const size_t smem = (size_t)(M + M / 16 + 2 * M) * sizeof(double2);
   int per_sm = (int)((227 * 1024) / smem);
@@ -1064,14 +1110,30 @@ void wh_plan(b200dd_wh *h) {
   h->gridCorr = (h->nSeg + h->segPerCta - 1) / h->segPerCta;
   const int Ma = 1 << h->log2m_a;
   h->Lout = Ma - h->nBins + 1;
-  h->gridApply = (int)(((uint64_t)h->N + h->Lout - 1) / h->Lout);
+  h->gridApply = (int)((span + h->Lout - 1) / h->Lout);
 }
 
 }  // namespace
 
 extern "C" {
 
+static int wh_create_impl(int32_t delay_min, int32_t delay_max, uint32_t n_samples, int32_t device, bool chunked,
+                          uint32_t chunk_begin, uint32_t chunk_len, b200dd_wh **out);
+
 int b200dd_wh_create(int32_t delay_min, int32_t delay_max, uint32_t n_samples, int32_t device, b200dd_wh **out) {
+  return wh_create_impl(delay_min, delay_max, n_samples, device, false, 0, 0, out);
+}
+
+int b200dd_wh_create_chunk(int32_t delay_min, int32_t delay_max, uint32_t n_samples, uint32_t chunk_begin, uint32_t chunk_len,
+                           int32_t device, b200dd_wh **out) {
+  if (delay_min > 0) return geom_fail("b200dd_wh_create_chunk: delayMin <= 0 only (the reference's index map is a plain rotation there)");
+  if (chunk_len == 0 || (uint64_t)chunk_begin + chunk_len > n_samples) return arg_fail("b200dd_wh_create_chunk: chunk outside the signal");
+  if ((uint64_t)n_samples >= (1ull << 30)) return geom_fail("b200dd_wh_create_chunk: signals up to 2^30 samples");
+  return wh_create_impl(delay_min, delay_max, n_samples, device, true, chunk_begin, chunk_len, out);
+}
+
+static int wh_create_impl(int32_t delay_min, int32_t delay_max, uint32_t n_samples, int32_t device, bool chunked,
+                          uint32_t chunk_begin, uint32_t chunk_len, b200dd_wh **out) {
   if (!out) return arg_fail("b200dd_wh_create: null argument");
   *out = nullptr;
   if (n_samples == 0) return arg_fail("b200dd_wh_create: n_samples must be > 0");
@@ -1085,6 +1147,17 @@ int b200dd_wh_create(int32_t delay_min, int32_t delay_max, uint32_t n_samples, i
   h->delayMax = delay_max;
   h->N = n_samples;
   h->nBins = (int)nb;
+  if (chunked) {
+    h->chunked = true;
+    h->c0 = chunk_begin;
+    h->nc = chunk_len;
+    const int sh = -delay_min;  // xs[i] = x[i + sh]
+    h->haloXL = (int)nb - 1 - sh > 0 ? (int)nb - 1 - sh : 0;   // the filter reaches back nBins - 1 samples of xs
+    h->haloXR = (int)nb - 1 + sh;                               // the correlations reach forward nBins - 1 samples of xs
+    h->haloYR = (int)nb - 1;
+    if ((uint32_t)(nb + sh) > chunk_len && n_samples != chunk_len)
+      { delete h; return geom_fail("b200dd_wh_create_chunk: a chunk must be longer than the filter (the halo comes from ONE neighbour)"); }
+  }
   auto fail = [&](int rc) { b200dd_wh_destroy(h); return rc; };
   int dev = device;
   if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaGetDevice", __FILE__, __LINE__));
@@ -1111,6 +1184,7 @@ int b200dd_wh_create(int32_t delay_min, int32_t delay_max, uint32_t n_samples, i
     B2_CUDA(cudaMalloc(&h->d_what, sizeof(double2) * M));
     B2_CUDA(cudaMalloc(&h->d_status, sizeof(int)));
     B2_CUDA(cudaMemset(h->d_status, 0, sizeof(int)));
+    if (h->chunked) B2_CUDA(cudaMalloc(&h->d_ab, sizeof(double2) * 2 * h->nBins));
     return B200DD_OK;
   };
   int rc = body();
@@ -1132,6 +1206,7 @@ void b200dd_wh_destroy(b200dd_wh *h) {
     free_dev(h->d_w);
     free_dev(h->d_what);
     free_dev(h->d_status);
+    free_dev(h->d_ab);
     free_dev(h->d_xd);
     free_dev(h->d_yd);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1151,6 +1226,59 @@ int b200dd_wh_process_device_f64(b200dd_wh *h, const void *d_x, const void *d_y,
   DeviceGuard guard(h->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   return wh_dispatch<double2>(h, d_x, d_y, d_y_out, st);
+}
+
+int b200dd_wh_chunk_halos(const b200dd_wh *h, uint32_t *x_left, uint32_t *x_right, uint32_t *y_right) {
+  if (!h || !h->chunked) return arg_fail("b200dd_wh_chunk_halos: not a chunk handle");
+  if (x_left) *x_left = (uint32_t)h->haloXL;
+  if (x_right) *x_right = (uint32_t)h->haloXR;
+  if (y_right) *y_right = (uint32_t)h->haloYR;
+  return B200DD_OK;
+}
+
+int b200dd_wh_chunk_corr_device(b200dd_wh *h, const void *d_x_loc, const void *d_y_loc, void *d_ab, void *stream) {
+  if (!h || !d_x_loc || !d_y_loc || !d_ab) return arg_fail("b200dd_wh_chunk_corr_device: null argument");
+  if (!h->chunked) return arg_fail("b200dd_wh_chunk_corr_device: not a chunk handle");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  // virtual pointers indexed by the GLOBAL sample number
+  const float2 *xv = (const float2 *)d_x_loc - ((long long)h->c0 - h->haloXL);
+  const float2 *yv = (const float2 *)d_y_loc - (long long)h->c0;
+  int rc = B200DD_ERR_GEOMETRY;
+  switch (h->log2m_c) {
+    case 9: rc = wh_launch_corr<9, float2>(h, xv, yv, st); break;
+    case 10: rc = wh_launch_corr<10, float2>(h, xv, yv, st); break;
+    case 11: rc = wh_launch_corr<11, float2>(h, xv, yv, st); break;
+    case 12: rc = wh_launch_corr<12, float2>(h, xv, yv, st); break;
+  }
+  if (rc != B200DD_OK) return rc;
+  const int n2 = 2 * h->nBins;
+  wh_reduce_partials_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(h->d_partial, h->gridCorr, n2, (double2 *)d_ab);
+  B2_LAUNCH_CHECK();
+  return B200DD_OK;
+}
+
+int b200dd_wh_chunk_filter_device(b200dd_wh *h, const void *d_ab, const void *d_x_loc, const void *d_y_loc, void *d_y_out,
+                                  void *stream) {
+  if (!h || !d_ab || !d_x_loc || !d_y_loc || !d_y_out) return arg_fail("b200dd_wh_chunk_filter_device: null argument");
+  if (!h->chunked) return arg_fail("b200dd_wh_chunk_filter_device: not a chunk handle");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  if (d_ab != (const void *)h->d_ab)
+    B2_CUDA(cudaMemcpyAsync(h->d_ab, d_ab, sizeof(double2) * 2 * h->nBins, cudaMemcpyDeviceToDevice, st));
+  int rc = wh_launch_solve(h, st);  // replicated on every GPU: identical sums in, identical weights out
+  if (rc != B200DD_OK) return rc;
+  const float2 *xv = (const float2 *)d_x_loc - ((long long)h->c0 - h->haloXL);
+  const float2 *yv = (const float2 *)d_y_loc - (long long)h->c0;
+  float2 *yo = (float2 *)d_y_out - (long long)h->c0;
+  rc = B200DD_ERR_GEOMETRY;
+  switch (h->log2m_a) {
+    case 9: rc = wh_launch_apply<9, float2>(h, xv, yv, yo, st); break;
+    case 10: rc = wh_launch_apply<10, float2>(h, xv, yv, yo, st); break;
+    case 11: rc = wh_launch_apply<11, float2>(h, xv, yv, yo, st); break;
+    case 12: rc = wh_launch_apply<12, float2>(h, xv, yv, yo, st); break;
+  }
+  return rc;
 }
 
 int b200dd_wh_profile_device(b200dd_wh *h, const void *d_x, const void *d_y, void *d_y_out, void *stream,

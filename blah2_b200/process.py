@@ -217,6 +217,55 @@ class WienerHopf:
             pass
 
 
+class WienerHopfChunk:
+    """The clutter filter on ONE CHUNK of a CPI that is split over several GPUs (C ABI
+    b200dd_wh_create_chunk).  Device path only (complex64 CUDA tensors).  x_loc / y_loc are the chunk plus the
+    halos `halos()` reports; blah2_b200.shard.wienerhopf_single_cpi_sharded drives it across ranks."""
+
+    def __init__(self, delayMin, delayMax, nSamples, chunk_begin, chunk_len, device=-1):
+        lib = capi.load()
+        h = C.c_void_p()
+        capi.check(lib.b200dd_wh_create_chunk(int(delayMin), int(delayMax), int(nSamples), int(chunk_begin), int(chunk_len),
+                                              int(device), C.byref(h)))
+        self._lib, self._h = lib, h
+        self.nSamples, self.chunk_begin, self.chunk_len = int(nSamples), int(chunk_begin), int(chunk_len)
+        self.nBins = int(lib.b200dd_wh_n_bins(h))
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        capi.check(lib.b200dd_wh_chunk_halos(h, C.byref(a), C.byref(b), C.byref(c)))
+        self.x_left, self.x_right, self.y_right = int(a.value), int(b.value), int(c.value)
+
+    def halos(self):
+        """(x_left, x_right, y_right) in samples."""
+        return self.x_left, self.x_right, self.y_right
+
+    def corr_device(self, d_x_loc, d_y_loc, d_ab, stream=None):
+        """d_ab (complex128 CUDA tensor, 2 nBins) <- this chunk's share of (a, b)."""
+        assert d_x_loc.numel() == self.x_left + self.chunk_len + self.x_right and d_y_loc.numel() == self.chunk_len + self.y_right
+        capi.check(self._lib.b200dd_wh_chunk_corr_device(self._h, capi.ptr(d_x_loc), capi.ptr(d_y_loc), capi.ptr(d_ab),
+                                                         capi.ptr(stream) if stream else None))
+
+    def filter_device(self, d_ab, d_x_loc, d_y_loc, d_y_out, stream=None):
+        """Replicated solve on the summed d_ab, then the chunk's chunk_len filtered samples into d_y_out."""
+        assert d_y_out.numel() == self.chunk_len
+        capi.check(self._lib.b200dd_wh_chunk_filter_device(self._h, capi.ptr(d_ab), capi.ptr(d_x_loc), capi.ptr(d_y_loc),
+                                                           capi.ptr(d_y_out), capi.ptr(stream) if stream else None))
+
+    def last_status(self) -> bool:
+        rc = capi.check(self._lib.b200dd_wh_last_status(self._h), allow=(capi.FILTER_FAILED,))
+        return rc == capi.OK
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200dd_wh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class SpectrumAnalyser:
     """SpectrumAnalyser(n, bandwidth) -- src/process/spectrum/SpectrumAnalyser.h:48.
 

@@ -68,10 +68,13 @@ class Comm:
         count = buf.numel() * (2 if buf.is_complex() else 1)
         self._capi.check(self._lib.b200dd_comm_allreduce_f64_async(self._h, self._capi.ptr(buf), count, self._sp(after)))
 
-    def shift_right_async(self, send, recv, nbytes: int, after=None):
-        self._capi.check(self._lib.b200dd_comm_shift_right_async(self._h, self._capi.ptr(send) if send is not None else None,
-                                                                 self._capi.ptr(recv) if recv is not None else None,
-                                                                 int(nbytes), self._sp(after)))
+    def sendrecv_async(self, send, send_peer: int, recv, recv_peer: int, after=None):
+        """One send (to send_peer) and / or one receive (from recv_peer) in one group; a peer of -1 skips that half."""
+        sb = send.numel() * send.element_size() if (send is not None and send_peer >= 0) else 0
+        rb = recv.numel() * recv.element_size() if (recv is not None and recv_peer >= 0) else 0
+        self._capi.check(self._lib.b200dd_comm_sendrecv_async(self._h, self._capi.ptr(send) if sb else None, sb, int(send_peer),
+                                                              self._capi.ptr(recv) if rb else None, rb, int(recv_peer),
+                                                              self._sp(after)))
 
     def join(self, stream):
         """`stream` waits for everything enqueued on the communicator so far."""

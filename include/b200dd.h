@@ -202,6 +202,23 @@ B200DD_API const int *b200dd_wh_device_status(b200dd_wh *h);
 B200DD_API int b200dd_wh_debug_weights(b200dd_wh *h, double *w, double *a, double *b);
 B200DD_API uint32_t b200dd_wh_n_bins(const b200dd_wh *h);
 
+/* ---- one CPI split over several GPUs: this handle filters the samples
+ * [chunk_begin, chunk_begin + chunk_len) of an n_samples-sample signal (delayMin <= 0, chunk longer than the
+ * filter).  The caller holds LOCAL float2 buffers with halos (b200dd_wh_chunk_halos):
+ *   x_loc: x[chunk_begin - x_left .. chunk_begin + chunk_len + x_right)   (indices taken modulo n_samples on the right:
+ *          the correlations are circular; the left halo of the first chunk is never read: zero filter history)
+ *   y_loc: y[chunk_begin .. chunk_begin + chunk_len + y_right)            (modulo n_samples as well)
+ * 1. b200dd_wh_chunk_corr_device -> d_ab = this chunk's share of (a[0..nBins), b[0..nBins)) (2 nBins complex128);
+ * 2. the caller sums d_ab over the GPUs (b200dd_comm_allreduce_f64_async, 4 nBins doubles);
+ * 3. b200dd_wh_chunk_filter_device solves the SAME system on every GPU and writes the chunk's chunk_len filtered
+ *    samples (float2) to d_y_out.  b200dd_wh_last_status reports a failed solve as for a whole signal. */
+B200DD_API int b200dd_wh_create_chunk(int32_t delay_min, int32_t delay_max, uint32_t n_samples, uint32_t chunk_begin,
+                                      uint32_t chunk_len, int32_t device, b200dd_wh **out);
+B200DD_API int b200dd_wh_chunk_halos(const b200dd_wh *h, uint32_t *x_left, uint32_t *x_right, uint32_t *y_right);
+B200DD_API int b200dd_wh_chunk_corr_device(b200dd_wh *h, const void *d_x_loc, const void *d_y_loc, void *d_ab, void *stream);
+B200DD_API int b200dd_wh_chunk_filter_device(b200dd_wh *h, const void *d_ab, const void *d_x_loc, const void *d_y_loc,
+                                             void *d_y_out, void *stream);
+
 /* The FFT plan of the two FFT stages (for measurement: transforms per CPI = 3 corr_segments + 2 corr_ctas in the
  * correlation kernel, 2 filter_blocks + 1 in the filter stage). */
 typedef struct {
@@ -440,8 +457,10 @@ B200DD_API int b200dd_comm_allgatherv_async(b200dd_comm *c, const void *d_send, 
                                             const size_t *offsets, void *after);
 /* in-place sum of `count` doubles over the ranks */
 B200DD_API int b200dd_comm_allreduce_f64_async(b200dd_comm *c, void *d_buf, size_t count, void *after);
-/* rank r sends `bytes` to rank r + 1 and receives as many from rank r - 1 (no wrap-around) */
-B200DD_API int b200dd_comm_shift_right_async(b200dd_comm *c, const void *d_send, void *d_recv, size_t bytes, void *after);
+/* one send and / or one receive in one NCCL group (halo exchange): a peer of -1 (or a size of 0) skips that half;
+ * the peers' calls must pair up (rank a sends to b <=> rank b receives from a, same size) */
+B200DD_API int b200dd_comm_sendrecv_async(b200dd_comm *c, const void *d_send, size_t send_bytes, int32_t send_peer,
+                                          void *d_recv, size_t recv_bytes, int32_t recv_peer, void *after);
 B200DD_API int b200dd_comm_join(b200dd_comm *c, void *stream);
 B200DD_API int b200dd_comm_sync(b200dd_comm *c);
 

@@ -155,3 +155,55 @@ def test_both_solve_kernels_give_the_same_weights(case, relerr, monkeypatch):
     assert relerr(ws["1"], ws["0"])[0] < 1e-11
 
 
+
+
+@pytest.mark.parametrize("case", [(300000, -10, 400, 3, 7), (120000, 0, 60, 2, 8), (200003, -3, 129, 4, 9)])
+def test_chunked_filter_emulating_several_ranks(case, relerr):
+    """One CPI split over several GPUs, emulated on one device: every 'rank' correlates its
+    chunk (right halo circular, as the reference's N-point correlations are), the partial (a, b) are summed, every
+    rank solves the same system and filters its chunk (left halo = filter history, zero before sample 0).  The
+    concatenated output must equal the one-GPU filter's and the oracle's."""
+    import torch
+    from blah2_b200.process import WienerHopfChunk
+    from blah2_b200.shard import block_range
+    n, dm, dM, world, seed = case
+    sc = _scene(n, seed)
+    xg = sc.x.astype(np.complex64)
+    yg = sc.y.astype(np.complex64)
+    wh = WienerHopf(dm, dM, n)
+    dx, dy = torch.from_numpy(xg).cuda(), torch.from_numpy(yg).cuda()
+    ref = torch.empty_like(dy)
+    torch.cuda.synchronize()
+    wh.process_device(dx, dy, ref)
+    torch.cuda.synchronize()
+    w_ref, a_ref, b_ref = wh.debug_weights()
+    s = torch.cuda.Stream()
+    chunks, ab_parts = [], []
+    with torch.cuda.stream(s):
+        for r in range(world):
+            c0, nc = block_range(n, r, world)
+            ch = WienerHopfChunk(dm, dM, n, c0, nc)
+            xl, xr, yr = ch.halos()
+            ix = (np.arange(c0 - xl, c0 + nc + xr)) % n          # (the first chunk's left halo is never used)
+            iy = (np.arange(c0, c0 + nc + yr)) % n
+            x_loc = torch.from_numpy(xg[ix]).cuda()
+            y_loc = torch.from_numpy(yg[iy]).cuda()
+            ab = torch.zeros(2 * ch.nBins, dtype=torch.complex128, device="cuda")
+            ch.corr_device(x_loc, y_loc, ab, s.cuda_stream)
+            chunks.append((ch, x_loc, y_loc, nc))
+            ab_parts.append(ab)
+        s.synchronize()
+        ab_sum = torch.stack(ab_parts).sum(0)              # what the all-reduce over the ranks computes
+        nb = chunks[0][0].nBins
+        assert relerr(ab_sum[:nb].cpu().numpy(), a_ref)[0] < 1e-12 and relerr(ab_sum[nb:].cpu().numpy(), b_ref)[0] < 1e-12
+        outs = []
+        for ch, x_loc, y_loc, nc in chunks:
+            o = torch.empty(nc, dtype=torch.complex64, device="cuda")
+            ch.filter_device(ab_sum, x_loc, y_loc, o, s.cuda_stream)
+            outs.append(o)
+        s.synchronize()
+    assert all(c[0].last_status() for c in chunks)
+    got = torch.cat(outs).cpu().numpy()
+    assert relerr(got, ref.cpu().numpy())[0] < 1e-6          # complex64 output rounding
+    ok, y_ref = O.wienerhopf_process(xg.astype(np.complex128), yg.astype(np.complex128), dm, dM)
+    assert ok and relerr(got, y_ref)[0] < 1e-6
