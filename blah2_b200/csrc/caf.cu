@@ -1331,6 +1331,17 @@ int b200dd_caf_doppler_device(b200dd_caf *h, const void *d_R, uint32_t col0, uin
   return dispatch_doppler(h->log2m2, da, st);
 }
 
+int b200dd_caf_place_tile_device(b200dd_caf *h, const void *d_tile, uint32_t col0, uint32_t n_cols, void *d_map, void *stream) {
+  if (!h || !d_tile || !d_map) return arg_fail("b200dd_caf_place_tile_device: null argument");
+  const HostGeom &g = h->g;
+  if (n_cols == 0 || (uint64_t)col0 + n_cols > g.nDel) return arg_fail("b200dd_caf_place_tile_device: column range outside the map");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  B2_CUDA(cudaMemcpy2DAsync((float2 *)d_map + col0, sizeof(float2) * g.nDel, d_tile, sizeof(float2) * n_cols, sizeof(float2) * n_cols,
+                            g.nDop, cudaMemcpyDeviceToDevice, st));
+  return B200DD_OK;
+}
+
 int b200dd_caf_debug_range_matrix(b200dd_caf *h, float *out) {
   if (!h || !out) return arg_fail("b200dd_caf_debug_range_matrix: null argument");
   DeviceGuard guard(h->device);

@@ -125,6 +125,11 @@ class Ambiguity:
         capi.check(self._lib.b200dd_caf_doppler_device(self._h, capi.ptr(d_R), int(col0), int(n_cols),
                                                        capi.ptr(d_map_tile), capi.ptr(stream) if stream else None))
 
+    def place_tile(self, d_tile, col0, n_cols, d_map, stream=None):
+        """Tile [nDop][n_cols] -> delay columns [col0, col0 + n_cols) of the row-major map d_map."""
+        capi.check(self._lib.b200dd_caf_place_tile_device(self._h, capi.ptr(d_tile), int(col0), int(n_cols), capi.ptr(d_map),
+                                                          capi.ptr(stream) if stream else None))
+
     def profile_device(self, d_x, d_y, d_map=None, stream=None):
         """(ms_range, ms_doppler): CUDA-event durations of the two CAF kernels for one CPI."""
         a, b = C.c_float(), C.c_float()

@@ -191,3 +191,164 @@ def caf_single_cpi_sharded(amb, d_x_local: torch.Tensor, d_y_local: torch.Tensor
         return None
     cols = torch.cat([torch.view_as_complex(gathered[r])[: ccounts[r]] for r in range(world)], dim=0)  # [nDel, nDop]
     return cols.transpose(0, 1).contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# Same interface as Comm on top of torch.distributed (gloo): CPU tests of the orchestration below
+# ------------------------------------------------------------------------------------------
+class TorchComm:
+    """Synchronous stand-in for Comm (tests/test_shard_cpu.py, world_size-2 gloo on CPU tensors)."""
+
+    def __init__(self, rank: int, world: int):
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def _bytes(t):
+        return torch.view_as_real(t).reshape(-1) if t.is_complex() else t.reshape(-1)
+
+    def gatherv_async(self, send, recv, sizes, offsets, dst=0, after=None):
+        es = send.element_size()
+        parts = None
+        if self.rank == dst:
+            parts = [torch.empty(int(sizes[r]) // es, dtype=send.dtype) for r in range(self.world)]
+        # gloo's gather wants equal sizes: pad to the largest block
+        k = max(int(v) for v in sizes) // es
+        buf = torch.zeros(k, dtype=send.dtype)
+        buf[: send.numel()] = send.reshape(-1)
+        got = [torch.empty_like(self._bytes(buf)) for _ in range(self.world)] if self.rank == dst else None
+        dist.gather(self._bytes(buf).contiguous(), got, dst=dst)
+        if self.rank == dst:
+            flat = recv.reshape(-1)
+            for r in range(self.world):
+                n_r = int(sizes[r]) // es
+                blk = got[r]
+                blk = torch.view_as_complex(blk.reshape(-1, 2)) if send.is_complex() else blk
+                flat[int(offsets[r]) // es: int(offsets[r]) // es + n_r] = blk[:n_r]
+
+    def allgatherv_async(self, send, recv, sizes, offsets, after=None):
+        es = send.element_size()
+        k = max(int(v) for v in sizes) // es
+        buf = torch.zeros(k, dtype=send.dtype)
+        buf[: send.numel()] = send.reshape(-1)
+        got = [torch.empty_like(self._bytes(buf)) for _ in range(self.world)]
+        dist.all_gather(got, self._bytes(buf).contiguous())
+        flat = recv.reshape(-1)
+        for r in range(self.world):
+            n_r = int(sizes[r]) // es
+            blk = torch.view_as_complex(got[r].reshape(-1, 2)) if send.is_complex() else got[r]
+            flat[int(offsets[r]) // es: int(offsets[r]) // es + n_r] = blk[:n_r]
+
+    def allreduce_f64_async(self, buf, after=None):
+        t = self._bytes(buf)
+        dist.all_reduce(t)
+
+    def sendrecv_async(self, send, send_peer, recv, recv_peer, after=None):
+        ops = []
+        if send is not None and send_peer >= 0 and send.numel():
+            if send_peer == self.rank and recv_peer == self.rank:
+                recv.copy_(send)
+                return
+            ops.append(dist.isend(self._bytes(send).contiguous(), send_peer))
+        tmp = None
+        if recv is not None and recv_peer >= 0 and recv.numel():
+            tmp = torch.empty_like(self._bytes(recv))
+            ops.append(dist.irecv(tmp, recv_peer))
+        for o in ops:
+            o.wait()
+        if tmp is not None:
+            self._bytes(recv).copy_(tmp) if recv.is_contiguous() else recv.copy_(torch.view_as_complex(tmp.reshape(-1, 2)).reshape(recv.shape))
+
+    def join(self, stream):
+        pass
+
+    def sync(self):
+        pass
+
+
+class SingleCpiPlan:
+    """ONE large CPI split over the ranks (BASELINE config 5), clutter filter included.
+
+    Rank r owns a contiguous block of batches -- samples [s0, s0 + ns) of the CPI, the last rank also the
+    N - nDop nCorr samples the Ambiguity stage leaves over (the filter runs over all N).  Per CPI:
+      1. [filter] halo exchange with the two neighbours (b200dd_comm_sendrecv_async), per-chunk correlations,
+         all-reduce of the 2 nBins sums, replicated solve, per-chunk filter          (WienerHopf.cpp:58-163);
+      2. range correlation of the rank's batches into its rows of the range matrix    (Ambiguity.cpp:106-149);
+      3. all-gather of the range matrix (nDop x nDel complex64, <= 17 MB) -- the one exchange the CAF needs:
+         the Doppler transform runs ALONG the batch axis;
+      4. Doppler transform of the rank's tile of delay columns                         (Ambiguity.cpp:152-169);
+      5. gather of the tiles to rank `dst`, placed into the row-major map.
+    All buffers are allocated here, once; `run` only enqueues kernels and exchanges (`comm` is a blah2_b200.shard.Comm
+    on GPUs, a TorchComm in the CPU tests; `amb` / `whc_factory` are the process-layer classes or CPU stand-ins)."""
+
+    def __init__(self, comm, amb, n_samples: int, device, clutter=None, whc_factory=None, dst: int = 0):
+        self.comm, self.amb, self.dst = comm, amb, dst
+        rank, world = comm.rank, comm.world
+        g = amb.geometry
+        self.n_dop, self.n_del, self.n_corr = g.n_doppler_bins, g.n_delay_bins, g.n_corr
+        n_used = self.n_dop * self.n_corr
+        self.b0, self.nb = block_range(self.n_dop, rank, world)
+        self.s0 = self.b0 * self.n_corr
+        self.ns = self.nb * self.n_corr + (n_samples - n_used if rank == world - 1 else 0)
+        c64 = torch.complex64
+        self.R_full = torch.zeros((self.n_dop, self.n_del), dtype=c64, device=device)
+        self.R_local = self.R_full[self.b0:self.b0 + self.nb]          # the rank's rows, in place
+        self.row_sizes = [block_range(self.n_dop, r, world)[1] * self.n_del * 8 for r in range(world)]
+        self.row_offsets = [block_range(self.n_dop, r, world)[0] * self.n_del * 8 for r in range(world)]
+        self.c0, self.nc = block_range(self.n_del, rank, world)
+        self.tile = torch.zeros((self.n_dop, self.nc), dtype=c64, device=device)
+        cols = [block_range(self.n_del, r, world) for r in range(world)]
+        self.tile_sizes = [self.n_dop * c[1] * 8 for c in cols]
+        self.tile_offsets = [self.n_dop * c[0] * 8 for c in cols]
+        self.cols = cols
+        self.tiles_all = torch.zeros(self.n_dop * self.n_del, dtype=c64, device=device) if rank == dst else None
+        self.map = torch.zeros((self.n_dop, self.n_del), dtype=c64, device=device) if rank == dst else None
+        # clutter filter on the rank's chunk
+        self.whc = None
+        if clutter is not None:
+            self.whc = whc_factory(clutter[0], clutter[1], n_samples, self.s0, self.ns)
+            xl, xr, yr = self.whc.halos()
+            self.xl, self.xr, self.yr = xl, xr, yr
+            self.x_loc = torch.zeros(xl + self.ns + xr, dtype=c64, device=device)
+            self.y_loc = torch.zeros(self.ns + yr, dtype=c64, device=device)
+            self.ab = torch.zeros(2 * self.whc.nBins, dtype=torch.complex128, device=device)
+            self.y_f = torch.zeros(self.ns, dtype=c64, device=device)
+            self.x_own = self.x_loc[xl:xl + self.ns]     # the caller writes its samples HERE (no staging copy)
+            self.y_own = self.y_loc[:self.ns]
+        else:
+            self.x_own = torch.zeros(self.ns, dtype=c64, device=device)
+            self.y_own = torch.zeros(self.ns, dtype=c64, device=device)
+
+    def run(self, stream=None):
+        """Process the CPI whose samples are in x_own / y_own.  Returns the [nDop, nDel] map on `dst`, None elsewhere
+        (valid once `stream` has drained)."""
+        comm, rank, world = self.comm, self.comm.rank, self.comm.world
+        sp = stream.cuda_stream if hasattr(stream, "cuda_stream") else stream
+        x, y = self.x_own, self.y_own
+        if self.whc is not None:
+            nxt, prv = (rank + 1) % world, (rank - 1) % world
+            # right halos (circular: the correlations are circular over N): my first samples go to the previous rank
+            comm.sendrecv_async(self.x_own[:self.xr], prv, self.x_loc[self.xl + self.ns:], nxt, after=stream)
+            comm.sendrecv_async(self.y_own[:self.yr], prv, self.y_loc[self.ns:], nxt, after=None)
+            # left halo = filter history (not circular: zero before sample 0): my last samples go to the next rank
+            if self.xl:
+                comm.sendrecv_async(self.x_own[self.ns - self.xl:], nxt if rank + 1 < world else -1, self.x_loc[:self.xl],
+                                    prv if rank > 0 else -1, after=None)
+            comm.join(stream)
+            self.whc.corr_device(self.x_loc, self.y_loc, self.ab, sp)
+            comm.allreduce_f64_async(self.ab, after=stream)
+            comm.join(stream)
+            self.whc.filter_device(self.ab, self.x_loc, self.y_loc, self.y_f, sp)
+            y = self.y_f
+        n_own = self.nb * self.n_corr
+        self.amb.range_device(x[:n_own], y[:n_own], self.b0, self.nb, self.R_local, sp)
+        comm.allgatherv_async(self.R_local, self.R_full, self.row_sizes, self.row_offsets, after=stream)
+        comm.join(stream)
+        self.amb.doppler_device(self.R_full, self.c0, self.nc, self.tile, sp)
+        comm.gatherv_async(self.tile, self.tiles_all, self.tile_sizes, self.tile_offsets, self.dst, after=stream)
+        if rank != self.dst:
+            return None
+        comm.join(stream)
+        for r, (c0, nc) in enumerate(self.cols):   # tiles -> columns of the row-major map (strided device copies)
+            off = self.tile_offsets[r] // 8
+            self.amb.place_tile(self.tiles_all[off:off + self.n_dop * nc], c0, nc, self.map, sp)
+        return self.map

@@ -153,6 +153,10 @@ B200DD_API int b200dd_caf_range_device(b200dd_caf *h, const void *d_x, const voi
                                        uint32_t n_batches, void *d_R, void *stream);
 B200DD_API int b200dd_caf_doppler_device(b200dd_caf *h, const void *d_R, uint32_t col0, uint32_t n_cols,
                                          void *d_map_tile, void *stream);
+/* A tile [nDop][n_cols] (as b200dd_caf_doppler_device writes it, possibly gathered from another GPU) into the delay
+ * columns [col0, col0 + n_cols) of a row-major [nDop][nDel] map: one strided device copy. */
+B200DD_API int b200dd_caf_place_tile_device(b200dd_caf *h, const void *d_tile, uint32_t col0, uint32_t n_cols, void *d_map,
+                                            void *stream);
 
 /* Profiling aid: same as b200dd_caf_process_device but brackets the range-correlation kernel and the
  * Doppler kernel with CUDA events on the launching stream and returns their durations (ms).

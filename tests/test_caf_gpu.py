@@ -252,3 +252,33 @@ def test_tma_staged_range_kernel_is_bit_identical(geom, monkeypatch):
     assert np.abs(maps[("0", 0)]).max() > 0
     assert np.array_equal(maps[("0", 0)], maps[("1", 0)])
     assert np.array_equal(maps[("0", 0)], maps[("1", 1)])
+
+
+def test_single_cpi_plan_with_filter_on_one_gpu_matches_the_pipeline(relerr):
+    """blah2_b200.shard.SingleCpiPlan (config-5 orchestration: chunked clutter filter + stage-wise CAF over the C-ABI
+    communicator) at world size 1 must reproduce the ordinary whole-CPI path and the oracle."""
+    import torch
+    from blah2_b200.process import WienerHopfChunk
+    from blah2_b200.shard import Comm, SingleCpiPlan
+    from blah2_b200.scene import make_scene
+    geom = (-5, 60, -200, 200, 100000, 100000, True)
+    clutter = (-4, 40)
+    sc = make_scene(geom[5], geom[4], seed=21, n_clutter=8)
+    x = sc.x.astype(np.complex64)
+    y = sc.y.astype(np.complex64)
+    comm = Comm(0, 1, torch.cuda.current_device())
+    amb = Ambiguity(*geom)
+    plan = SingleCpiPlan(comm, amb, geom[5], torch.device("cuda"), clutter=clutter,
+                         whc_factory=lambda a, b, n, c0, nc: WienerHopfChunk(a, b, n, c0, nc))
+    plan.x_own.copy_(torch.from_numpy(x))
+    plan.y_own.copy_(torch.from_numpy(y))
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        m = plan.run(s)
+    s.synchronize()
+    assert plan.whc.last_status()
+    ok, yf = O.wienerhopf_process(x.astype(np.complex128), y.astype(np.complex128), *clutter)
+    ref, _, _ = O.ambiguity_process(x.astype(np.complex128), yf.astype(np.complex64).astype(np.complex128), O.ambiguity_geometry(*geom))
+    e = relerr(m.cpu().numpy().astype(np.complex128), ref)
+    assert ok and e[0] < TOL and e[1] < TOL, e
+    comm.close()

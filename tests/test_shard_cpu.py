@@ -122,3 +122,99 @@ def test_single_cpi_split_over_two_ranks_gloo():
     ref, _, _ = O.ambiguity_process(x.astype(np.complex64), y.astype(np.complex64), O.ambiguity_geometry(*_GEOM))
     assert out.shape == ref.shape
     assert np.max(np.abs(out - ref)) / np.max(np.abs(ref)) < 1e-5
+
+
+# ---- SingleCpiPlan (clutter filter + CAF of one CPI over the ranks) with CPU stand-ins for the CUDA stages ----------
+class _CpuChunkFilter:
+    """Same interface as blah2_b200.process.WienerHopfChunk, computed on CPU tensors from the DEFINITIONS
+    (WienerHopf.cpp:76-108 sums restricted to the chunk, :125-160 filter) -- test infrastructure only."""
+
+    def __init__(self, delayMin, delayMax, nSamples, c0, nc):
+        self.nBins = delayMax - delayMin
+        self.sh = -delayMin
+        self.c0, self.nc = c0, nc
+        self.xl, self.xr, self.yr = max(self.nBins - 1 - self.sh, 0), self.nBins - 1 + self.sh, self.nBins - 1
+
+    def halos(self):
+        return self.xl, self.xr, self.yr
+
+    def _xs(self, x_loc, i):           # xs[i] = x[i + sh], i a global index array
+        return x_loc[i + self.sh - (self.c0 - self.xl)]
+
+    def corr_device(self, x_loc, y_loc, ab, stream=None):
+        x, y = x_loc.numpy().astype(np.complex128), y_loc.numpy().astype(np.complex128)
+        n = np.arange(self.c0, self.c0 + self.nc)
+        a = np.array([np.sum(self._xs(x, n) * np.conj(self._xs(x, n + k))) for k in range(self.nBins)])
+        b = np.array([np.sum(y[n + k - self.c0] * np.conj(self._xs(x, n))) for k in range(self.nBins)])
+        ab.copy_(torch.from_numpy(np.concatenate([a, b])))
+
+    def filter_device(self, ab, x_loc, y_loc, y_out, stream=None):
+        import scipy.linalg as sla
+        v = ab.numpy()
+        a, b = v[:self.nBins], v[self.nBins:]
+        # A(i,j) = a[j-i] (j >= i), conj(a[i-j]) (i > j)   (WienerHopf.cpp:85-97)
+        A = sla.toeplitz(np.conj(a), a)
+        w = np.linalg.solve(A, b)
+        x, y = x_loc.numpy().astype(np.complex128), y_loc.numpy().astype(np.complex128)
+        out = np.empty(self.nc, dtype=np.complex128)
+        for j in range(self.nc):
+            i = self.c0 + j
+            k = np.arange(0, min(self.nBins, i + 1))
+            out[j] = y[j] - np.sum(w[k] * self._xs(x, i - k))
+        y_out.copy_(torch.from_numpy(out.astype(np.complex64)))
+
+
+class _CpuAmbiguityPlus(_CpuAmbiguity):
+    def place_tile(self, tile, c0, nc, m, stream=None):
+        m[:, c0:c0 + nc] = tile.reshape(m.shape[0], nc)
+
+
+_GEOM2 = (-3, 20, -50, 50, 10000, 4000, True)
+_CLUT2 = (-2, 9)
+
+
+def _worker_plan(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from blah2_b200.scene import make_scene
+        from blah2_b200.shard import SingleCpiPlan, TorchComm
+        amb = _CpuAmbiguityPlus(_GEOM2)
+        sc = make_scene(_GEOM2[5], _GEOM2[4], seed=5, n_clutter=6)
+        plan = SingleCpiPlan(TorchComm(rank, world), amb, _GEOM2[5], "cpu", clutter=_CLUT2, whc_factory=_CpuChunkFilter)
+        plan.x_own.copy_(torch.from_numpy(sc.x[plan.s0:plan.s0 + plan.ns].astype(np.complex64)))   # each rank holds only its slice
+        plan.y_own.copy_(torch.from_numpy(sc.y[plan.s0:plan.s0 + plan.ns].astype(np.complex64)))
+        m = plan.run(None)
+        if rank == 0:
+            q.put(m.numpy().copy())
+        else:
+            assert m is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_single_cpi_plan_with_clutter_filter_gloo(world):
+    """Halo exchange (circular right halos, one-sided left halo), all-reduce of the partial correlations, replicated
+    solve, per-chunk filter, range stage on the rank's batches, all-gather, column tiles, gather + placement: the map
+    on rank 0 equals the oracle's WienerHopf + Ambiguity on the whole CPI."""
+    from blah2_b200.scene import make_scene
+    from oracle import blah2_oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker_plan, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    sc = make_scene(_GEOM2[5], _GEOM2[4], seed=5, n_clutter=6)
+    x, y = sc.x.astype(np.complex64).astype(np.complex128), sc.y.astype(np.complex64).astype(np.complex128)
+    ok, yf = O.wienerhopf_process(x, y, *_CLUT2)
+    assert ok
+    ref, _, _ = O.ambiguity_process(x, yf.astype(np.complex64), O.ambiguity_geometry(*_GEOM2))
+    assert out.shape == ref.shape
+    assert np.max(np.abs(out - ref)) / np.max(np.abs(ref)) < 1e-4   # complex64 hand-offs of y' between the stages
