@@ -356,14 +356,19 @@ def main():
     if comm is not None and rank == 0:
         recv_ring = torch.empty((NPIPE, world, g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda")
 
+    sent = [None] * NPIPE   # event on the communicator's stream: "the gather that read dmaps[p] has finished"
+
     def submit(i, gather=True):
         p = i % NPIPE
         with torch.cuda.stream(streams[p]):
-            if comm is not None and gather:
-                comm.join(streams[p])  # the gather of this pipeline's previous map has read dmaps[p]
+            if sent[p] is not None:
+                streams[p].wait_event(sent[p])  # only THIS pipeline's previous gather: the other pipelines keep running
             pipes[p].submit_device(xs[i % NB], ys[i % NB], dmaps[p], streams[p].cuda_stream)
             if comm is not None and gather:  # NCCL send/recv on the communicator's stream, behind this CPI's kernels only
                 comm.gather_async(dmaps[p], recv_ring[p] if rank == 0 else None, 0, after=streams[p])
+                if sent[p] is None:
+                    sent[p] = torch.cuda.Event()
+                sent[p].record(comm.torch_stream())
 
     # ---- device-resident throughput: a stream of independent CPIs, NPIPE in flight ----
     # Plan creation (untimed, before the warm-up steps): the CUDA graph of the chain for every (input set, pipeline)

@@ -166,6 +166,8 @@ SIGNATURES = [
     ("b200dd_comm_sync", C.c_int, [_VP]),
     ("b200dd_ubench_fp64_tflops", C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
     ("b200dd_bind_host_to_device", C.c_int, [C.c_int32, C.c_char_p, C.c_int32]),
+    ("b200dd_host_alloc", _VP, [C.c_size_t]),
+    ("b200dd_host_free", None, [_VP]),
 ]
 
 _lib = None

@@ -50,3 +50,17 @@ extern "C" int b200dd_bind_host_to_device(int32_t device, char *cpulist_out, int
   if (sched_setaffinity(0, sizeof(want), &want) != 0) { set_last_error("b200dd_bind_host_to_device: sched_setaffinity failed"); return B200DD_ERR_ARG; }
   return B200DD_OK;
 }
+
+// Pinned (page-locked) host memory for the drop-in classes' staging buffers: a pageable std::vector crosses PCIe at a
+// third of the pinned rate.  Plain malloc/free semantics; NULL on failure.
+extern "C" void *b200dd_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void b200dd_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}

@@ -7,6 +7,7 @@
 #define B200DD_DROPIN_AMBIGUITY_H
 
 #include "data/IqData.h"
+#include "process/PinnedBuffer.h"
 #include "data/Map.h"
 #include "process/meta/HammingNumber.h"
 
@@ -47,7 +48,7 @@ private:
   uint16_t nDelayBins, nDopplerBins, nCorr;
   uint32_t nfft, nUsed;
   double dopplerMiddle, cpi;
-  std::vector<Complex> hostX, hostY, hostMap;
+  PinnedBuffer hostX, hostY, hostMap;
   std::unique_ptr<Map<Complex>> map;
 };
 

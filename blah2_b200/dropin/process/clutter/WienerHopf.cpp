@@ -2,6 +2,7 @@
 
 #include "b200dd.h"
 
+#include <algorithm>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -28,11 +29,9 @@ bool WienerHopf::process(IqData *x, IqData *y)
     const std::deque<std::complex<double>> yd = y->get_data();
     if (xd.size() < nSamples || yd.size() < nSamples)
       throw std::runtime_error("WienerHopf::process: fewer than nSamples queued");
-    for (uint32_t i = 0; i < nSamples; i++)
-    {
-      hostX[i] = xd[i];
-      hostY[i] = yd[i];
-    }
+    // sequential deque iteration (operator[] on a deque recomputes the block address for every element)
+    std::copy(xd.begin(), xd.begin() + nSamples, hostX.data());
+    std::copy(yd.begin(), yd.begin() + nSamples, hostY.data());
   }
   const int rc = b200dd_wh_process_host(handle, reinterpret_cast<const double *>(hostX.data()),
                                         reinterpret_cast<double *>(hostY.data()));

@@ -4,6 +4,7 @@
 #define B200DD_DROPIN_WIENERHOPF_H
 
 #include "data/IqData.h"
+#include "process/PinnedBuffer.h"
 
 #include <stdint.h>
 #include <complex>
@@ -25,7 +26,7 @@ public:
 private:
   b200dd_wh *handle;
   uint32_t nSamples;
-  std::vector<std::complex<double>> hostX, hostY;
+  PinnedBuffer hostX, hostY;
 };
 
 #endif

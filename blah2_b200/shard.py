@@ -80,6 +80,13 @@ class Comm:
         """`stream` waits for everything enqueued on the communicator so far."""
         self._capi.check(self._lib.b200dd_comm_join(self._h, self._sp(stream)))
 
+    def torch_stream(self):
+        """The communicator's CUDA stream as a torch stream (to record / wait on events for finer-grained ordering
+        than join(): e.g. 'the gather that read THIS buffer has finished')."""
+        if getattr(self, "_ts", None) is None:
+            self._ts = torch.cuda.ExternalStream(int(self._lib.b200dd_comm_stream(self._h)))
+        return self._ts
+
     def sync(self):
         self._capi.check(self._lib.b200dd_comm_sync(self._h))
 
@@ -318,11 +325,19 @@ class SingleCpiPlan:
             self.x_own = torch.zeros(self.ns, dtype=c64, device=device)
             self.y_own = torch.zeros(self.ns, dtype=c64, device=device)
 
-    def run(self, stream=None):
+    def run(self, stream=None, marks=None):
         """Process the CPI whose samples are in x_own / y_own.  Returns the [nDop, nDel] map on `dst`, None elsewhere
-        (valid once `stream` has drained)."""
+        (valid once `stream` has drained).  `marks` (a list) receives (label, event) pairs recorded on `stream`
+        after each stage, for the per-stage timing of tools/bench_cfg5.py."""
         comm, rank, world = self.comm, self.comm.rank, self.comm.world
         sp = stream.cuda_stream if hasattr(stream, "cuda_stream") else stream
+
+        def mark(label):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                marks.append((label, e))
+        mark("start")
         x, y = self.x_own, self.y_own
         if self.whc is not None:
             nxt, prv = (rank + 1) % world, (rank - 1) % world
@@ -334,21 +349,30 @@ class SingleCpiPlan:
                 comm.sendrecv_async(self.x_own[self.ns - self.xl:], nxt if rank + 1 < world else -1, self.x_loc[:self.xl],
                                     prv if rank > 0 else -1, after=None)
             comm.join(stream)
+            mark("halo")
             self.whc.corr_device(self.x_loc, self.y_loc, self.ab, sp)
+            mark("wh_corr")
             comm.allreduce_f64_async(self.ab, after=stream)
             comm.join(stream)
+            mark("allreduce")
             self.whc.filter_device(self.ab, self.x_loc, self.y_loc, self.y_f, sp)
+            mark("wh_solve_filter")
             y = self.y_f
         n_own = self.nb * self.n_corr
         self.amb.range_device(x[:n_own], y[:n_own], self.b0, self.nb, self.R_local, sp)
+        mark("range")
         comm.allgatherv_async(self.R_local, self.R_full, self.row_sizes, self.row_offsets, after=stream)
         comm.join(stream)
+        mark("allgather_R")
         self.amb.doppler_device(self.R_full, self.c0, self.nc, self.tile, sp)
+        mark("doppler")
         comm.gatherv_async(self.tile, self.tiles_all, self.tile_sizes, self.tile_offsets, self.dst, after=stream)
         if rank != self.dst:
             return None
         comm.join(stream)
+        mark("gather_tiles")
         for r, (c0, nc) in enumerate(self.cols):   # tiles -> columns of the row-major map (strided device copies)
             off = self.tile_offsets[r] // 8
             self.amb.place_tile(self.tiles_all[off:off + self.n_dop * nc], c0, nc, self.map, sp)
+        mark("place_tiles")
         return self.map

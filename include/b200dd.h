@@ -477,6 +477,10 @@ B200DD_API int b200dd_ubench_fp64_tflops(int32_t device, double *tflops);
  * GPU's NUMA node.  cpulist_out (nullable, `cap` bytes) receives the kernel's list, e.g. "0-31,64-95". */
 B200DD_API int b200dd_bind_host_to_device(int32_t device, char *cpulist_out, int32_t cap);
 
+/* Pinned host memory for staging buffers (malloc / free semantics, NULL on failure). */
+B200DD_API void *b200dd_host_alloc(size_t bytes);
+B200DD_API void b200dd_host_free(void *p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,13 @@ def main():
     ms = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # per-stage times of one more CPI (rank 0's stream; exchanges include waiting for the slowest rank)
+    marks = []
+    with torch.cuda.stream(s):
+        plan.run(s, marks)
+    comm.sync()
+    torch.cuda.synchronize()
+    stages = {marks[i][0]: round(marks[i - 1][1].elapsed_time(marks[i][1]), 4) for i in range(1, len(marks))}
     ok = plan.whc.last_status() if plan.whc is not None else True
     if rank == 0:
         byts = (2 * 16 * geom[5] if use_filter else 0) + 16 * g.n_used + 8 * g.n_doppler_bins * g.n_delay_bins
@@ -64,7 +71,7 @@ def main():
                           "msamples_per_s": round(geom[5] / float(ms) / 1e3, 1),
                           "algorithmic_GBps_aggregate": round(byts / float(ms) / 1e6, 1), "filter_ok": bool(ok),
                           "range_fft": g.range_fft_len, "segments": g.range_segments, "doppler_fft": g.doppler_fft_len,
-                          "map_finite": bool(torch.isfinite(torch.view_as_real(m)).all()), "map_absmax": float(m.abs().max())}), flush=True)
+                          "stage_ms_rank0": stages, "map_finite": bool(torch.isfinite(torch.view_as_real(m)).all()), "map_absmax": float(m.abs().max())}), flush=True)
     comm.close()
     if world > 1:
         dist.destroy_process_group()
