@@ -232,6 +232,9 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_corr_kernel(CorrA
     r15 = direct(d, 0, a.nBegin + (uint32_t)s0 * (uint32_t)a.L, tid + 15 * NT);
   }
   double2 vxp[16];
+  double2 za[16];  // a-spectrum accumulator: registers (the b-spectrum's lives in shared memory)
+#pragma unroll
+  for (int q = 0; q < 16; q++) za[q] = zero;
   for (int s = s0; s < s1; s++) {
     const uint32_t n0 = a.nBegin + (uint32_t)s * (uint32_t)a.L;
     // NOT unrolled: three (five with the inverses) copies of the transform overflow the instruction cache
@@ -277,13 +280,15 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_corr_kernel(CorrA
       if (t == 0) {
 #pragma unroll
         for (int q = 0; q < 16; q++) vxp[q] = v[q];
-      } else {
-        double2 *Z = t == 1 ? Za : Zb;  // a-spectrum += W conj(P), b-spectrum += V conj(P)
+      } else if (t == 1) {  // a-spectrum += W conj(P)
+#pragma unroll
+        for (int q = 0; q < 16; q++) cfmac(za[q], v[brev<16>(q)], vxp[brev<16>(q)]);
+      } else {              // b-spectrum += V conj(P)
 #pragma unroll
         for (int q = 0; q < 16; q++) {
-          double2 acc = Z[q * NT + tid];
+          double2 acc = Zb[q * NT + tid];
           cfmac(acc, v[brev<16>(q)], vxp[brev<16>(q)]);
-          Z[q * NT + tid] = acc;
+          Zb[q * NT + tid] = acc;
         }
       }
       __syncthreads();
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_corr_kernel(CorrA
     const double sgn = c == 0 ? -scale : scale;
     double2 z[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) z[q] = Z[q * NT + tid];
+    for (int q = 0; q < 16; q++) z[q] = c == 0 ? za[q] : Z[q * NT + tid];
     dit_transform<LOG2M, +1>(A, tw, tid, z);
 #pragma unroll
     for (int q = 0; q < 16; q++) {
