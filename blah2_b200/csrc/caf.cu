@@ -694,6 +694,82 @@ __global__ void __launch_bounds__(Plan<LOG2M>::NT) caf_doppler_kernel(DopplerArg
   }
 }
 
+// ---- second-generation Doppler kernel (fft_dit.cuh): same Bluestein evaluation, M2 = 512 .. 4096 -----------------
+// Thread tid owns the slow-time samples i = tid + NT k (its 16 column-strided loads and 16 chirp values are all
+// requested before anything is consumed), the forward spectrum stays in registers, is multiplied by the filter
+// spectrum stored in the same thread order (bhat[q NT + tid] = B^[tid + NT q], coalesced) and goes straight into the
+// inverse transform; output sample m = tid + NT q is written with the fftshift folded into the row index.
+template <int LOG2M>
+__global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT) caf_doppler_dit_kernel(DopplerArgs a) {
+  using P = dit::Plan3<LOG2M>;
+  constexpr int NT = P::NT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2 *A = reinterpret_cast<float2 *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int col = a.col0 + blockIdx.x;
+  const float2 zero = make_float2(0.f, 0.f);
+  const size_t plane = (size_t)a.nDop * a.nDel;
+  TwPairF tw;
+  tw.t1 = dit::pass1_twiddle<float, LOG2M>(a.tw, tid);
+  tw.t2 = dit::pass2_twiddle<float, LOG2M>(a.tw, tid);
+  float2 v[16], ch[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const int ic = min(tid + NT * k, a.nDop - 1);  // unconditional loads on a valid row, masked below
+    v[k] = __ldg(a.R + (size_t)ic * a.nDel + col);
+    ch[k] = __ldg(a.chirp + ic);
+  }
+  for (int q = 1; q < a.nParts; q++) {  // fixed order: deterministic
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const int ic = min(tid + NT * k, a.nDop - 1);
+      v[k] = cadd(v[k], __ldg(a.R + q * plane + (size_t)ic * a.nDel + col));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 16; k++) v[k] = tid + NT * k < a.nDop ? cmul(v[k], ch[k]) : zero;
+  dit_transform_f32<LOG2M, -1>(A, tw, tid, v, [] {});
+  float2 z[16];
+#pragma unroll
+  for (int q = 0; q < 16; q++) z[q] = cmul(v[brev<16>(q)], __ldg(a.bhat + q * NT + tid));
+  // the chirp values of the outputs this thread will write, requested before the inverse transform
+#pragma unroll
+  for (int q = 0; q < 16; q++) ch[q] = __ldg(a.chirp + min(tid + NT * q, a.nDop - 1));
+  __syncthreads();
+  dit_transform_f32<LOG2M, +1>(A, tw, tid, z, [] {});
+  const float scale = 1.0f / (float)P::M;
+  const int shift = a.nDop / 2 + 1;
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    const int m = tid + NT * q;
+    if (m < a.nDop) {
+      const float2 d = cmul(z[brev<16>(q)], ch[q]);
+      int k = m - shift;
+      if (k < 0) k += a.nDop;
+      a.out[(size_t)k * a.ldOut + blockIdx.x] = make_float2(d.x * scale, d.y * scale);
+    }
+  }
+}
+
+// natural-order input -> spectrum in the thread order of the DIT kernels: out[q NT + tid] = X[tid + NT q]
+template <int LOG2M>
+__global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT) fft_forward_dit_kernel(const float2 *in, float2 *out, const float2 *tw) {
+  using P = dit::Plan3<LOG2M>;
+  constexpr int NT = P::NT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2 *A = reinterpret_cast<float2 *>(smem_raw);
+  const int tid = threadIdx.x;
+  TwPairF t;
+  t.t1 = dit::pass1_twiddle<float, LOG2M>(tw, tid);
+  t.t2 = dit::pass2_twiddle<float, LOG2M>(tw, tid);
+  float2 v[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) v[k] = in[tid + NT * k];
+  dit_transform_f32<LOG2M, -1>(A, t, tid, v, [] {});
+#pragma unroll
+  for (int q = 0; q < 16; q++) out[q * NT + tid] = v[brev<16>(q)];
+}
+
 // rows [row0, row0 + nRows) of the range matrix = fixed-order sum of the parts (sharded single-CPI mode)
 __global__ void caf_sum_parts_kernel(const float2 *__restrict__ parts, int nParts, size_t plane, size_t first, size_t count,
                                      float2 *__restrict__ out) {
@@ -855,6 +931,22 @@ template <int LOG2M> int launch_doppler(const DopplerArgs &a, cudaStream_t st) {
   return B200DD_OK;
 }
 
+template <int LOG2M> int launch_doppler_dit(const DopplerArgs &a, cudaStream_t st) {
+  using P = dit::Plan3<LOG2M>;
+  caf_doppler_dit_kernel<LOG2M><<<a.nCols, P::NT, (size_t)P::MP * sizeof(float2), st>>>(a);
+  B2_LAUNCH_CHECK();
+  return B200DD_OK;
+}
+template <int LOG2M> int launch_fft_forward_dit(const float2 *in, float2 *out, const float2 *tw, cudaStream_t st) {
+  using P = dit::Plan3<LOG2M>;
+  const size_t smem = (size_t)P::MP * sizeof(float2);
+  B2_CUDA(cudaFuncSetAttribute(fft_forward_dit_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2_CUDA(cudaFuncSetAttribute(caf_doppler_dit_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fft_forward_dit_kernel<LOG2M><<<1, P::NT, smem, st>>>(in, out, tw);
+  B2_LAUNCH_CHECK();
+  return B200DD_OK;
+}
+
 template <int LOG2M> int launch_fft_forward(const float2 *in, float2 *out, const float2 *tw, cudaStream_t st) {
   using P = Plan<LOG2M>;
   const size_t smem = (size_t)P::MP * sizeof(float2);
@@ -908,6 +1000,25 @@ int dispatch_doppler(int log2m, const DopplerArgs &a, cudaStream_t st) {
   return geom_fail("Doppler FFT length out of range");
 }
 
+int dispatch_doppler_dit(int log2m, const DopplerArgs &a, cudaStream_t st) {
+  switch (log2m) {
+    case 9: return launch_doppler_dit<9>(a, st);
+    case 10: return launch_doppler_dit<10>(a, st);
+    case 11: return launch_doppler_dit<11>(a, st);
+    case 12: return launch_doppler_dit<12>(a, st);
+  }
+  return geom_fail("Doppler FFT length out of range");
+}
+int dispatch_fft_forward_dit(int log2m, const float2 *in, float2 *out, const float2 *tw, cudaStream_t st) {
+  switch (log2m) {
+    case 9: return launch_fft_forward_dit<9>(in, out, tw, st);
+    case 10: return launch_fft_forward_dit<10>(in, out, tw, st);
+    case 11: return launch_fft_forward_dit<11>(in, out, tw, st);
+    case 12: return launch_fft_forward_dit<12>(in, out, tw, st);
+  }
+  return geom_fail("FFT length out of range");
+}
+
 int dispatch_fft_forward(int log2m, const float2 *in, float2 *out, const float2 *tw, cudaStream_t st) {
   switch (log2m) {
     case 8: return launch_fft_forward<8>(in, out, tw, st);
@@ -942,6 +1053,7 @@ struct b200dd_caf {
   cudaStream_t stream = nullptr;
   // range stage plan
   int log2m = 12, nSeg = 1, L = 0, nParts = 1, segPerPart = 1, nGroups = 1;
+  bool dit_doppler = false;  // second-generation Doppler kernel: Bluestein lengths 512 .. 4096
   bool dit_range = false;  // second-generation range kernel (fft_dit.cuh + TMA staging): FFT lengths 512 .. 4096
   int num_sms = 148;
   // doppler stage plan
@@ -1044,7 +1156,12 @@ int caf_setup_device(b200dd_caf *h) {
   B2_CUDA(cudaMalloc(&d_bw, sizeof(float2) * M2));
   B2_CUDA(cudaMalloc(&h->d_bhat, sizeof(float2) * M2));
   B2_CUDA(cudaMemcpy(d_bw, bw.data(), sizeof(float2) * M2, cudaMemcpyHostToDevice));
-  int rc = dispatch_fft_forward(h->log2m2, d_bw, h->d_bhat, h->d_tw2, h->stream);
+  {
+    const char *kenv = getenv("B200DD_CAF_KERNEL");
+    h->dit_doppler = !(kenv && strcmp(kenv, "legacy") == 0) && h->log2m2 >= 9 && h->log2m2 <= 12;
+  }
+  int rc = h->dit_doppler ? dispatch_fft_forward_dit(h->log2m2, d_bw, h->d_bhat, h->d_tw2, h->stream)
+                          : dispatch_fft_forward(h->log2m2, d_bw, h->d_bhat, h->d_tw2, h->stream);
   if (rc != B200DD_OK) { cudaFree(d_bw); return rc; }
   B2_CUDA(cudaStreamSynchronize(h->stream));
   cudaFree(d_bw);
@@ -1092,7 +1209,7 @@ int caf_run_device(b200dd_caf *h, const float2 *d_x, const float2 *d_y, float2 *
   da.col0 = 0;
   da.nCols = (int)g.nDel;
   da.ldOut = (int)g.nDel;
-  rc = dispatch_doppler(h->log2m2, da, st);
+  rc = h->dit_doppler ? dispatch_doppler_dit(h->log2m2, da, st) : dispatch_doppler(h->log2m2, da, st);
   if (rc != B200DD_OK) return rc;
   if (ev) B2_CUDA(cudaEventRecord(ev[2], st));
   return B200DD_OK;
@@ -1328,7 +1445,7 @@ int b200dd_caf_doppler_device(b200dd_caf *h, const void *d_R, uint32_t col0, uin
   da.R = (const float2 *)d_R; da.nParts = 1; da.out = (float2 *)d_map_tile; da.chirp = h->d_chirp; da.bhat = h->d_bhat;
   da.tw = h->d_tw2; da.nDop = (int)g.nDop; da.nDel = (int)g.nDel; da.col0 = (int)col0; da.nCols = (int)n_cols;
   da.ldOut = (int)n_cols;
-  return dispatch_doppler(h->log2m2, da, st);
+  return h->dit_doppler ? dispatch_doppler_dit(h->log2m2, da, st) : dispatch_doppler(h->log2m2, da, st);
 }
 
 int b200dd_caf_place_tile_device(b200dd_caf *h, const void *d_tile, uint32_t col0, uint32_t n_cols, void *d_map, void *stream) {
