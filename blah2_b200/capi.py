@@ -90,6 +90,7 @@ SIGNATURES = [
     ("b200dd_caf_range_device", C.c_int, [_VP, _VP, _VP, C.c_uint32, C.c_uint32, _VP, _VP]),
     ("b200dd_caf_doppler_device", C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, _VP, _VP]),
     ("b200dd_caf_place_tile_device", C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, _VP, _VP]),
+    ("b200dd_caf_place_tiles_device", C.c_int, [_VP, _VP, C.c_uint32, _VP, _VP]),
     ("b200dd_caf_profile_device", C.c_int, [_VP, _VP, _VP, C.c_uint32, _VP, _VP, C.POINTER(C.c_float),
                                             C.POINTER(C.c_float)]),
     ("b200dd_caf_debug_range_matrix", C.c_int, [_VP, _VP]),

@@ -770,6 +770,20 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT) fft_forward_dit_kernel(
   for (int q = 0; q < 16; q++) out[q * NT + tid] = v[brev<16>(q)];
 }
 
+// gathered column tiles -> row-major map, all tiles in one launch.  tiles = tile 0 | tile 1 | ... (tile t =
+// [nDop][nc_t], contiguous); tile t covers the delay columns [col0_t, col0_t + nc_t).  Reads and writes are
+// contiguous runs of nc_t elements.
+__global__ void caf_place_tiles_kernel(const float2 *__restrict__ tiles, int nTiles, int nDop, int nDel, float2 *__restrict__ map) {
+  // equal split of nDel columns over nTiles (block_range of the orchestration): sizes differ by at most one
+  const int base = nDel / nTiles, rem = nDel % nTiles;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)nDop * nDel; i += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / nDel), col = (int)(i % nDel);
+    int t = col < rem * (base + 1) ? col / (base + 1) : rem + (col - rem * (base + 1)) / base;
+    const int c0 = t * base + min(t, rem), nc = base + (t < rem ? 1 : 0);
+    map[i] = tiles[(size_t)nDop * c0 + (size_t)row * nc + (col - c0)];
+  }
+}
+
 // rows [row0, row0 + nRows) of the range matrix = fixed-order sum of the parts (sharded single-CPI mode)
 __global__ void caf_sum_parts_kernel(const float2 *__restrict__ parts, int nParts, size_t plane, size_t first, size_t count,
                                      float2 *__restrict__ out) {
@@ -1456,6 +1470,18 @@ int b200dd_caf_place_tile_device(b200dd_caf *h, const void *d_tile, uint32_t col
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   B2_CUDA(cudaMemcpy2DAsync((float2 *)d_map + col0, sizeof(float2) * g.nDel, d_tile, sizeof(float2) * n_cols, sizeof(float2) * n_cols,
                             g.nDop, cudaMemcpyDeviceToDevice, st));
+  return B200DD_OK;
+}
+
+int b200dd_caf_place_tiles_device(b200dd_caf *h, const void *d_tiles, uint32_t n_tiles, void *d_map, void *stream) {
+  if (!h || !d_tiles || !d_map) return arg_fail("b200dd_caf_place_tiles_device: null argument");
+  const HostGeom &g = h->g;
+  if (n_tiles == 0 || n_tiles > g.nDel) return arg_fail("b200dd_caf_place_tiles_device: bad tile count");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  caf_place_tiles_kernel<<<grid_for(g.nDop * g.nDel), 256, 0, st>>>((const float2 *)d_tiles, (int)n_tiles, (int)g.nDop, (int)g.nDel,
+                                                                     (float2 *)d_map);
+  B2_LAUNCH_CHECK();
   return B200DD_OK;
 }
 

@@ -130,6 +130,11 @@ class Ambiguity:
         capi.check(self._lib.b200dd_caf_place_tile_device(self._h, capi.ptr(d_tile), int(col0), int(n_cols), capi.ptr(d_map),
                                                           capi.ptr(stream) if stream else None))
 
+    def place_tiles(self, d_tiles, n_tiles, d_map, stream=None):
+        """All gathered tiles of an equal column split (shard.block_range) -> the row-major map, one kernel."""
+        capi.check(self._lib.b200dd_caf_place_tiles_device(self._h, capi.ptr(d_tiles), int(n_tiles), capi.ptr(d_map),
+                                                           capi.ptr(stream) if stream else None))
+
     def profile_device(self, d_x, d_y, d_map=None, stream=None):
         """(ms_range, ms_doppler): CUDA-event durations of the two CAF kernels for one CPI."""
         a, b = C.c_float(), C.c_float()

@@ -371,8 +371,11 @@ class SingleCpiPlan:
             return None
         comm.join(stream)
         mark("gather_tiles")
-        for r, (c0, nc) in enumerate(self.cols):   # tiles -> columns of the row-major map (strided device copies)
-            off = self.tile_offsets[r] // 8
-            self.amb.place_tile(self.tiles_all[off:off + self.n_dop * nc], c0, nc, self.map, sp)
+        if hasattr(self.amb, "place_tiles"):       # tiles -> columns of the row-major map: one kernel
+            self.amb.place_tiles(self.tiles_all, world, self.map, sp)
+        else:
+            for r, (c0, nc) in enumerate(self.cols):
+                off = self.tile_offsets[r] // 8
+                self.amb.place_tile(self.tiles_all[off:off + self.n_dop * nc], c0, nc, self.map, sp)
         mark("place_tiles")
         return self.map

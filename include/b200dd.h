@@ -157,6 +157,10 @@ B200DD_API int b200dd_caf_doppler_device(b200dd_caf *h, const void *d_R, uint32_
  * columns [col0, col0 + n_cols) of a row-major [nDop][nDel] map: one strided device copy. */
 B200DD_API int b200dd_caf_place_tile_device(b200dd_caf *h, const void *d_tile, uint32_t col0, uint32_t n_cols, void *d_map,
                                             void *stream);
+/* All tiles of an EQUAL split of the delay columns over n_tiles ranks (tile t = columns [t b + min(t, r), ...) with
+ * b = nDel / n_tiles, r = nDel % n_tiles: the first r tiles one column wider), stored back to back in d_tiles as the
+ * gather delivers them, into the row-major map: one kernel. */
+B200DD_API int b200dd_caf_place_tiles_device(b200dd_caf *h, const void *d_tiles, uint32_t n_tiles, void *d_map, void *stream);
 
 /* Profiling aid: same as b200dd_caf_process_device but brackets the range-correlation kernel and the
  * Doppler kernel with CUDA events on the launching stream and returns their durations (ms).
