@@ -282,3 +282,30 @@ def test_single_cpi_plan_with_filter_on_one_gpu_matches_the_pipeline(relerr):
     e = relerr(m.cpu().numpy().astype(np.complex128), ref)
     assert ok and e[0] < TOL and e[1] < TOL, e
     comm.close()
+
+
+@pytest.mark.parametrize("n_tiles", [1, 2, 3, 8])
+def test_tile_placement_kernel_rebuilds_the_map(n_tiles):
+    """b200dd_caf_place_tiles_device: the gathered delay-column tiles of an equal split (shard.block_range), stored back
+    to back, become the row-major map in one kernel; b200dd_caf_place_tile_device does the same tile by tile."""
+    import torch
+    from blah2_b200.shard import block_range
+    amb = Ambiguity(-5, 60, -200, 200, 100000, 100000, True)
+    g = amb.geometry
+    ref = torch.randn((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda")
+    cols = [block_range(g.n_delay_bins, r, n_tiles) for r in range(n_tiles)]
+    tiles = torch.cat([ref[:, c0:c0 + nc].contiguous().reshape(-1) for c0, nc in cols])
+    out = torch.zeros_like(ref)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        amb.place_tiles(tiles, n_tiles, out, s.cuda_stream)
+    s.synchronize()
+    assert torch.equal(out, ref)
+    out2 = torch.zeros_like(ref)
+    off = 0
+    with torch.cuda.stream(s):
+        for c0, nc in cols:
+            amb.place_tile(tiles[off:off + g.n_doppler_bins * nc], c0, nc, out2, s.cuda_stream)
+            off += g.n_doppler_bins * nc
+    s.synchronize()
+    assert torch.equal(out2, ref)
