@@ -163,6 +163,7 @@ SIGNATURES = [
     ("b200dd_comm_allgatherv_async", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     ("b200dd_comm_allreduce_f64_async", C.c_int, [_VP, _VP, C.c_size_t, _VP]),
     ("b200dd_comm_sendrecv_async", C.c_int, [_VP, _VP, C.c_size_t, C.c_int32, _VP, C.c_size_t, C.c_int32, _VP]),
+    ("b200dd_comm_wait_stream", C.c_int, [_VP, _VP]),
     ("b200dd_comm_join", C.c_int, [_VP, _VP]),
     ("b200dd_comm_sync", C.c_int, [_VP]),
     ("b200dd_ubench_fp64_tflops", C.c_int, [C.c_int32, C.POINTER(C.c_double)]),

@@ -285,6 +285,12 @@ int b200dd_comm_sendrecv_async(b200dd_comm *c, const void *d_send, size_t send_b
   return B200DD_OK;
 }
 
+int b200dd_comm_wait_stream(b200dd_comm *c, void *stream) {
+  if (!c || !stream) return arg_fail("b200dd_comm_wait_stream: null argument");
+  DeviceGuard guard(c->device);
+  return comm_after(c, stream);
+}
+
 int b200dd_comm_join(b200dd_comm *c, void *stream) {
   if (!c || !stream) return arg_fail("b200dd_comm_join: null argument");
   DeviceGuard guard(c->device);

@@ -76,6 +76,10 @@ class Comm:
                                                               self._capi.ptr(recv) if rb else None, rb, int(recv_peer),
                                                               self._sp(after)))
 
+    def wait_stream(self, stream):
+        """The communicator's stream waits for everything enqueued so far on `stream`."""
+        self._capi.check(self._lib.b200dd_comm_wait_stream(self._h, self._sp(stream)))
+
     def join(self, stream):
         """`stream` waits for everything enqueued on the communicator so far."""
         self._capi.check(self._lib.b200dd_comm_join(self._h, self._sp(stream)))

@@ -469,6 +469,9 @@ B200DD_API int b200dd_comm_allreduce_f64_async(b200dd_comm *c, void *d_buf, size
  * the peers' calls must pair up (rank a sends to b <=> rank b receives from a, same size) */
 B200DD_API int b200dd_comm_sendrecv_async(b200dd_comm *c, const void *d_send, size_t send_bytes, int32_t send_peer,
                                           void *d_recv, size_t recv_bytes, int32_t recv_peer, void *after);
+/* the communicator's stream waits for everything enqueued so far on `stream` (what `after` does inside the *_async
+ * calls; call it once per compute stream when an exchange depends on several of them, then pass after = NULL) */
+B200DD_API int b200dd_comm_wait_stream(b200dd_comm *c, void *stream);
 B200DD_API int b200dd_comm_join(b200dd_comm *c, void *stream);
 B200DD_API int b200dd_comm_sync(b200dd_comm *c);
 
