@@ -281,7 +281,6 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch every kernel of every CPI instead of replaying the chain as a CUDA graph")
     ap.add_argument("--streams", type=int, default=6, help="CPIs in flight per GPU (independent pipelines on their own streams)")
-    ap.add_argument("--no-gather", action="store_true", help="diagnostic: N > 1 without the map gather (not a bench mode)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -339,6 +338,8 @@ def main():
     hx = [torch.from_numpy(np.roll(sc.x, 977 * b)).pin_memory() for b in range(2)]
     hy = [torch.from_numpy(np.roll(sc.y, 977 * b)).pin_memory() for b in range(2)]
     hmap = torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex128).pin_memory()
+    dmaps = [torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda") for _ in range(NPIPE)]
+    dmap = dmaps[0]
     streams = [torch.cuda.Stream() for _ in range(NPIPE)]
     stream = streams[0]
     st = stream.cuda_stream
@@ -349,46 +350,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # Map gather (N > 1): the CPIs are submitted in groups of NPIPE (one per pipeline); a group's NPIPE maps sit back to
-    # back in one half of a double-buffered local ring and travel to rank 0 in ONE exchange per group
-    # (b200dd_comm_gather_async: NCCL send/recv on the communicator's stream) while the next group computes into the
-    # other half.  (One exchange per CPI cost 13 % of the step at N = 2: a resident, spinning NCCL kernel per CPI and
-    # three times the launch traffic of the CPI's own graph launch; profiles/r02_summary.md.)
+    # rank 0 receives every rank's finished maps: [NPIPE ring slots][world] maps, allocated once
     map_bytes = cells * 8
-    NSLOT = 2 * NPIPE if comm is not None else NPIPE
-    ring = torch.empty((NSLOT, g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda")
-    dmaps = [ring[k] for k in range(NSLOT)]
-    dmap = dmaps[0]
     recv_ring = None
-    if comm is not None and rank == 0:   # [half][world][NPIPE] maps, allocated once
-        recv_ring = torch.empty((2, world, NPIPE, g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda")
-    sent = [None, None]   # event on the communicator's stream: "the gather that read this half of the ring has finished"
+    if comm is not None and rank == 0:
+        recv_ring = torch.empty((NPIPE, world, g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda")
 
-    def slot_of(i):
-        return (i % NPIPE) + (NPIPE * ((i // NPIPE) % 2) if comm is not None else 0)
-
-    def gather_group(half, n_in_group):
-        for q in range(n_in_group):
-            comm.wait_stream(streams[q])
-        comm.gather_async(ring[half * NPIPE:(half + 1) * NPIPE], recv_ring[half] if rank == 0 else None, 0, after=None)
-        if sent[half] is None:
-            sent[half] = torch.cuda.Event()
-        sent[half].record(comm.torch_stream())
+    sent = [None] * NPIPE   # event on the communicator's stream: "the gather that read dmaps[p] has finished"
 
     def submit(i, gather=True):
         p = i % NPIPE
-        half = (i // NPIPE) % 2
         with torch.cuda.stream(streams[p]):
-            if comm is not None and sent[half] is not None:
-                streams[p].wait_event(sent[half])  # the gather two groups back has read this half (long finished)
-            pipes[p].submit_device(xs[i % NB], ys[i % NB], dmaps[slot_of(i)], streams[p].cuda_stream)
-        if comm is not None and gather and not args.no_gather and p == NPIPE - 1:
-            gather_group(half, NPIPE)
-
-    def flush_gather(n_submitted):
-        """the last, partial group (n_submitted not a multiple of NPIPE)"""
-        if comm is not None and not args.no_gather and n_submitted % NPIPE:
-            gather_group((n_submitted // NPIPE) % 2, n_submitted % NPIPE)
+            if sent[p] is not None:
+                streams[p].wait_event(sent[p])  # only THIS pipeline's previous gather: the other pipelines keep running
+            pipes[p].submit_device(xs[i % NB], ys[i % NB], dmaps[p], streams[p].cuda_stream)
+            if comm is not None and gather:  # NCCL send/recv on the communicator's stream, behind this CPI's kernels only
+                comm.gather_async(dmaps[p], recv_ring[p] if rank == 0 else None, 0, after=streams[p])
+                if sent[p] is None:
+                    sent[p] = torch.cuda.Event()
+                sent[p].record(comm.torch_stream())
 
     # ---- device-resident throughput: a stream of independent CPIs, NPIPE in flight ----
     # Plan creation (untimed, before the warm-up steps): the CUDA graph of the chain for every (input set, pipeline)
@@ -396,12 +376,11 @@ def main():
     # launches at 111 us per CPI; at this round's ~60 us per CPI the 13 launches of a CPI are what the submitting
     # thread cannot keep up with.)  --eager turns it off.
     if args.graph:
-        for i in range(NB * NSLOT):   # submit(i) uses (i % NB, pipeline i % NPIPE, slot_of(i)): the pattern repeats after lcm(NB, NSLOT) steps
+        for i in range(NB * NPIPE):   # submit(i) uses (i % NB, i % NPIPE): the pattern repeats after lcm(NB, NPIPE) steps
             p = i % NPIPE
-            pipes[p].prepare_device(xs[i % NB], ys[i % NB], dmaps[slot_of(i)], streams[p].cuda_stream)
+            pipes[p].prepare_device(xs[i % NB], ys[i % NB], dmaps[p], streams[p].cuda_stream)
     for i in range(args.warmup):
         submit(i)   # (also warms the communicator and the gather path)
-    flush_gather(args.warmup)
     for p in range(NPIPE):
         last = pipes[p].fetch(streams[p].cuda_stream)
     if comm is not None:
@@ -423,7 +402,6 @@ def main():
         s_.wait_event(e0)
     for i in range(args.steps):
         submit(i)
-    flush_gather(args.steps)
     for p in reversed(range(NPIPE)):  # synchronises each stream; detections + metrics of the final CPIs on the host
         last = pipes[p].fetch(streams[p].cuda_stream)
     with torch.cuda.stream(stream):
@@ -436,10 +414,9 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     gather_check = None
-    if comm is not None and rank == 0 and not args.no_gather:   # rank 0's own block of the ring equals its device maps: the gather really ran
-        last = args.steps - 1
-        hf, pl = (last // NPIPE) % 2, last % NPIPE
-        gather_check = bool(torch.equal(recv_ring[hf, 0, pl], dmaps[slot_of(last)])) and bool(torch.isfinite(torch.view_as_real(recv_ring)).all())
+    if comm is not None and rank == 0:   # rank 0's own slot of the ring equals its device map: the gather really ran
+        pl = (args.steps - 1) % NPIPE
+        gather_check = bool(torch.equal(recv_ring[pl, 0], dmaps[pl])) and bool(torch.isfinite(torch.view_as_real(recv_ring)).all())
 
     # ---- end to end through the host API (pinned complex128 in, complex128 map out) ----
     # Two pipelines alternate: submit_host(i) enqueues H2D + kernels + D2H, fetch(i-1) collects the
@@ -611,7 +588,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "cpis_per_step_per_gpu": 1, "parallelism": f"independent CPIs x{world}",
                    "l2": f"{NB} distinct CPI input sets rotated ({NB * 32} MB > L2)", "cpis_in_flight": NPIPE, "submission": "cuda graph replay (b200dd_pipeline_prepare_device)" if args.graph else "eager launches",
-                   "host_cpus": host_cpus, "map_gather": (f"every finished map to rank 0, one b200dd_comm_gather_async (NCCL send/recv on a dedicated stream) per group of {NPIPE} CPIs, check {gather_check}" if world > 1 else "none (1 GPU)"),
+                   "host_cpus": host_cpus, "map_gather": (f"every finished map to rank 0 by b200dd_comm_gather_async (NCCL send/recv on a dedicated stream), check {gather_check}" if world > 1 else "none (1 GPU)"),
                    "range_fft": f"M={g.range_fft_len} x{g.range_segments} segments, hop {g.range_hop}, "
                                 f"{g.range_groups} warp group(s) x {g.range_parts} part(s) per batch",
                    "doppler_fft": f"Bluestein M2={g.doppler_fft_len}"},
