@@ -743,7 +743,7 @@ template <int MAXT> __global__ void __launch_bounds__(MAXT, 1) wh_solve_short_ke
 // ---------------------------------------------------------------------------------
 template <int LOG2M>
 __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_wspec_kernel(const double2 *w, int nBins, double2 *what,
-                                                                        const double2 *tw) {
+                                                                        const double2 *tw, int *next_block, int first_free) {
   using P = dit::Plan3<LOG2M>;
   constexpr int NT = P::NT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -759,6 +759,7 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, 1) wh_wspec_kernel(cons
   dit_transform<LOG2M, -1>(A, t, tid, v);
 #pragma unroll
   for (int q = 0; q < 16; q++) what[q * NT + tid] = v[brev<16>(q)];
+  if (tid == 0) *next_block = first_free;  // the filter kernel's work queue: blocks [0, grid) are taken by blockIdx
 }
 
 struct ApplyArgs {
@@ -773,6 +774,7 @@ struct ApplyArgs {
   long long xLo, xHi;      // readable element range of x relative to the pointer above
   XsMap xs;
   int nBins, Lout, nBlocks;
+  int *next_block;  // work queue of the persistent CTAs: first block not yet claimed (reset by wh_wspec_kernel)
 };
 
 template <class TOUT> __device__ __forceinline__ void st_iq(TOUT *p, uint32_t i, double2 v);
@@ -844,15 +846,22 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, wh_min_ctas<LOG2M>()) w
     }
     return w;
   };
+  // Work queue instead of a fixed stride: a CTA claims its NEXT block (atomic counter) while it transforms the current
+  // one.  With a static b += gridDim.x schedule a few SMs held by another kernel -- a resident NCCL send / receive in the
+  // multi-GPU runs -- left their share of the blocks for a serial second wave (13 % of the step at N = 2,
+  // profiles/r02_summary.md); it also evens out the last round on one GPU.
+  __shared__ int s_next;
   uint32_t phase = 0;
   if constexpr (kStage) {
     if (tid == 0) {
       tma::mbar_init(mbar, 1);
       tma::issue(stage_window(blockIdx.x), S, mbar);
     }
-    __syncthreads();
   }
-  for (int b = blockIdx.x; b < a.nBlocks; b += gridDim.x) {
+  __syncthreads();
+  int b_next = 0;
+  for (int b = blockIdx.x; b < a.nBlocks; b = b_next) {
+    if (tid == 0) s_next = atomicAdd(a.next_block, 1);  // read by everybody after the first barrier of the forward transform
     const uint32_t i0 = a.iBegin + (uint32_t)b * (uint32_t)a.Lout;
     const int nOut = (int)min((uint32_t)a.Lout, a.iEnd - i0);
     const tma::Window w = stage_window(b);
@@ -885,8 +894,9 @@ __global__ void __launch_bounds__(dit::Plan3<LOG2M>::NT, wh_min_ctas<LOG2M>()) w
       v[k] = make_double2(ok ? (double)e.x : 0.0, ok ? (double)e.y : 0.0);
     }
     dit_transform_ld<LOG2M, -1>(A, a.tw, tid, v, [&] {
+      b_next = s_next;
       if constexpr (kStage) {
-        if (tid == 0) tma::issue(stage_window(b + (int)gridDim.x), S, mbar);
+        if (tid == 0) tma::issue(stage_window(b_next), S, mbar);
       }
     });
     double2 z[16];
@@ -940,6 +950,7 @@ struct b200dd_wh {
   int Lout = 0, gridApply = 1;                       // filter stage
   double2 *d_tw_c = nullptr, *d_tw_a = nullptr, *d_partial = nullptr, *d_a = nullptr, *d_b = nullptr, *d_w = nullptr, *d_what = nullptr;
   int *d_status = nullptr;
+  int *d_next_block = nullptr;  // work queue of the persistent filter CTAs
   double2 *d_xd = nullptr, *d_yd = nullptr;  // host path staging (complex128)
   int num_sms = 148;
   bool solve_short = true;  // B200DD_WH_SOLVE_SHORT, read once at create
@@ -995,7 +1006,13 @@ template <int LOG2M, class TIN> int wh_launch_apply(b200dd_wh *h, const void *x,
     B2_CUDA(cudaFuncSetAttribute(wh_wspec_kernel<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem<LOG2M>()));
     done = true;
   }
-  wh_wspec_kernel<LOG2M><<<1, P::NT, fft_smem<LOG2M>(), st>>>(h->d_w, h->nBins, h->d_what, h->d_tw_a);
+  // persistent CTAs: as many as are resident at once (shared memory and the 128-register bound decide)
+  int per_sm = (int)((227 * 1024) / apply_smem<LOG2M>());
+  if (per_sm > wh_min_ctas<LOG2M>()) per_sm = wh_min_ctas<LOG2M>();
+  if (per_sm < 1) per_sm = 1;
+  int grid = h->num_sms * per_sm;
+  if (grid > h->gridApply) grid = h->gridApply;
+  wh_wspec_kernel<LOG2M><<<1, P::NT, fft_smem<LOG2M>(), st>>>(h->d_w, h->nBins, h->d_what, h->d_tw_a, h->d_next_block, grid);
   B2_LAUNCH_CHECK();
   ApplyArgs aa;
   aa.x = x; aa.y = y; aa.y_out = y_out; aa.what = h->d_what; aa.tw = h->d_tw_a; aa.status = h->d_status;
@@ -1007,13 +1024,7 @@ template <int LOG2M, class TIN> int wh_launch_apply(b200dd_wh *h, const void *x,
     aa.N = h->N; aa.iBegin = 0; aa.iEnd = h->N; aa.xs = make_xs_map(h->N, h->delayMin);
     aa.xLo = 0; aa.xHi = (long long)h->N;
   }
-  aa.nBins = h->nBins; aa.Lout = h->Lout; aa.nBlocks = h->gridApply;
-  // persistent CTAs: as many as are resident at once (shared memory and the 128-register bound decide)
-  int per_sm = (int)((227 * 1024) / apply_smem<LOG2M>());
-  if (per_sm > wh_min_ctas<LOG2M>()) per_sm = wh_min_ctas<LOG2M>();
-  if (per_sm < 1) per_sm = 1;
-  int grid = h->num_sms * per_sm;
-  if (grid > h->gridApply) grid = h->gridApply;
+  aa.nBins = h->nBins; aa.Lout = h->Lout; aa.nBlocks = h->gridApply; aa.next_block = h->d_next_block;
   wh_apply_kernel<LOG2M, TIN><<<grid, P::NT, apply_smem<LOG2M>(), st>>>(aa);
   B2_LAUNCH_CHECK();
   return B200DD_OK;
@@ -1189,6 +1200,7 @@ static int wh_create_impl(int32_t delay_min, int32_t delay_max, uint32_t n_sampl
     B2_CUDA(cudaMalloc(&h->d_what, sizeof(double2) * M));
     B2_CUDA(cudaMalloc(&h->d_status, sizeof(int)));
     B2_CUDA(cudaMemset(h->d_status, 0, sizeof(int)));
+    B2_CUDA(cudaMalloc(&h->d_next_block, sizeof(int)));
     if (h->chunked) B2_CUDA(cudaMalloc(&h->d_ab, sizeof(double2) * 2 * h->nBins));
     return B200DD_OK;
   };
@@ -1211,6 +1223,7 @@ void b200dd_wh_destroy(b200dd_wh *h) {
     free_dev(h->d_w);
     free_dev(h->d_what);
     free_dev(h->d_status);
+    free_dev(h->d_next_block);
     free_dev(h->d_ab);
     free_dev(h->d_xd);
     free_dev(h->d_yd);
