@@ -281,6 +281,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch every kernel of every CPI instead of replaying the chain as a CUDA graph")
     ap.add_argument("--streams", type=int, default=6, help="CPIs in flight per GPU (independent pipelines on their own streams)")
+    ap.add_argument("--no-gather", action="store_true", help="diagnostic: N > 1 without the map gather (not a bench mode)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -338,8 +339,6 @@ def main():
     hx = [torch.from_numpy(np.roll(sc.x, 977 * b)).pin_memory() for b in range(2)]
     hy = [torch.from_numpy(np.roll(sc.y, 977 * b)).pin_memory() for b in range(2)]
     hmap = torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex128).pin_memory()
-    dmaps = [torch.empty((g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda") for _ in range(NPIPE)]
-    dmap = dmaps[0]
     streams = [torch.cuda.Stream() for _ in range(NPIPE)]
     stream = streams[0]
     st = stream.cuda_stream
@@ -350,25 +349,39 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # rank 0 receives every rank's finished maps: [NPIPE ring slots][world] maps, allocated once
+    # Map gather (N > 1): every CPI of the region writes its map into its OWN slot of a device-resident ring (no slot is
+    # reused inside the region, so the compute streams never wait for the communicator); the maps of a chunk of NPIPE
+    # consecutive CPIs travel to rank 0 in ONE exchange (b200dd_comm_gather_async: NCCL send/recv on the communicator's
+    # stream) as soon as the chunk's CPIs have finished, beside the next chunk's kernels.  (One exchange per CPI cost
+    # 13 % of the step at N = 2 -- the NCCL calls take longer on the submitting thread than the CPI's graph launch;
+    # profiles/r02_summary.md.)
     map_bytes = cells * 8
-    recv_ring = None
-    if comm is not None and rank == 0:
-        recv_ring = torch.empty((NPIPE, world, g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda")
+    NMAPS = max(args.steps, args.warmup) if comm is not None else NPIPE
+    ring = torch.empty((NMAPS, g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda")
+    dmaps = [ring[k] for k in range(NMAPS)]
+    dmap = dmaps[0]
+    n_chunks = (NMAPS + NPIPE - 1) // NPIPE
+    recv_all = None
+    if comm is not None and rank == 0:   # [chunk][world][NPIPE] maps, allocated once
+        recv_all = torch.empty((n_chunks, world, NPIPE, g.n_doppler_bins, g.n_delay_bins), dtype=torch.complex64, device="cuda")
 
-    sent = [None] * NPIPE   # event on the communicator's stream: "the gather that read dmaps[p] has finished"
+    def slot_of(i):
+        return i if comm is not None else i % NPIPE
 
-    def submit(i, gather=True):
+    def gather_chunk(first, count):
+        """maps of the CPIs [first, first + count) -> rank 0, behind the pipelines that produced them"""
+        for q in range(count):
+            comm.wait_stream(streams[(first + q) % NPIPE])
+        c = first // NPIPE
+        comm.gather_async(ring[first:first + count], recv_all[c].view(-1)[: world * count * cells].view(world, count, g.n_doppler_bins, g.n_delay_bins) if rank == 0 else None, 0, after=None)
+
+    def submit(i, n_total):
         p = i % NPIPE
         with torch.cuda.stream(streams[p]):
-            if sent[p] is not None:
-                streams[p].wait_event(sent[p])  # only THIS pipeline's previous gather: the other pipelines keep running
-            pipes[p].submit_device(xs[i % NB], ys[i % NB], dmaps[p], streams[p].cuda_stream)
-            if comm is not None and gather:  # NCCL send/recv on the communicator's stream, behind this CPI's kernels only
-                comm.gather_async(dmaps[p], recv_ring[p] if rank == 0 else None, 0, after=streams[p])
-                if sent[p] is None:
-                    sent[p] = torch.cuda.Event()
-                sent[p].record(comm.torch_stream())
+            pipes[p].submit_device(xs[i % NB], ys[i % NB], dmaps[slot_of(i)], streams[p].cuda_stream)
+        if comm is not None and not args.no_gather and ((i + 1) % NPIPE == 0 or i == n_total - 1):
+            first = (i // NPIPE) * NPIPE
+            gather_chunk(first, i - first + 1)
 
     # ---- device-resident throughput: a stream of independent CPIs, NPIPE in flight ----
     # Plan creation (untimed, before the warm-up steps): the CUDA graph of the chain for every (input set, pipeline)
@@ -376,11 +389,12 @@ def main():
     # launches at 111 us per CPI; at this round's ~60 us per CPI the 13 launches of a CPI are what the submitting
     # thread cannot keep up with.)  --eager turns it off.
     if args.graph:
-        for i in range(NB * NPIPE):   # submit(i) uses (i % NB, i % NPIPE): the pattern repeats after lcm(NB, NPIPE) steps
+        n_prep = NB * NPIPE if comm is None else NMAPS   # 1 GPU: (i % NB, i % NPIPE) repeats after lcm(NB, NPIPE) steps
+        for i in range(n_prep):
             p = i % NPIPE
-            pipes[p].prepare_device(xs[i % NB], ys[i % NB], dmaps[p], streams[p].cuda_stream)
+            pipes[p].prepare_device(xs[i % NB], ys[i % NB], dmaps[slot_of(i)], streams[p].cuda_stream)
     for i in range(args.warmup):
-        submit(i)   # (also warms the communicator and the gather path)
+        submit(i, args.warmup)   # (also warms the communicator and the gather path)
     for p in range(NPIPE):
         last = pipes[p].fetch(streams[p].cuda_stream)
     if comm is not None:
@@ -400,8 +414,10 @@ def main():
     e0.record(stream)
     for s_ in streams[1:]:
         s_.wait_event(e0)
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
-        submit(i)
+        submit(i, args.steps)
+    host_submit_us = (time.perf_counter() - t_host0) / args.steps * 1e6   # the submitting thread's time per CPI
     for p in reversed(range(NPIPE)):  # synchronises each stream; detections + metrics of the final CPIs on the host
         last = pipes[p].fetch(streams[p].cuda_stream)
     with torch.cuda.stream(stream):
@@ -414,9 +430,11 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     gather_check = None
-    if comm is not None and rank == 0:   # rank 0's own slot of the ring equals its device map: the gather really ran
-        pl = (args.steps - 1) % NPIPE
-        gather_check = bool(torch.equal(recv_ring[pl, 0], dmaps[pl])) and bool(torch.isfinite(torch.view_as_real(recv_ring)).all())
+    if comm is not None and rank == 0 and not args.no_gather:   # rank 0's own block of the last chunk equals its device maps: the gather really ran
+        first = ((args.steps - 1) // NPIPE) * NPIPE
+        count = args.steps - first
+        got = recv_all[first // NPIPE].view(-1)[: world * count * cells].view(world, count, g.n_doppler_bins, g.n_delay_bins)
+        gather_check = bool(torch.equal(got[0], ring[first:first + count])) and bool(torch.isfinite(torch.view_as_real(got)).all())
 
     # ---- end to end through the host API (pinned complex128 in, complex128 map out) ----
     # Two pipelines alternate: submit_host(i) enqueues H2D + kernels + D2H, fetch(i-1) collects the
@@ -588,7 +606,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "cpis_per_step_per_gpu": 1, "parallelism": f"independent CPIs x{world}",
                    "l2": f"{NB} distinct CPI input sets rotated ({NB * 32} MB > L2)", "cpis_in_flight": NPIPE, "submission": "cuda graph replay (b200dd_pipeline_prepare_device)" if args.graph else "eager launches",
-                   "host_cpus": host_cpus, "map_gather": (f"every finished map to rank 0 by b200dd_comm_gather_async (NCCL send/recv on a dedicated stream), check {gather_check}" if world > 1 else "none (1 GPU)"),
+                   "host_cpus": host_cpus, "map_gather": (f"every finished map to rank 0, one b200dd_comm_gather_async (NCCL send/recv on a dedicated stream) per chunk of {NPIPE} CPIs, check {gather_check}" if world > 1 else "none (1 GPU)"),
+                   "host_submit_us_per_step": round(host_submit_us, 1),
                    "range_fft": f"M={g.range_fft_len} x{g.range_segments} segments, hop {g.range_hop}, "
                                 f"{g.range_groups} warp group(s) x {g.range_parts} part(s) per batch",
                    "doppler_fft": f"Bluestein M2={g.doppler_fft_len}"},
