@@ -52,7 +52,8 @@ def test_survey_size_table_and_default_plan():
     # SURVEY.md s8 size table; the plan the round's measurements were made with (148 SMs assumed without a device)
     g = capi.caf_plan(0, 299, -128, 128, 2000000, 2000000, True)[0]
     assert (g.n_delay_bins, g.n_doppler_bins, g.n_corr, g.nfft) == (300, 257, 7782, 15625)
-    assert (g.range_fft_len, g.range_segments, g.range_groups, g.range_parts, g.doppler_fft_len) == (2048, 5, 2, 1, 1024)
+    # round 2: the DIT range kernel has no warp groups; a batch is split into parts until ~5 CTAs per SM exist
+    assert (g.range_fft_len, g.range_segments, g.range_groups, g.range_parts, g.doppler_fft_len) == (2048, 5, 1, 2, 1024)
     g = capi.caf_plan(0, 511, -256, 256, 10000000, 20000000, True)[0]
     assert (g.n_delay_bins, g.n_doppler_bins, g.n_corr, g.nfft) == (512, 1025, 19512, 39366)
     assert (g.range_fft_len, g.range_groups, g.range_parts, g.doppler_fft_len) == (2048, 1, 1, 4096)
