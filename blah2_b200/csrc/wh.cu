@@ -737,6 +737,205 @@ template <int MAXT> __global__ void __launch_bounds__(MAXT, 1) wh_solve_short_ke
   if (tid == 0) *s.status = ok ? 0 : 1;
 }
 
+// ---- split variant (n <= 496 taps: two thread groups of ceil32(n) rows + one warp fit 1024 threads) -----------
+// In the kernel above every step pays for BOTH recursions although the Levinson accumulation (2) only consumes two
+// numbers per step of the Schur recursion (1): rho_k = b_k / p_k and g_k = r_k sigma_k.  Here they run as a
+// producer and a consumer inside one CTA, each thread group with its own named barrier:
+//   * threads [0, NTS): Schur rows (generator update + forward substitution), threads [NTS, NTS + 32): the pivot
+//     chain; this group never waits for the other.  At the start of step k the pivot warp forms (rho_k, g_k) from
+//     the values published during step k - 1, appends them to a queue in shared memory (one slot per step: no
+//     reuse, no back-pressure) and raises `ready`;
+//   * threads [NTS + 32, 2 NTS + 32): Levinson rows.  Their first warp polls `ready`, then the group's barrier
+//     both ends step k - 1 and opens step k.
+// The Schur steps are widest (n - k rows) when the Levinson steps are narrowest (k rows) and vice versa, so the
+// elapsed time is about  sum_k max(T_schur(k), T_levinson(k))  instead of the sum of both.  A pivot that is not
+// positive is passed down the queue as a NaN rho (a NaN that arises by itself means the same thing).
+// Same arithmetic per row as the kernels above, except that rho_k and g_k are rounded once by the producer
+// instead of once per consumer thread -- identical values.
+__device__ __forceinline__ void named_barrier(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+__global__ void __launch_bounds__(1024, 1) wh_solve_split_kernel(SolveArgs s) {
+  extern __shared__ __align__(16) double2 sm[];
+  const int n = s.nBins;
+  const int ALB0 = 0, ALB1 = n;          // generator a_i, ping-pong (neighbour shift)
+  const int PHB0 = 2 * n, PHB1 = 3 * n;  // predictor phi_i, ping-pong (mirrored access)
+  const int RING = 4 * n;                // queue: rho_k at RING + 2k, g_k at RING + 2k + 1
+  const int SC = 6 * n;                  // state of parity q at SC + 4q: (p s, 1/p), (s, sigma), (p, -); raw b_k / r_k at SC + 8 + q / SC + 10 + q
+  __shared__ double s_t0;
+  __shared__ int s_ready;                // number of queue entries published
+  const int tid = threadIdx.x;
+  const int NTS = (n + 31) & ~31;
+  const bool schur = tid < NTS, pivot_warp = tid >= NTS && tid < NTS + 32;
+  const int i = schur ? tid : tid - NTS - 32;  // row (both row groups)
+  const int row_lo = i & ~31, row_hi = row_lo + 31;
+  const double2 zero = make_double2(0.0, 0.0);
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+
+  // fixed-order reduction of the per-CTA partial correlations (deterministic): a by the Schur rows, b by the Levinson rows
+  double2 sum = zero;
+  if (!pivot_warp && i < n) {
+    const double2 *src = s.partial + i + (schur ? 0 : n);
+    int p = 0;
+    for (; p + 8 <= s.nPartial; p += 8) {
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = __ldg(src + (size_t)(p + u) * 2 * n);
+#pragma unroll
+      for (int u = 0; u < 8; u++) { sum.x += v[u].x; sum.y += v[u].y; }
+    }
+    for (; p < s.nPartial; p++) {
+      const double2 v = __ldg(src + (size_t)p * 2 * n);
+      sum.x += v.x; sum.y += v.y;
+    }
+    if (schur) {
+      s.a_out[i] = sum;
+      if (i == 0) s_t0 = sum.x;
+    } else {
+      s.b_out[i] = sum;
+      sm[ALB1 + i] = sum;  // handed to the Schur row (the buffer's first use as a generator is step 0's output)
+    }
+  }
+  if (tid == 0) s_ready = 0;
+  __syncthreads();
+  const double t0 = s_t0;
+  bool ok = (t0 > 0.0) && isfinite(t0);
+  const double inv_t0 = ok ? 1.0 / t0 : 1.0;
+  double2 al = zero, be = zero, rr = zero;
+  if (schur && i < n) {
+    al = make_double2(sum.x * inv_t0, -sum.y * inv_t0);  // a_i^(0) = conj(a[i]) / t_0  (p_0 = 1)
+    be = i ? al : zero;
+    rr = sm[ALB1 + i];
+    sm[ALB0 + i] = al;
+    if (i == 0) {
+      sm[SC + 10] = rr;                         // r_0
+      sm[SC + 0] = make_double2(1.0, 1.0);      // (p s, 1/p)
+      sm[SC + 1] = make_double2(1.0, inv_t0);   // (s, sigma_0 = 1 / t_0)
+      sm[SC + 2] = make_double2(1.0, 0.0);      // p_0
+    }
+    if (i == 1) sm[SC + 8] = be;                // b_0
+  }
+  if (!schur && !pivot_warp && i < n) {
+    sm[PHB0 + i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // phi^(1) = [1]
+    sm[PHB1 + i] = zero;
+  }
+  if (n == 1 && tid == 0) sm[SC + 8] = zero;
+  __syncthreads();
+
+  if (schur || pivot_warp) {
+    // ================= producer: Schur recursion + pivot chain, barrier 1 =================
+    const int count = NTS + 32;
+    int k = 0;
+    if (ok) {
+      for (; k < n - 1; k++) {
+        const int par = k & 1;
+        const double2 st0 = sm[SC + 4 * par];  // (p s, 1/p)
+        if (pivot_warp) {
+          const double2 st1 = sm[SC + 4 * par + 1];
+          const double2 b = sm[SC + 8 + par], r = sm[SC + 10 + par];
+          const double p = sm[SC + 4 * par + 2].x;
+          const bool good = st0.x > 0.0;
+          if ((tid & 31) == 0) {
+            sm[RING + 2 * k] = good ? make_double2(b.x * st0.y, b.y * st0.y) : make_double2(qnan, qnan);  // rho_k
+            sm[RING + 2 * k + 1] = make_double2(r.x * st1.y, r.y * st1.y);                                   // g_k
+            __threadfence_block();
+            *(volatile int *)&s_ready = k + 1;
+          }
+          // p_{k+1} = s (p^2 - |b|^2) and everything derived from it, for the next step
+          const double pnew = st0.x * p - ((b.x * st1.x) * b.x + (b.y * st1.x) * b.y);
+          const double inv_pn = rcp_newton(pnew);
+          const double scn = pow2_scale(pnew);
+          const double sign = st1.y * st0.x * p * inv_pn;  // sigma / (1 - |rho|^2)
+          if ((tid & 31) == 0) {
+            sm[SC + 4 * (par ^ 1)] = make_double2(pnew * scn, inv_pn);
+            sm[SC + 4 * (par ^ 1) + 1] = make_double2(scn, sign);
+            sm[SC + 4 * (par ^ 1) + 2] = make_double2(pnew, 0.0);
+          }
+        } else if (row_hi > k) {
+          // rows i > k of this warp; computed on clamped indices for all lanes, committed by selects
+          const double2 *ac = sm + (par ? ALB1 : ALB0);
+          double2 *an = sm + (par ? ALB0 : ALB1);
+          const double2 at = ac[max(i - 1, 0)];
+          const double sc = sm[SC + 4 * par + 1].x;
+          const double2 b = sm[SC + 8 + par], r = sm[SC + 10 + par];
+          const double ps = st0.x;
+          const double2 bs = make_double2(b.x * sc, b.y * sc);
+          const double2 q = make_double2(r.x * st0.y, r.y * st0.y);  // r_k / p_k
+          const bool act = i > k && i < n;
+          double2 na, nb, nr;
+          na.x = ps * at.x - (bs.x * be.x + bs.y * be.y);   // s (p at - conj(b) be)
+          na.y = ps * at.y - (bs.x * be.y - bs.y * be.x);
+          nb.x = ps * be.x - (bs.x * at.x - bs.y * at.y);   // s (p be - b at)
+          nb.y = ps * be.y - (bs.x * at.y + bs.y * at.x);
+          nr.x = rr.x - (al.x * q.x - al.y * q.y);          // r_i -= a_i (r_k / p_k)
+          nr.y = rr.y - (al.x * q.y + al.y * q.x);
+          if (act) an[i] = na;
+          if (i == k + 2 && i < n) sm[SC + 8 + (par ^ 1)] = nb;  // b_{k+1}
+          if (i == k + 1) sm[SC + 10 + (par ^ 1)] = nr;          // r_{k+1}
+          al = act ? na : al;
+          be = act ? nb : be;
+          rr = act ? nr : rr;
+        }
+        if (!(st0.x > 0.0)) break;  // uniform: every thread read the same published pivot (its NaN rho is in the queue)
+        named_barrier(1, count);
+      }
+    }
+    if (pivot_warp && (tid & 31) == 0) {
+      // the last innovation g_{n-1}, or the verdict on the last pivot / the initial check, closes the queue
+      const int par = k & 1;
+      const double2 st0 = sm[SC + 4 * par], st1 = sm[SC + 4 * par + 1], r = sm[SC + 10 + par];
+      const bool good = ok && k == n - 1 && st0.x > 0.0;
+      if (k == n - 1 || !ok) {  // (a break inside the loop has already queued its NaN at slot k)
+        const int slot = ok ? n - 1 : 0;
+        sm[RING + 2 * slot] = good ? zero : make_double2(qnan, qnan);
+        sm[RING + 2 * slot + 1] = make_double2(r.x * st1.y, r.y * st1.y);
+        __threadfence_block();
+        *(volatile int *)&s_ready = n;
+      }
+    }
+    return;
+  }
+
+  // ================= consumer: Levinson accumulation, barrier 2 =================
+  double2 xx = zero;
+  bool fine = true;
+  for (int k = 0; k < n; k++) {
+    if (i < 32) {  // the group's first warp waits for the producer
+      while (*(volatile int *)&s_ready <= k) {}
+      __threadfence_block();
+    }
+    named_barrier(2, NTS);  // ends step k - 1 (phi of parity k complete) and opens step k
+    const int par = k & 1;
+    const double2 rho = sm[RING + 2 * k];
+    if (!(rho.x == rho.x)) { fine = false; break; }  // uniform: one queue entry
+    if (row_lo > k + 1) continue;                    // rows not yet reached by the recursion
+    const double2 *pc = sm + (par ? PHB1 : PHB0);
+    double2 *pn_ = sm + (par ? PHB0 : PHB1);
+    const double2 g = sm[RING + 2 * k + 1];
+    const int ic = min(i, n - 1);
+    const double2 ph_x = pc[max(k - ic, 0)];
+    // x_i += (r_k sigma_k) conj(phi[k - i])   (i <= k)
+    const double nx = xx.x + (g.x * ph_x.x + g.y * ph_x.y);
+    const double ny = xx.y + (g.y * ph_x.x - g.x * ph_x.y);
+    xx.x = i <= k ? nx : xx.x;
+    xx.y = i <= k ? ny : xx.y;
+    if (k < n - 1) {
+      // phi'[i] = phi[i] (i <= k) - rho conj(phi[k + 1 - i]) (i >= 1)
+      const double2 ph_i = pc[ic];
+      const double2 ph_m = pc[min(max(k + 1 - ic, 0), n - 1)];
+      const double2 pi_ = i <= k ? ph_i : zero;
+      const double2 pm_ = i >= 1 ? ph_m : zero;
+      double2 np_;
+      np_.x = pi_.x - (rho.x * pm_.x + rho.y * pm_.y);
+      np_.y = pi_.y - (rho.y * pm_.x - rho.x * pm_.y);
+      if (i <= k + 1 && i < n) pn_[i] = np_;
+    }
+  }
+  if (i < n) s.w_out[i] = fine ? xx : zero;
+  if (i == 0) *s.status = fine ? 0 : 1;
+}
+
 // ---------------------------------------------------------------------------------
 // spectrum of the zero-padded weights, once per CPI: what[q NT + tid] = W^[tid + NT q] (the order in which the
 // filter kernel's threads hold their spectra: coalesced 16-byte loads)
@@ -954,6 +1153,7 @@ struct b200dd_wh {
   double2 *d_xd = nullptr, *d_yd = nullptr;  // host path staging (complex128)
   int num_sms = 148;
   bool solve_short = true;  // B200DD_WH_SOLVE_SHORT, read once at create
+  bool solve_split = true;  // B200DD_WH_SOLVE_SPLIT, read once at create
   // chunk mode (one CPI split over several GPUs): this handle filters the samples [c0, c0 + nc) of an N-sample signal
   bool chunked = false;
   uint32_t c0 = 0, nc = 0;
@@ -1038,13 +1238,16 @@ int wh_launch_solve(b200dd_wh *h, cudaStream_t st) {
     B2_CUDA(cudaFuncSetAttribute(wh_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
     B2_CUDA(cudaFuncSetAttribute(wh_solve_short_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
     B2_CUDA(cudaFuncSetAttribute(wh_solve_short_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
+    B2_CUDA(cudaFuncSetAttribute(wh_solve_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem_max));
     h->attr_solve = true;
   }
   SolveArgs sa;
   sa.partial = h->chunked ? h->d_ab : h->d_partial; sa.nPartial = h->chunked ? 1 : h->gridCorr; sa.nBins = h->nBins;
   sa.a_out = h->d_a; sa.b_out = h->d_b; sa.w_out = h->d_w; sa.status = h->d_status;
   const int threads = ((h->nBins + 31) / 32) * 32;
-  if (h->solve_short && threads + 32 <= 1024) {  // includes the reference's configuration (410 taps)
+  if (h->solve_split && 2 * threads + 32 <= 1024) {  // includes the reference's configuration (410 taps)
+    wh_solve_split_kernel<<<1, 2 * threads + 32, solve_smem, st>>>(sa);
+  } else if (h->solve_short && threads + 32 <= 1024) {
     if (threads + 32 <= 512) wh_solve_short_kernel<512><<<1, threads + 32, solve_smem, st>>>(sa);
     else wh_solve_short_kernel<1024><<<1, threads + 32, solve_smem, st>>>(sa);
   } else if (h->nBins <= 1024) {
@@ -1108,6 +1311,7 @@ int wh_pick_log2m(const b200dd_wh *h, const char *env1, const char *env2, bool f
 
 void wh_plan(b200dd_wh *h) {
   if (const char *e = getenv("B200DD_WH_SOLVE_SHORT")) h->solve_short = atoi(e) != 0;
+  if (const char *e = getenv("B200DD_WH_SOLVE_SPLIT")) h->solve_split = atoi(e) != 0;
   h->log2m_c = wh_pick_log2m(h, "B200DD_WH_LOG2M", "B200DD_WH_CORR_LOG2M", false);
   h->log2m_a = wh_pick_log2m(h, "B200DD_WH_LOG2M", "B200DD_WH_APPLY_LOG2M", true);
   if (!h->log2m_c || !h->log2m_a) return;

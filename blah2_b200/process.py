@@ -264,6 +264,14 @@ class WienerHopfChunk:
         rc = capi.check(self._lib.b200dd_wh_last_status(self._h), allow=(capi.FILTER_FAILED,))
         return rc == capi.OK
 
+    def debug_weights(self):
+        """(w, a, b) of the last filter_device call (tests)."""
+        w = np.empty(self.nBins, dtype=np.complex128)
+        a = np.empty(self.nBins, dtype=np.complex128)
+        b = np.empty(self.nBins, dtype=np.complex128)
+        capi.check(self._lib.b200dd_wh_debug_weights(self._h, capi.ptr(w), capi.ptr(a), capi.ptr(b)))
+        return w, a, b
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.b200dd_wh_destroy(self._h)

@@ -139,22 +139,83 @@ def test_every_fft_plan_gives_the_same_filter(log2m, relerr, monkeypatch):
     assert e[0] < 1e-9 and e[1] < 1e-9, f"radix {radix} M=2^{log2m}: {e}"
 
 
-@pytest.mark.parametrize("case", [(20011, -10, 40, 2), (200000, -10, 400, 4)])
-def test_both_solve_kernels_give_the_same_weights(case, relerr, monkeypatch):
-    """B200DD_WH_SOLVE_SHORT=0 selects the generic one-row-per-thread kernel for small systems too; the
-    short-path kernel (default) runs the same recursion with a Newton reciprocal instead of a division."""
+@pytest.mark.parametrize("case", [(20011, -10, 40, 2), (200000, -10, 400, 4), (150000, 0, 1, 5), (150000, -3, 30, 6),
+                                  (200000, -10, 480, 7), (200000, -10, 500, 8)])
+def test_all_solve_kernels_give_the_same_weights(case, relerr, monkeypatch):
+    """Three kernels run the same Schur + Levinson recursion: the split producer / consumer kernel (default up to 496
+    taps), the one-barrier-per-step short kernel (B200DD_WH_SOLVE_SPLIT=0; default up to 992 taps) and the generic
+    kernel (B200DD_WH_SOLVE_SHORT=0 as well).  Sizes: one tap, one warp, 410 (the reference's), the largest split
+    system's neighbourhood (490 taps: split, 510: falls back to the short kernel)."""
     n, dm, dM, seed = case
     sc = _scene(n, seed)
     ws = {}
-    for mode in ("1", "0"):
-        monkeypatch.setenv("B200DD_WH_SOLVE_SHORT", mode)
+    for mode in (("1", "1"), ("0", "1"), ("0", "0")):
+        monkeypatch.setenv("B200DD_WH_SOLVE_SPLIT", mode[0])
+        monkeypatch.setenv("B200DD_WH_SOLVE_SHORT", mode[1])
         wh = WienerHopf(dm, dM, n)
         ok, _ = wh.process(sc.x, sc.y)
         assert ok
         ws[mode] = wh.debug_weights()[0]
-    assert relerr(ws["1"], ws["0"])[0] < 1e-11
+    assert relerr(ws[("1", "1")], ws[("0", "0")])[0] < 1e-11
+    assert relerr(ws[("0", "1")], ws[("0", "0")])[0] < 1e-11
 
 
+def _ar_sequence(nb, seed, pole=0.9):
+    """First column a[k] of a Hermitian positive-definite Toeplitz matrix: the autocorrelation of a few complex AR(1) lines."""
+    rng = np.random.default_rng(seed)
+    k = np.arange(nb)
+    a = np.zeros(nb, dtype=np.complex128)
+    for _ in range(4):
+        a += rng.uniform(0.5, 2.0) * (pole * rng.uniform(0.5, 1.0) * np.exp(2j * np.pi * rng.uniform())) ** k
+    a[0] = a[0].real * 1.01
+    return a
+
+
+@pytest.mark.parametrize("nb,bad_at", [(1, None), (1, 0), (33, None), (33, 1), (33, 20), (410, None), (410, 1), (410, 215),
+                                       (410, 409), (496, None), (496, 495), (600, 300)])
+@pytest.mark.parametrize("mode", [("1", "1"), ("0", "1"), ("0", "0")])
+def test_solve_kernels_on_given_toeplitz_systems(nb, bad_at, mode, relerr, monkeypatch):
+    """The solve kernels on correlation sums handed in through the chunk API (b200dd_wh_chunk_filter_device): weights
+    against LAPACK on the matrix the reference builds (WienerHopf.cpp:85-97), and the 'not positive definite' verdict
+    -- WienerHopf.cpp:111-117: chol() fails -> process() returns false, y untouched -- when the leading minor of
+    order bad_at + 1 is the first indefinite one (first pivot / early / mid-recursion / last pivot)."""
+    import scipy.linalg as sla
+    import torch
+    from blah2_b200.process import WienerHopfChunk
+    monkeypatch.setenv("B200DD_WH_SOLVE_SPLIT", mode[0])
+    monkeypatch.setenv("B200DD_WH_SOLVE_SHORT", mode[1])
+    n = 40000
+    a = _ar_sequence(nb, nb)
+    rng = np.random.default_rng(nb + 1)
+    b = rng.standard_normal(nb) + 1j * rng.standard_normal(nb)
+    if bad_at == 0:
+        a[0] = -1.0
+    elif bad_at is not None:
+        a[bad_at] = 3.0 * a[0]           # |a[k]| > a[0]: the minor of order k + 1 is indefinite, the smaller ones are not
+    A = sla.toeplitz(np.conj(a), a)      # A(i,j) = a[j-i] (j >= i), conj(a[i-j]) (i > j)
+    expect_ok = True
+    try:
+        np.linalg.cholesky(A)
+    except np.linalg.LinAlgError:
+        expect_ok = False
+    assert expect_ok == (bad_at is None)
+    if bad_at:
+        np.linalg.cholesky(A[:bad_at, :bad_at])          # ... and it is the FIRST bad minor
+    ch = WienerHopfChunk(0, nb, n, 0, n)
+    xl, xr, yr = ch.halos()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x_loc = torch.view_as_complex(torch.randn((xl + n + xr, 2), device="cuda", generator=g))
+    y_loc = torch.view_as_complex(torch.randn((n + yr, 2), device="cuda", generator=g))
+    out = torch.full((n,), complex(7, 7), dtype=torch.complex64, device="cuda")
+    ab = torch.from_numpy(np.concatenate([a, b])).cuda()
+    ch.filter_device(ab, x_loc, y_loc, out)
+    torch.cuda.synchronize()
+    assert ch.last_status() == expect_ok
+    if expect_ok:
+        w = ch.debug_weights()[0]
+        assert relerr(w, np.linalg.solve(A, b))[0] < 1e-10
+    else:
+        assert torch.equal(out, y_loc[:n])               # the surveillance channel passes through
 
 
 @pytest.mark.parametrize("case", [(300000, -10, 400, 3, 7), (120000, 0, 60, 2, 8), (200003, -3, 129, 4, 9)])
