@@ -737,36 +737,46 @@ template <int MAXT> __global__ void __launch_bounds__(MAXT, 1) wh_solve_short_ke
   if (tid == 0) *s.status = ok ? 0 : 1;
 }
 
-// ---- split variant (n <= 496 taps: two thread groups of ceil32(n) rows + one warp fit 1024 threads) -----------
+// ---- split variant (n <= 480 taps: two thread groups of ceil32(n) rows + one warp fit 1024 threads) -----------
 // In the kernel above every step pays for BOTH recursions although the Levinson accumulation (2) only consumes two
 // numbers per step of the Schur recursion (1): rho_k = b_k / p_k and g_k = r_k sigma_k.  Here they run as a
-// producer and a consumer inside one CTA, each thread group with its own named barrier:
+// producer and a consumer inside one CTA, each thread group with its own named barriers:
 //   * threads [0, NTS): Schur rows (generator update + forward substitution), threads [NTS, NTS + 32): the pivot
-//     chain; this group never waits for the other.  At the start of step k the pivot warp forms (rho_k, g_k) from
-//     the values published during step k - 1, appends them to a queue in shared memory (one slot per step: no
-//     reuse, no back-pressure) and raises `ready`;
+//     chain; this group never waits for the other.  During step k the pivot warp forms (rho_k, g_k) from the
+//     values published in step k - 1, appends them to a queue in shared memory (one slot per step: no reuse, no
+//     back-pressure) and raises `ready`.  A row warp whose rows are all <= k has nothing left to do and EXITS:
+//     the barrier of step k counts only the warps that ran step k;
 //   * threads [NTS + 32, 2 NTS + 32): Levinson rows.  Their first warp polls `ready`, then the group's barrier
-//     both ends step k - 1 and opens step k.
-// The Schur steps are widest (n - k rows) when the Levinson steps are narrowest (k rows) and vice versa, so the
-// elapsed time is about  sum_k max(T_schur(k), T_levinson(k))  instead of the sum of both.  A pivot that is not
-// positive is passed down the queue as a NaN rho (a NaN that arises by itself means the same thing).
-// Same arithmetic per row as the kernels above, except that rho_k and g_k are rounded once by the producer
-// instead of once per consumer thread -- identical values.
+//     both ends step k - 1 and opens step k.  A warp whose rows are all > k + 1 has nothing to do YET: it sleeps
+//     on an mbarrier that the first warp completes one step before the recursion reaches its first row, and the
+//     barrier counts only the warps that are awake.
+// Both barriers alternate between two hardware ids so that consecutive phases with different counts never meet.
+// The Schur steps are widest (n - k rows) when the Levinson steps are narrowest (k rows) and vice versa: no warp
+// spends instructions on a step it has no rows in, and the elapsed time is about sum_k max(T_schur(k), T_lev(k))
+// instead of the sum of both.  A pivot that is not positive travels down the queue as a NaN rho (a NaN that
+// arises by itself means the same thing).  Same arithmetic per row as the kernels above.
+// Measured history: profiles/r02_summary.md s7.
 __device__ __forceinline__ void named_barrier(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tma::smem_u32(bar)) : "memory");
 }
 
 __global__ void __launch_bounds__(1024, 1) wh_solve_split_kernel(SolveArgs s) {
   extern __shared__ __align__(16) double2 sm[];
   const int n = s.nBins;
-  const int ALB0 = 0, ALB1 = n;          // generator a_i, ping-pong (neighbour shift)
-  const int PHB0 = 2 * n, PHB1 = 3 * n;  // predictor phi_i, ping-pong (mirrored access)
-  const int RING = 4 * n;                // queue: rho_k at RING + 2k, g_k at RING + 2k + 1
-  const int SC = 6 * n;                  // state of parity q at SC + 4q: (p s, 1/p), (s, sigma), (p, -); raw b_k / r_k at SC + 8 + q / SC + 10 + q
+  const int ALB0 = 0, ALB1 = n;                  // generator a_i, ping-pong (neighbour shift)
+  const int PHB0 = 2 * n + 1, PHB1 = 3 * n + 2;  // predictor phi_i, ping-pong (mirrored access); element -1 of each is a zero
+  const int RING = 4 * n + 2;                    // queue: rho_k at RING + 2k, g_k at RING + 2k + 1
+  const int SC = 6 * n + 2;                      // state of parity q at SC + 4q: (p s, 1/p), (s, sigma), (p, -); raw b_k / r_k at SC + 8 + q / SC + 10 + q
   __shared__ double s_t0;
-  __shared__ int s_ready;                // number of queue entries published
+  __shared__ int s_ready;                        // number of queue entries published
+  __shared__ int s_abort;                        // the consumer stopped early: sleeping warps must not start
+  __shared__ __align__(8) uint64_t s_join[16];   // wake-up of Levinson warp w
   const int tid = threadIdx.x;
-  const int NTS = (n + 31) & ~31;
+  const int NTS = (n + 31) & ~31, NW = NTS >> 5;
   const bool schur = tid < NTS, pivot_warp = tid >= NTS && tid < NTS + 32;
   const int i = schur ? tid : tid - NTS - 32;  // row (both row groups)
   const int row_lo = i & ~31, row_hi = row_lo + 31;
@@ -797,10 +807,11 @@ __global__ void __launch_bounds__(1024, 1) wh_solve_split_kernel(SolveArgs s) {
       sm[ALB1 + i] = sum;  // handed to the Schur row (the buffer's first use as a generator is step 0's output)
     }
   }
-  if (tid == 0) s_ready = 0;
+  if (tid == 0) { s_ready = 0; s_abort = 0; }
+  if (tid < 16) tma::mbar_init(&s_join[tid], 1);
   __syncthreads();
   const double t0 = s_t0;
-  bool ok = (t0 > 0.0) && isfinite(t0);
+  const bool ok = (t0 > 0.0) && isfinite(t0);
   const double inv_t0 = ok ? 1.0 / t0 : 1.0;
   double2 al = zero, be = zero, rr = zero;
   if (schur && i < n) {
@@ -813,35 +824,29 @@ __global__ void __launch_bounds__(1024, 1) wh_solve_split_kernel(SolveArgs s) {
       sm[SC + 0] = make_double2(1.0, 1.0);      // (p s, 1/p)
       sm[SC + 1] = make_double2(1.0, inv_t0);   // (s, sigma_0 = 1 / t_0)
       sm[SC + 2] = make_double2(1.0, 0.0);      // p_0
+      if (n == 1) sm[SC + 8] = zero;            // (b_0 of a one-tap system: never used)
     }
     if (i == 1) sm[SC + 8] = be;                // b_0
   }
   if (!schur && !pivot_warp && i < n) {
-    sm[PHB0 + i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // phi^(1) = [1]
+    sm[PHB0 + i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // phi^(0) = [1]
     sm[PHB1 + i] = zero;
+    if (i == 0) sm[PHB0 - 1] = sm[PHB1 - 1] = zero;
   }
-  if (n == 1 && tid == 0) sm[SC + 8] = zero;
   __syncthreads();
 
   if (schur || pivot_warp) {
-    // ================= producer: Schur recursion + pivot chain, barrier 1 =================
-    const int count = NTS + 32;
+    // ================= producer: Schur recursion + pivot chain, barriers 1 / 3 =================
     int k = 0;
     if (ok) {
       for (; k < n - 1; k++) {
+        if (schur && row_hi <= k) return;       // every row of this warp is final
         const int par = k & 1;
-        const double2 st0 = sm[SC + 4 * par];  // (p s, 1/p)
+        const double2 st0 = sm[SC + 4 * par];   // (p s, 1/p)
         if (pivot_warp) {
           const double2 st1 = sm[SC + 4 * par + 1];
           const double2 b = sm[SC + 8 + par], r = sm[SC + 10 + par];
           const double p = sm[SC + 4 * par + 2].x;
-          const bool good = st0.x > 0.0;
-          if ((tid & 31) == 0) {
-            sm[RING + 2 * k] = good ? make_double2(b.x * st0.y, b.y * st0.y) : make_double2(qnan, qnan);  // rho_k
-            sm[RING + 2 * k + 1] = make_double2(r.x * st1.y, r.y * st1.y);                                   // g_k
-            __threadfence_block();
-            *(volatile int *)&s_ready = k + 1;
-          }
           // p_{k+1} = s (p^2 - |b|^2) and everything derived from it, for the next step
           const double pnew = st0.x * p - ((b.x * st1.x) * b.x + (b.y * st1.x) * b.y);
           const double inv_pn = rcp_newton(pnew);
@@ -851,34 +856,36 @@ __global__ void __launch_bounds__(1024, 1) wh_solve_split_kernel(SolveArgs s) {
             sm[SC + 4 * (par ^ 1)] = make_double2(pnew * scn, inv_pn);
             sm[SC + 4 * (par ^ 1) + 1] = make_double2(scn, sign);
             sm[SC + 4 * (par ^ 1) + 2] = make_double2(pnew, 0.0);
+            // the consumer's share of step k (after the group's own: the fence is off the group's critical path)
+            sm[RING + 2 * k] = st0.x > 0.0 ? make_double2(b.x * st0.y, b.y * st0.y) : make_double2(qnan, qnan);  // rho_k
+            sm[RING + 2 * k + 1] = make_double2(r.x * st1.y, r.y * st1.y);                                        // g_k
+            fence_cta();
+            *(volatile int *)&s_ready = k + 1;
           }
-        } else if (row_hi > k) {
-          // rows i > k of this warp; computed on clamped indices for all lanes, committed by selects
+        } else if (i > k && i < n) {
           const double2 *ac = sm + (par ? ALB1 : ALB0);
           double2 *an = sm + (par ? ALB0 : ALB1);
-          const double2 at = ac[max(i - 1, 0)];
+          const double2 at = ac[i - 1];
           const double sc = sm[SC + 4 * par + 1].x;
           const double2 b = sm[SC + 8 + par], r = sm[SC + 10 + par];
           const double ps = st0.x;
           const double2 bs = make_double2(b.x * sc, b.y * sc);
           const double2 q = make_double2(r.x * st0.y, r.y * st0.y);  // r_k / p_k
-          const bool act = i > k && i < n;
-          double2 na, nb, nr;
-          na.x = ps * at.x - (bs.x * be.x + bs.y * be.y);   // s (p at - conj(b) be)
-          na.y = ps * at.y - (bs.x * be.y - bs.y * be.x);
-          nb.x = ps * be.x - (bs.x * at.x - bs.y * at.y);   // s (p be - b at)
-          nb.y = ps * be.y - (bs.x * at.y + bs.y * at.x);
-          nr.x = rr.x - (al.x * q.x - al.y * q.y);          // r_i -= a_i (r_k / p_k)
-          nr.y = rr.y - (al.x * q.y + al.y * q.x);
-          if (act) an[i] = na;
-          if (i == k + 2 && i < n) sm[SC + 8 + (par ^ 1)] = nb;  // b_{k+1}
-          if (i == k + 1) sm[SC + 10 + (par ^ 1)] = nr;          // r_{k+1}
-          al = act ? na : al;
-          be = act ? nb : be;
-          rr = act ? nr : rr;
+          double2 na, nb;  // 20 FP64 instructions per row and step, written out as the FMAs they are
+          na.x = fma(ps, at.x, -fma(bs.x, be.x, bs.y * be.y));   // s (p at - conj(b) be)
+          na.y = fma(ps, at.y, -fma(bs.x, be.y, -(bs.y * be.x)));
+          nb.x = fma(ps, be.x, -fma(bs.x, at.x, -(bs.y * at.y)));  // s (p be - b at)
+          nb.y = fma(ps, be.y, -fma(bs.x, at.y, bs.y * at.x));
+          rr.x = fma(al.y, q.y, fma(-al.x, q.x, rr.x));           // r_i -= a_i (r_k / p_k)
+          rr.y = fma(-al.y, q.x, fma(-al.x, q.y, rr.y));
+          an[i] = na;
+          if (i == k + 2) sm[SC + 8 + (par ^ 1)] = nb;      // b_{k+1}
+          if (i == k + 1) sm[SC + 10 + (par ^ 1)] = rr;     // r_{k+1}
+          al = na;
+          be = nb;
         }
         if (!(st0.x > 0.0)) break;  // uniform: every thread read the same published pivot (its NaN rho is in the queue)
-        named_barrier(1, count);
+        named_barrier(1 + 2 * par, 32 * (NW - ((k + 1) >> 5) + 1));  // the row warps that ran step k + the pivot warp
       }
     }
     if (pivot_warp && (tid & 31) == 0) {
@@ -890,46 +897,50 @@ __global__ void __launch_bounds__(1024, 1) wh_solve_split_kernel(SolveArgs s) {
         const int slot = ok ? n - 1 : 0;
         sm[RING + 2 * slot] = good ? zero : make_double2(qnan, qnan);
         sm[RING + 2 * slot + 1] = make_double2(r.x * st1.y, r.y * st1.y);
-        __threadfence_block();
+        fence_cta();
         *(volatile int *)&s_ready = n;
       }
     }
     return;
   }
 
-  // ================= consumer: Levinson accumulation, barrier 2 =================
-  double2 xx = zero;
+  // ================= consumer: Levinson accumulation, barriers 2 / 4 =================
+  const int w = i >> 5;
+  double2 xx = zero, own = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // x_i and this row's phi_i
   bool fine = true;
-  for (int k = 0; k < n; k++) {
-    if (i < 32) {  // the group's first warp waits for the producer
-      while (*(volatile int *)&s_ready <= k) {}
-      __threadfence_block();
+  int k = 0, next_join = 1;
+  if (w > 0) {
+    tma::mbar_wait(&s_join[w], 0);            // completed during step 32 w - 2 (or by an abort)
+    if (*(volatile int *)&s_abort) fine = false;
+    k = 32 * w - 1;                           // the first step that touches row 32 w
+  }
+  if (fine) {
+    for (; k < n; k++) {
+      if (w == 0) {  // the group's first warp waits for the producer
+        while (*(volatile int *)&s_ready <= k) {}
+      }
+      const int par = k & 1;
+      named_barrier(2 + 2 * par, 32 * min(NW, ((k + 1) >> 5) + 1));  // ends step k - 1 (phi of parity k complete), opens step k
+      const double2 rho = sm[RING + 2 * k];
+      if (!(rho.x == rho.x)) { fine = false; break; }  // uniform: one queue entry
+      // the recursion reaches row 32 w' at step 32 w' - 1: wake that warp now, it joins the next barrier
+      if (w == 0 && (tid & 31) == 0 && ((k + 2) & 31) == 0 && next_join < NW) mbar_arrive(&s_join[next_join++]);
+      if (i <= k + 1 && i < n) {
+        const double2 *pc = sm + (par ? PHB1 : PHB0);
+        const double2 g = sm[RING + 2 * k + 1];
+        const double2 ph_x = pc[k - i];      // (element -1 is zero: row k + 1 starts with x = 0)
+        const double2 ph_m = pc[k + 1 - i];  // (element k + 1 is still zero: phi'[0] = phi[0]; unused in the last step)
+        xx.x = fma(g.y, ph_x.y, fma(g.x, ph_x.x, xx.x));   // x_i += (r_k sigma_k) conj(phi[k - i])
+        xx.y = fma(-g.x, ph_x.y, fma(g.y, ph_x.x, xx.y));
+        own.x = fma(-rho.y, ph_m.y, fma(-rho.x, ph_m.x, own.x));  // phi'[i] = phi[i] - rho conj(phi[k + 1 - i])
+        own.y = fma(rho.x, ph_m.y, fma(-rho.y, ph_m.x, own.y));
+        if (k < n - 1) sm[(par ? PHB0 : PHB1) + i] = own;
+      }
     }
-    named_barrier(2, NTS);  // ends step k - 1 (phi of parity k complete) and opens step k
-    const int par = k & 1;
-    const double2 rho = sm[RING + 2 * k];
-    if (!(rho.x == rho.x)) { fine = false; break; }  // uniform: one queue entry
-    if (row_lo > k + 1) continue;                    // rows not yet reached by the recursion
-    const double2 *pc = sm + (par ? PHB1 : PHB0);
-    double2 *pn_ = sm + (par ? PHB0 : PHB1);
-    const double2 g = sm[RING + 2 * k + 1];
-    const int ic = min(i, n - 1);
-    const double2 ph_x = pc[max(k - ic, 0)];
-    // x_i += (r_k sigma_k) conj(phi[k - i])   (i <= k)
-    const double nx = xx.x + (g.x * ph_x.x + g.y * ph_x.y);
-    const double ny = xx.y + (g.y * ph_x.x - g.x * ph_x.y);
-    xx.x = i <= k ? nx : xx.x;
-    xx.y = i <= k ? ny : xx.y;
-    if (k < n - 1) {
-      // phi'[i] = phi[i] (i <= k) - rho conj(phi[k + 1 - i]) (i >= 1)
-      const double2 ph_i = pc[ic];
-      const double2 ph_m = pc[min(max(k + 1 - ic, 0), n - 1)];
-      const double2 pi_ = i <= k ? ph_i : zero;
-      const double2 pm_ = i >= 1 ? ph_m : zero;
-      double2 np_;
-      np_.x = pi_.x - (rho.x * pm_.x + rho.y * pm_.y);
-      np_.y = pi_.y - (rho.y * pm_.x - rho.x * pm_.y);
-      if (i <= k + 1 && i < n) pn_[i] = np_;
+    if (!fine && w == 0 && (tid & 31) == 0) {  // nobody will reach the sleepers' steps: wake them
+      *(volatile int *)&s_abort = 1;
+      fence_cta();
+      for (; next_join < NW; next_join++) mbar_arrive(&s_join[next_join]);
     }
   }
   if (i < n) s.w_out[i] = fine ? xx : zero;
@@ -1153,7 +1164,7 @@ struct b200dd_wh {
   double2 *d_xd = nullptr, *d_yd = nullptr;  // host path staging (complex128)
   int num_sms = 148;
   bool solve_short = true;  // B200DD_WH_SOLVE_SHORT, read once at create
-  bool solve_split = true;  // B200DD_WH_SOLVE_SPLIT, read once at create
+  bool solve_split = false;  // B200DD_WH_SOLVE_SPLIT, read once at create
   // chunk mode (one CPI split over several GPUs): this handle filters the samples [c0, c0 + nc) of an N-sample signal
   bool chunked = false;
   uint32_t c0 = 0, nc = 0;
