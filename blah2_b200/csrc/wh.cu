@@ -737,24 +737,27 @@ template <int MAXT> __global__ void __launch_bounds__(MAXT, 1) wh_solve_short_ke
   if (tid == 0) *s.status = ok ? 0 : 1;
 }
 
-// ---- split variant (n <= 480 taps: two thread groups of ceil32(n) rows + one warp fit 1024 threads) -----------
+// ---- split variant (n <= 448 taps: two thread groups of ceil32(n) rows + three warps fit 1024 threads) --------
 // In the kernel above every step pays for BOTH recursions although the Levinson accumulation (2) only consumes two
 // numbers per step of the Schur recursion (1): rho_k = b_k / p_k and g_k = r_k sigma_k.  Here they run as a
 // producer and a consumer inside one CTA, each thread group with its own named barriers:
-//   * threads [0, NTS): Schur rows (generator update + forward substitution), threads [NTS, NTS + 32): the pivot
-//     chain; this group never waits for the other.  During step k the pivot warp forms (rho_k, g_k) from the
-//     values published in step k - 1, appends them to a queue in shared memory (one slot per step: no reuse, no
-//     back-pressure) and raises `ready`.  A row warp whose rows are all <= k has nothing left to do and EXITS:
-//     the barrier of step k counts only the warps that ran step k;
-//   * threads [NTS + 32, 2 NTS + 32): Levinson rows.  Their first warp polls `ready`, then the group's barrier
-//     both ends step k - 1 and opens step k.  A warp whose rows are all > k + 1 has nothing to do YET: it sleeps
-//     on an mbarrier that the first warp completes one step before the recursion reaches its first row, and the
+//   * threads [0, NTS): Schur rows (generator update + forward substitution); warp NTS/32: the pivot chain
+//     (state of step k + 1); warp NTS/32 + 1: the queue -- during step k it forms (rho_k, g_k) from the values
+//     published in step k - 1, appends them to a queue in shared memory (one slot per step: no reuse, no
+//     back-pressure) and raises `ready`.  This group never waits for the other.  A row warp whose rows are all
+//     <= k has nothing left to do and EXITS: the barrier of step k counts only the warps that ran step k;
+//   * the next NTS threads: Levinson rows, and one last warp, the gate: it polls `ready`, then the group's barrier
+//     both ends step k - 1 and opens step k.  A row warp whose rows are all > k + 1 has nothing to do YET: it
+//     sleeps on an mbarrier that the gate completes one step before the recursion reaches its first row, and the
 //     barrier counts only the warps that are awake.
-// Both barriers alternate between two hardware ids so that consecutive phases with different counts never meet.
-// The Schur steps are widest (n - k rows) when the Levinson steps are narrowest (k rows) and vice versa: no warp
-// spends instructions on a step it has no rows in, and the elapsed time is about sum_k max(T_schur(k), T_lev(k))
-// instead of the sum of both.  A pivot that is not positive travels down the queue as a NaN rho (a NaN that
-// arises by itself means the same thing).  Same arithmetic per row as the kernels above.
+// Steps are grouped in blocks of 32 (k + 1 in [32 B, 32 B + 32)): inside a block the set of participating warps
+// and therefore the barrier count is fixed, one warp per group is the "boundary" warp that tests its rows against
+// k, the others run unpredicated; the step bodies are instantiated per parity of k so that every ping-pong
+// buffer address is a per-thread constant.  A warp's instruction stream per step is what bounds a step (in-order
+// issue, ~5 clocks per dependent instruction): ~35 (Schur) / ~25 (Levinson) instructions against ~100 in the
+// kernel above.  Both barriers alternate between two hardware ids so that consecutive phases with different
+// counts never meet.  A pivot that is not positive travels down the queue as a NaN rho (a NaN that arises by
+// itself means the same thing).  Same arithmetic per row as the kernels above.
 // Measured history: profiles/r02_summary.md s7.
 __device__ __forceinline__ void named_barrier(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -764,28 +767,119 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tma::smem_u32(bar)) : "memory");
 }
 
+// S = sm + SC: state of parity q at S[4q]: (p s, 1/p), (s, sigma), (p, -); raw b_k / r_k at S[8 + q] / S[10 + q]
+// one Schur row, step k = kk - 1 of parity PAR; returns true when the recursion stops (pivot not positive)
+template <int PAR, bool BOUNDARY>
+__device__ __forceinline__ bool schur_row_step(double2 *S, const double2 *at_p, double2 *an_p, bool live, int i, int kk, int cnt,
+                                               double2 &al, double2 &be, double2 &rr) {
+  const double2 st0 = S[4 * PAR];  // (p s, 1/p)
+  if (live && (!BOUNDARY || i >= kk)) {
+    const double sc = S[4 * PAR + 1].x;
+    const double2 b = S[8 + PAR], r = S[10 + PAR];
+    const double2 at = *at_p;
+    const double ps = st0.x;
+    const double2 bs = make_double2(b.x * sc, b.y * sc);
+    const double2 q = make_double2(r.x * st0.y, r.y * st0.y);  // r_k / p_k
+    double2 na, nb;  // 20 FP64 instructions per row and step, written out as the FMAs they are
+    na.x = fma(ps, at.x, -fma(bs.x, be.x, bs.y * be.y));     // s (p at - conj(b) be)
+    na.y = fma(ps, at.y, -fma(bs.x, be.y, -(bs.y * be.x)));
+    nb.x = fma(ps, be.x, -fma(bs.x, at.x, -(bs.y * at.y)));  // s (p be - b at)
+    nb.y = fma(ps, be.y, -fma(bs.x, at.y, bs.y * at.x));
+    rr.x = fma(al.y, q.y, fma(-al.x, q.x, rr.x));            // r_i -= a_i (r_k / p_k)
+    rr.y = fma(-al.y, q.x, fma(-al.x, q.y, rr.y));
+    *an_p = na;
+    if (i == kk + 1) S[8 + (PAR ^ 1)] = nb;  // b_{k+1}
+    if (i == kk) S[10 + (PAR ^ 1)] = rr;     // r_{k+1}
+    al = na;
+    be = nb;
+  }
+  if (!(st0.x > 0.0)) return true;  // uniform: every thread read the same published pivot (its NaN rho is in the queue)
+  named_barrier(1 + 2 * PAR, cnt);
+  return false;
+}
+
+// the pivot chain: p_{k+1} = s (p^2 - |b|^2) and everything derived from it, for the next step
+template <int PAR> __device__ __forceinline__ bool schur_state_step(double2 *S, bool lane0, int cnt) {
+  const double2 st0 = S[4 * PAR], st1 = S[4 * PAR + 1], b = S[8 + PAR];
+  const double p = S[4 * PAR + 2].x;
+  const double pnew = st0.x * p - ((b.x * st1.x) * b.x + (b.y * st1.x) * b.y);
+  const double inv_pn = rcp_newton(pnew);
+  const double scn = pow2_scale(pnew);
+  const double sign = st1.y * st0.x * p * inv_pn;  // sigma / (1 - |rho|^2)
+  if (lane0) {
+    S[4 * (PAR ^ 1)] = make_double2(pnew * scn, inv_pn);
+    S[4 * (PAR ^ 1) + 1] = make_double2(scn, sign);
+    S[4 * (PAR ^ 1) + 2] = make_double2(pnew, 0.0);
+  }
+  if (!(st0.x > 0.0)) return true;
+  named_barrier(1 + 2 * PAR, cnt);
+  return false;
+}
+
+// the consumer's share of step k: (rho_k, g_k) into the queue slot, then `ready`
+template <int PAR> __device__ __forceinline__ bool schur_queue_step(double2 *S, double2 *slot, volatile int *ready, int k, bool lane0, int cnt) {
+  const double2 st0 = S[4 * PAR], b = S[8 + PAR], r = S[10 + PAR];
+  const double sigma = S[4 * PAR + 1].y;
+  if (lane0) {
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    slot[0] = st0.x > 0.0 ? make_double2(b.x * st0.y, b.y * st0.y) : make_double2(qnan, qnan);  // rho_k
+    slot[1] = make_double2(r.x * sigma, r.y * sigma);                                           // g_k
+    fence_cta();
+    *ready = k + 1;
+  }
+  if (!(st0.x > 0.0)) return true;
+  named_barrier(1 + 2 * PAR, cnt);
+  return false;
+}
+
+// one Levinson row, step k = kk - 1 of parity PAR (phi of parity PAR is read, the other written); px = &phi[k - i] of
+// that parity; returns true on a NaN rho
+template <int PAR, bool BOUNDARY>
+__device__ __forceinline__ bool levinson_row_step(const double2 *slot, const double2 *px, double2 *pn_p, bool live, int i, int kk, int cnt,
+                                                  double2 &xx, double2 &own) {
+  named_barrier(2 + 2 * PAR, cnt);  // ends step k - 1 (phi of parity PAR complete), opens step k
+  const double2 rho = slot[0];
+  if (!(rho.x == rho.x)) return true;  // uniform: one queue entry
+  if (live && (!BOUNDARY || i <= kk)) {
+    const double2 g = slot[1];
+    const double2 ph_x = px[0];  // phi[k - i]      (element -1 is zero: row k + 1 starts with x = 0)
+    const double2 ph_m = px[1];  // phi[k + 1 - i]  (element k + 1 is still zero: phi'[0] = phi[0])
+    xx.x = fma(g.y, ph_x.y, fma(g.x, ph_x.x, xx.x));          // x_i += (r_k sigma_k) conj(phi[k - i])
+    xx.y = fma(-g.x, ph_x.y, fma(g.y, ph_x.x, xx.y));
+    own.x = fma(-rho.y, ph_m.y, fma(-rho.x, ph_m.x, own.x));  // phi'[i] = phi[i] - rho conj(phi[k + 1 - i])
+    own.y = fma(rho.x, ph_m.y, fma(-rho.y, ph_m.x, own.y));
+    *pn_p = own;
+  }
+  return false;
+}
+
 __global__ void __launch_bounds__(1024, 1) wh_solve_split_kernel(SolveArgs s) {
   extern __shared__ __align__(16) double2 sm[];
   const int n = s.nBins;
   const int ALB0 = 0, ALB1 = n;                  // generator a_i, ping-pong (neighbour shift)
   const int PHB0 = 2 * n + 1, PHB1 = 3 * n + 2;  // predictor phi_i, ping-pong (mirrored access); element -1 of each is a zero
   const int RING = 4 * n + 2;                    // queue: rho_k at RING + 2k, g_k at RING + 2k + 1
-  const int SC = 6 * n + 2;                      // state of parity q at SC + 4q: (p s, 1/p), (s, sigma), (p, -); raw b_k / r_k at SC + 8 + q / SC + 10 + q
+  const int SC = 6 * n + 2;                      // step scalars (layout above schur_row_step)
   __shared__ double s_t0;
   __shared__ int s_ready;                        // number of queue entries published
   __shared__ int s_abort;                        // the consumer stopped early: sleeping warps must not start
   __shared__ __align__(8) uint64_t s_join[16];   // wake-up of Levinson warp w
   const int tid = threadIdx.x;
   const int NTS = (n + 31) & ~31, NW = NTS >> 5;
-  const bool schur = tid < NTS, pivot_warp = tid >= NTS && tid < NTS + 32;
-  const int i = schur ? tid : tid - NTS - 32;  // row (both row groups)
-  const int row_lo = i & ~31, row_hi = row_lo + 31;
+  const bool schur = tid < NTS, scalar = tid >= NTS && tid < NTS + 64;
+  const bool state_warp = scalar && tid < NTS + 32, queue_warp = scalar && !state_warp;
+  const int i = schur ? tid : tid - NTS - 64;  // row (both row groups)
+  const int w = i >> 5;                        // row warp
+  const bool lane0 = (tid & 31) == 0;
+  const bool poller = tid >= 2 * NTS + 64;     // last warp: the consumer group's gate
+  const bool live = i < n;
   const double2 zero = make_double2(0.0, 0.0);
-  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  double2 *S = sm + SC;
+  volatile int *ready = &s_ready;
 
   // fixed-order reduction of the per-CTA partial correlations (deterministic): a by the Schur rows, b by the Levinson rows
   double2 sum = zero;
-  if (!pivot_warp && i < n) {
+  if (!scalar && live) {
     const double2 *src = s.partial + i + (schur ? 0 : n);
     int p = 0;
     for (; p + 8 <= s.nPartial; p += 8) {
@@ -814,136 +908,142 @@ __global__ void __launch_bounds__(1024, 1) wh_solve_split_kernel(SolveArgs s) {
   const bool ok = (t0 > 0.0) && isfinite(t0);
   const double inv_t0 = ok ? 1.0 / t0 : 1.0;
   double2 al = zero, be = zero, rr = zero;
-  if (schur && i < n) {
+  if (schur && live) {
     al = make_double2(sum.x * inv_t0, -sum.y * inv_t0);  // a_i^(0) = conj(a[i]) / t_0  (p_0 = 1)
     be = i ? al : zero;
     rr = sm[ALB1 + i];
     sm[ALB0 + i] = al;
     if (i == 0) {
-      sm[SC + 10] = rr;                         // r_0
-      sm[SC + 0] = make_double2(1.0, 1.0);      // (p s, 1/p)
-      sm[SC + 1] = make_double2(1.0, inv_t0);   // (s, sigma_0 = 1 / t_0)
-      sm[SC + 2] = make_double2(1.0, 0.0);      // p_0
-      if (n == 1) sm[SC + 8] = zero;            // (b_0 of a one-tap system: never used)
+      S[10] = rr;                         // r_0
+      S[0] = make_double2(1.0, 1.0);      // (p s, 1/p)
+      S[1] = make_double2(1.0, inv_t0);   // (s, sigma_0 = 1 / t_0)
+      S[2] = make_double2(1.0, 0.0);      // p_0
+      if (n == 1) S[8] = zero;            // (b_0 of a one-tap system: never used)
     }
-    if (i == 1) sm[SC + 8] = be;                // b_0
+    if (i == 1) S[8] = be;                // b_0
   }
-  if (!schur && !pivot_warp && i < n) {
+  if (!schur && !scalar && live) {
     sm[PHB0 + i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // phi^(0) = [1]
     sm[PHB1 + i] = zero;
     if (i == 0) sm[PHB0 - 1] = sm[PHB1 - 1] = zero;
   }
   __syncthreads();
 
-  if (schur || pivot_warp) {
-    // ================= producer: Schur recursion + pivot chain, barriers 1 / 3 =================
-    int k = 0;
+  if (schur || scalar) {
+    // ================= producer: Schur recursion + pivot chain + queue, barriers 1 / 3 =================
+    const double2 *at0 = sm + ALB0 + i - 1, *at1 = sm + ALB1 + i - 1;  // a_{i-1} of the even / odd steps
+    double2 *an0 = sm + ALB1 + i, *an1 = sm + ALB0 + i;                // where the even / odd steps write a_i
+    int kk = 1;                                                         // step k = kk - 1
     if (ok) {
-      for (; k < n - 1; k++) {
-        if (schur && row_hi <= k) return;       // every row of this warp is final
-        const int par = k & 1;
-        const double2 st0 = sm[SC + 4 * par];   // (p s, 1/p)
-        if (pivot_warp) {
-          const double2 st1 = sm[SC + 4 * par + 1];
-          const double2 b = sm[SC + 8 + par], r = sm[SC + 10 + par];
-          const double p = sm[SC + 4 * par + 2].x;
-          // p_{k+1} = s (p^2 - |b|^2) and everything derived from it, for the next step
-          const double pnew = st0.x * p - ((b.x * st1.x) * b.x + (b.y * st1.x) * b.y);
-          const double inv_pn = rcp_newton(pnew);
-          const double scn = pow2_scale(pnew);
-          const double sign = st1.y * st0.x * p * inv_pn;  // sigma / (1 - |rho|^2)
-          if ((tid & 31) == 0) {
-            sm[SC + 4 * (par ^ 1)] = make_double2(pnew * scn, inv_pn);
-            sm[SC + 4 * (par ^ 1) + 1] = make_double2(scn, sign);
-            sm[SC + 4 * (par ^ 1) + 2] = make_double2(pnew, 0.0);
-            // the consumer's share of step k (after the group's own: the fence is off the group's critical path)
-            sm[RING + 2 * k] = st0.x > 0.0 ? make_double2(b.x * st0.y, b.y * st0.y) : make_double2(qnan, qnan);  // rho_k
-            sm[RING + 2 * k + 1] = make_double2(r.x * st1.y, r.y * st1.y);                                        // g_k
-            fence_cta();
-            *(volatile int *)&s_ready = k + 1;
-          }
-        } else if (i > k && i < n) {
-          const double2 *ac = sm + (par ? ALB1 : ALB0);
-          double2 *an = sm + (par ? ALB0 : ALB1);
-          const double2 at = ac[i - 1];
-          const double sc = sm[SC + 4 * par + 1].x;
-          const double2 b = sm[SC + 8 + par], r = sm[SC + 10 + par];
-          const double ps = st0.x;
-          const double2 bs = make_double2(b.x * sc, b.y * sc);
-          const double2 q = make_double2(r.x * st0.y, r.y * st0.y);  // r_k / p_k
-          double2 na, nb;  // 20 FP64 instructions per row and step, written out as the FMAs they are
-          na.x = fma(ps, at.x, -fma(bs.x, be.x, bs.y * be.y));   // s (p at - conj(b) be)
-          na.y = fma(ps, at.y, -fma(bs.x, be.y, -(bs.y * be.x)));
-          nb.x = fma(ps, be.x, -fma(bs.x, at.x, -(bs.y * at.y)));  // s (p be - b at)
-          nb.y = fma(ps, be.y, -fma(bs.x, at.y, bs.y * at.x));
-          rr.x = fma(al.y, q.y, fma(-al.x, q.x, rr.x));           // r_i -= a_i (r_k / p_k)
-          rr.y = fma(-al.y, q.x, fma(-al.x, q.y, rr.y));
-          an[i] = na;
-          if (i == k + 2) sm[SC + 8 + (par ^ 1)] = nb;      // b_{k+1}
-          if (i == k + 1) sm[SC + 10 + (par ^ 1)] = rr;     // r_{k+1}
-          al = na;
-          be = nb;
+      for (int B = 0; 32 * B < n; B++) {       // block B: k + 1 in [32 B, 32 B + 32): the same warps take part in every step
+        if (schur && w < B) return;            // every row of this warp is final
+        const int cnt = 32 * (NW - B + 2);     // row warps B .. NW - 1, the pivot warp, the queue warp
+        const int kk_end = min(32 * B + 32, n);
+        bool stop = false;
+        if (schur && w > B) {
+          for (; kk < kk_end && !stop; kk++)
+            stop = (kk & 1) ? schur_row_step<0, false>(S, at0, an0, live, i, kk, cnt, al, be, rr)
+                            : schur_row_step<1, false>(S, at1, an1, live, i, kk, cnt, al, be, rr);
+        } else if (schur) {
+          for (; kk < kk_end && !stop; kk++)
+            stop = (kk & 1) ? schur_row_step<0, true>(S, at0, an0, live, i, kk, cnt, al, be, rr)
+                            : schur_row_step<1, true>(S, at1, an1, live, i, kk, cnt, al, be, rr);
+        } else if (state_warp) {
+          for (; kk < kk_end && !stop; kk++)
+            stop = (kk & 1) ? schur_state_step<0>(S, lane0, cnt) : schur_state_step<1>(S, lane0, cnt);
+        } else {
+          for (; kk < kk_end && !stop; kk++)
+            stop = (kk & 1) ? schur_queue_step<0>(S, sm + RING + 2 * (kk - 1), ready, kk - 1, lane0, cnt)
+                            : schur_queue_step<1>(S, sm + RING + 2 * (kk - 1), ready, kk - 1, lane0, cnt);
         }
-        if (!(st0.x > 0.0)) break;  // uniform: every thread read the same published pivot (its NaN rho is in the queue)
-        named_barrier(1 + 2 * par, 32 * (NW - ((k + 1) >> 5) + 1));  // the row warps that ran step k + the pivot warp
+        if (stop) return;  // (the queue warp has put the NaN into this step's slot)
       }
     }
-    if (pivot_warp && (tid & 31) == 0) {
-      // the last innovation g_{n-1}, or the verdict on the last pivot / the initial check, closes the queue
-      const int par = k & 1;
-      const double2 st0 = sm[SC + 4 * par], st1 = sm[SC + 4 * par + 1], r = sm[SC + 10 + par];
-      const bool good = ok && k == n - 1 && st0.x > 0.0;
-      if (k == n - 1 || !ok) {  // (a break inside the loop has already queued its NaN at slot k)
-        const int slot = ok ? n - 1 : 0;
-        sm[RING + 2 * slot] = good ? zero : make_double2(qnan, qnan);
-        sm[RING + 2 * slot + 1] = make_double2(r.x * st1.y, r.y * st1.y);
-        fence_cta();
-        *(volatile int *)&s_ready = n;
-      }
+    if (queue_warp && lane0) {
+      // kk == n here (or the initial check failed): the last innovation g_{n-1}, or the verdict on the last pivot /
+      // the initial check, closes the queue
+      const int par = (n - 1) & 1;
+      const double2 st0 = S[4 * par], st1 = S[4 * par + 1], r = S[10 + par];
+      const bool good = ok && st0.x > 0.0;
+      const int slot = ok ? n - 1 : 0;
+      const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+      sm[RING + 2 * slot] = good ? zero : make_double2(qnan, qnan);
+      sm[RING + 2 * slot + 1] = make_double2(r.x * st1.y, r.y * st1.y);
+      fence_cta();
+      *ready = n;
     }
     return;
   }
 
   // ================= consumer: Levinson accumulation, barriers 2 / 4 =================
-  const int w = i >> 5;
+  if (poller) {
+    // the gate: it alone polls the queue; the group's barrier of step k opens when it has seen entry k.  It also wakes
+    // the sleeping row warps (one step before the recursion reaches their first row) and, on a NaN rho, all of them.
+    int kk = 1;  // step k = kk - 1; steps kk < n belong to block kk >> 5 (warps 0 .. kk >> 5 awake), step n is the last x update
+    bool stop = false;
+    for (; kk <= n; kk++) {
+      const int k = kk - 1;
+      while (*ready <= k) {}
+      named_barrier(2 + 2 * (k & 1), kk < n ? 32 * ((kk >> 5) + 2) : 32 * (NW + 1));
+      const double2 rho = sm[RING + 2 * k];
+      if (!(rho.x == rho.x)) { stop = true; break; }
+      if (lane0 && kk < n && (kk & 31) == 31 && (kk >> 5) + 1 < NW) mbar_arrive(&s_join[(kk >> 5) + 1]);
+    }
+    if (stop && lane0) {  // nobody will reach the sleepers' steps: wake them (warps 1 .. kk >> 5 are awake)
+      *(volatile int *)&s_abort = 1;
+      fence_cta();
+      for (int j = (kk >> 5) + 1; j < NW; j++) mbar_arrive(&s_join[j]);
+    }
+    return;
+  }
   double2 xx = zero, own = make_double2(i == 0 ? 1.0 : 0.0, 0.0);  // x_i and this row's phi_i
+  const double2 *pc0 = sm + PHB0, *pc1 = sm + PHB1;                // phi read by the even / odd steps
+  double2 *pn0 = sm + PHB1 + i, *pn1 = sm + PHB0 + i;              // where the even / odd steps write phi'_i
   bool fine = true;
-  int k = 0, next_join = 1;
+  int B = 0;
   if (w > 0) {
     tma::mbar_wait(&s_join[w], 0);            // completed during step 32 w - 2 (or by an abort)
     if (*(volatile int *)&s_abort) fine = false;
-    k = 32 * w - 1;                           // the first step that touches row 32 w
+    B = w;                                    // block w: step 32 w - 1 is the first that touches row 32 w
   }
   if (fine) {
-    for (; k < n; k++) {
-      if (w == 0) {  // the group's first warp waits for the producer
-        while (*(volatile int *)&s_ready <= k) {}
-      }
-      const int par = k & 1;
-      named_barrier(2 + 2 * par, 32 * min(NW, ((k + 1) >> 5) + 1));  // ends step k - 1 (phi of parity k complete), opens step k
-      const double2 rho = sm[RING + 2 * k];
-      if (!(rho.x == rho.x)) { fine = false; break; }  // uniform: one queue entry
-      // the recursion reaches row 32 w' at step 32 w' - 1: wake that warp now, it joins the next barrier
-      if (w == 0 && (tid & 31) == 0 && ((k + 2) & 31) == 0 && next_join < NW) mbar_arrive(&s_join[next_join++]);
-      if (i <= k + 1 && i < n) {
-        const double2 *pc = sm + (par ? PHB1 : PHB0);
-        const double2 g = sm[RING + 2 * k + 1];
-        const double2 ph_x = pc[k - i];      // (element -1 is zero: row k + 1 starts with x = 0)
-        const double2 ph_m = pc[k + 1 - i];  // (element k + 1 is still zero: phi'[0] = phi[0]; unused in the last step)
-        xx.x = fma(g.y, ph_x.y, fma(g.x, ph_x.x, xx.x));   // x_i += (r_k sigma_k) conj(phi[k - i])
-        xx.y = fma(-g.x, ph_x.y, fma(g.y, ph_x.x, xx.y));
-        own.x = fma(-rho.y, ph_m.y, fma(-rho.x, ph_m.x, own.x));  // phi'[i] = phi[i] - rho conj(phi[k + 1 - i])
-        own.y = fma(rho.x, ph_m.y, fma(-rho.y, ph_m.x, own.y));
-        if (k < n - 1) sm[(par ? PHB0 : PHB1) + i] = own;
+    int kk = max(32 * B, 1);                  // step k = kk - 1
+    const double2 *slot = sm + RING + 2 * (kk - 1);                    // queue entry of step k
+    const double2 *px0 = pc0 + (kk - 1 - i), *px1 = pc1 + (kk - 1 - i);  // &phi[k - i] in either buffer
+    for (; 32 * B < n; B++) {
+      const int cnt = 32 * (B + 2);           // warps 0 .. B are awake, and the gate
+      const int kk_end = min(32 * B + 32, n);
+      if (w < B) {
+        for (; kk < kk_end; kk++, slot += 2, px0++, px1++) {
+          if ((kk & 1) ? levinson_row_step<0, false>(slot, px0, pn0, live, i, kk, cnt, xx, own)
+                       : levinson_row_step<1, false>(slot, px1, pn1, live, i, kk, cnt, xx, own)) goto aborted;
+        }
+      } else {
+        for (; kk < kk_end; kk++, slot += 2, px0++, px1++) {
+          if ((kk & 1) ? levinson_row_step<0, true>(slot, px0, pn0, live, i, kk, cnt, xx, own)
+                       : levinson_row_step<1, true>(slot, px1, pn1, live, i, kk, cnt, xx, own)) goto aborted;
+        }
       }
     }
-    if (!fine && w == 0 && (tid & 31) == 0) {  // nobody will reach the sleepers' steps: wake them
-      *(volatile int *)&s_abort = 1;
-      fence_cta();
-      for (; next_join < NW; next_join++) mbar_arrive(&s_join[next_join]);
+    {
+      // last step, k = n - 1: x_i += (r_{n-1} sigma_{n-1}) conj(phi[n - 1 - i]) -- or the verdict on the last pivot
+      const int par = (n - 1) & 1;
+      named_barrier(2 + 2 * par, 32 * (NW + 1));
+      const double2 rho = slot[0];
+      if (!(rho.x == rho.x)) goto aborted;
+      if (live) {
+        const double2 g = slot[1];
+        const double2 ph_x = *(par ? px1 : px0);
+        xx.x = fma(g.y, ph_x.y, fma(g.x, ph_x.x, xx.x));
+        xx.y = fma(-g.x, ph_x.y, fma(g.y, ph_x.x, xx.y));
+      }
     }
   }
-  if (i < n) s.w_out[i] = fine ? xx : zero;
+  if (false) {
+  aborted:
+    fine = false;
+  }
+  if (live) s.w_out[i] = fine ? xx : zero;
   if (i == 0) *s.status = fine ? 0 : 1;
 }
 
@@ -1164,7 +1264,7 @@ struct b200dd_wh {
   double2 *d_xd = nullptr, *d_yd = nullptr;  // host path staging (complex128)
   int num_sms = 148;
   bool solve_short = true;  // B200DD_WH_SOLVE_SHORT, read once at create
-  bool solve_split = false;  // B200DD_WH_SOLVE_SPLIT, read once at create
+  bool solve_split = true;  // B200DD_WH_SOLVE_SPLIT, read once at create
   // chunk mode (one CPI split over several GPUs): this handle filters the samples [c0, c0 + nc) of an N-sample signal
   bool chunked = false;
   uint32_t c0 = 0, nc = 0;
@@ -1256,8 +1356,8 @@ int wh_launch_solve(b200dd_wh *h, cudaStream_t st) {
   sa.partial = h->chunked ? h->d_ab : h->d_partial; sa.nPartial = h->chunked ? 1 : h->gridCorr; sa.nBins = h->nBins;
   sa.a_out = h->d_a; sa.b_out = h->d_b; sa.w_out = h->d_w; sa.status = h->d_status;
   const int threads = ((h->nBins + 31) / 32) * 32;
-  if (h->solve_split && 2 * threads + 32 <= 1024) {  // includes the reference's configuration (410 taps)
-    wh_solve_split_kernel<<<1, 2 * threads + 32, solve_smem, st>>>(sa);
+  if (h->solve_split && 2 * threads + 96 <= 1024) {  // includes the reference's configuration (410 taps)
+    wh_solve_split_kernel<<<1, 2 * threads + 96, solve_smem, st>>>(sa);
   } else if (h->solve_short && threads + 32 <= 1024) {
     if (threads + 32 <= 512) wh_solve_short_kernel<512><<<1, threads + 32, solve_smem, st>>>(sa);
     else wh_solve_short_kernel<1024><<<1, threads + 32, solve_smem, st>>>(sa);

@@ -43,7 +43,7 @@
  *   B200DD_CAF_GROUPS                        warp groups per range CTA, each on its own segments (1..4)
  *   B200DD_CAF_TMA=1                         stage IQ segments through shared memory with bulk async copies
  *   B200DD_WH_LOG2M, B200DD_WH_CORR_LOG2M, B200DD_WH_APPLY_LOG2M   WienerHopf FFT plans
- *   B200DD_WH_SOLVE_SPLIT=0                  one-barrier-per-step Toeplitz solve kernel also for <= 480 taps
+ *   B200DD_WH_SOLVE_SPLIT=0                  one-barrier-per-step Toeplitz solve kernel also for <= 448 taps
  *   B200DD_WH_SOLVE_SHORT=0                  generic Toeplitz solve kernel also for <= 992 taps
  *   B200DD_PIPELINE_GRAPH=1 / 0              CUDA-graph replay of the device chain for every buffer triple / never
  *                                            (default: only triples given to b200dd_pipeline_prepare_device)

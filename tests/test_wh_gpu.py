@@ -140,12 +140,12 @@ def test_every_fft_plan_gives_the_same_filter(log2m, relerr, monkeypatch):
 
 
 @pytest.mark.parametrize("case", [(20011, -10, 40, 2), (200000, -10, 400, 4), (150000, 0, 1, 5), (150000, -3, 30, 6),
-                                  (200000, -10, 470, 7), (200000, -10, 500, 8)])
+                                  (200000, -10, 438, 7), (200000, -10, 500, 8)])
 def test_all_solve_kernels_give_the_same_weights(case, relerr, monkeypatch):
-    """Three kernels run the same Schur + Levinson recursion: the split producer / consumer kernel (default up to 480
+    """Three kernels run the same Schur + Levinson recursion: the split producer / consumer kernel (default up to 448
     taps), the one-barrier-per-step short kernel (B200DD_WH_SOLVE_SPLIT=0; default up to 992 taps) and the generic
     kernel (B200DD_WH_SOLVE_SHORT=0 as well).  Sizes: one tap, one warp, 410 (the reference's), the largest split
-    system (480 taps) and one beyond it (510: falls back to the short kernel)."""
+    system (448 taps) and one beyond it (510: falls back to the short kernel)."""
     n, dm, dM, seed = case
     sc = _scene(n, seed)
     ws = {}
@@ -173,7 +173,7 @@ def _ar_sequence(nb, seed, pole=0.9):
 
 @pytest.mark.parametrize("nb,bad_at", [(1, None), (1, 0), (32, None), (33, None), (33, 1), (33, 20), (64, None), (65, 33),
                                        (410, None), (410, 1), (410, 30), (410, 31), (410, 215), (410, 409),
-                                       (480, None), (480, 479), (496, None), (496, 495), (600, 300)])
+                                       (448, None), (448, 447), (480, None), (480, 479), (496, None), (496, 495), (600, 300)])
 @pytest.mark.parametrize("mode", [("1", "1"), ("0", "1"), ("0", "0")])
 def test_solve_kernels_on_given_toeplitz_systems(nb, bad_at, mode, relerr, monkeypatch):
     """The solve kernels on correlation sums handed in through the chunk API (b200dd_wh_chunk_filter_device): weights
