@@ -54,3 +54,18 @@ def test_cta_fft_dit_core_host_simulation(tmp_path):
                     os.path.join(ROOT, "tests", "native", "fft_dit_sim.cu")], check=True, capture_output=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "FFT_DIT_SIM OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="no nvcc")
+def test_split_toeplitz_solve_host_simulation(tmp_path):
+    """blah2_b200/csrc/solve_steps.cuh (the per-step bodies of wh_solve_split_kernel: Schur row, pivot chain, queue
+    entry, Levinson row) executed on the CPU in the kernel's shared-memory layout and block / boundary-warp
+    structure: weights against a dense long-double Cholesky of the matrix of WienerHopf.cpp:85-97 (1 ... 448 taps)
+    and the 'not positive definite' verdict for a first bad minor at the initial check, early, mid-way, at the last
+    pivots (WienerHopf.cpp:111-117)."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "solve_split_sim")
+    subprocess.run([nvcc, "-std=c++17", "-O1", "-Wno-deprecated-gpu-targets", "-o", exe,
+                    os.path.join(ROOT, "tests", "native", "solve_split_sim.cu")], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "SOLVE_SPLIT_SIM OK" in r.stdout, r.stdout + r.stderr
